@@ -1,0 +1,215 @@
+"""ctypes binding of libdtfill.so (include/dtfill.h) -- the only way Python reaches the CUDA kernels.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is usable, importing the
+library or creating a handle raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtfill.so")
+
+E_ARG, E_CUDA, E_INDEX, E_NOMEM = -1, -2, -3, -4
+METRICS_KITTI, METRICS_NYU = 0, 1
+METRIC_COLS = 9
+METRIC_NAMES = ("mse", "rmse", "mae", "irmse", "imae", "delta1", "delta2", "delta3", "count")
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_lib = None
+_lock = threading.Lock()
+
+
+class DTFillError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libdtfill.so and declare every symbol of include/dtfill.h."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DTFillError(
+                f"{LIB_PATH} is missing: build it with `python -m distancetransform_depthcompletion_b200.build` "
+                "(needs nvcc; there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.dtfill_abi_version.restype = ci
+        L.dtfill_last_error.restype = ctypes.c_char_p
+        L.dtfill_create.argtypes = [ci, ctypes.POINTER(vp)]
+        L.dtfill_destroy.argtypes = [vp]
+        L.dtfill_destroy.restype = None
+        L.dtfill_set_stream.argtypes = [vp, vp]
+        L.dtfill_synchronize.argtypes = [vp]
+        L.dtfill_run.argtypes = [vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, ci, _c_int_p]
+        L.dtfill_run_async.argtypes = [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp]
+        L.dtfill_status.argtypes = [vp, _c_int_p, _c_int_p]
+        L.dtfill_metrics.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
+        L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+        L.dtfill_host_free.argtypes = [vp]
+        L.dtfill_host_free.restype = None
+        for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
+                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc"):
+            getattr(L, name).restype = ci
+        _lib = L
+        return L
+
+
+def last_error() -> str:
+    return load().dtfill_last_error().decode("utf-8", "replace")
+
+
+def _check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == E_INDEX:
+        raise IndexError(msg)
+    if rc == E_ARG:
+        raise ValueError(f"{what}: {msg}")
+    if rc == E_NOMEM:
+        raise MemoryError(f"{what}: {msg}")
+    raise DTFillError(f"{what}: {msg}")
+
+
+def _ptr(a):
+    """Address of a numpy array's buffer, or an int device pointer, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(int(a))
+
+
+class Handle:
+    """One dtfill_t: a CUDA device, a stream and a growing workspace (include/dtfill.h)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load()
+        h = ctypes.c_void_p()
+        _check(self._L.dtfill_create(int(device), ctypes.byref(h)), "dtfill_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dtfill_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(self._L.dtfill_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)), "dtfill_set_stream")
+
+    def synchronize(self):
+        _check(self._L.dtfill_synchronize(self._h), "dtfill_synchronize")
+
+    # ---- host (numpy) path -------------------------------------------------------------------------
+    def run_host(self, frames: np.ndarray, src_thr: float, val_thr: float, want_dt=False, want_lbl=False,
+                 want_mask=False, want_counts=True, out=None):
+        """frames float32 [B,H,W] C-contiguous -> dict of numpy outputs.  Raises IndexError like numpy."""
+        assert frames.dtype == np.float32 and frames.ndim == 3 and frames.flags.c_contiguous
+        B, H, W = frames.shape
+        out = out or {}
+        depth = out.get("depth") if out.get("depth") is not None else np.empty((B, H, W), np.float32)
+        dt = (out.get("dt") if out.get("dt") is not None else np.empty((B, H, W), np.float32)) if want_dt else None
+        lbl = (out.get("lbl") if out.get("lbl") is not None else np.empty((B, H, W), np.int32)) if want_lbl else None
+        mask = (out.get("mask") if out.get("mask") is not None else np.empty((B, H, W), np.uint8)) if want_mask else None
+        counts = np.empty((B, 2), np.int32) if want_counts else None
+        bad = ctypes.c_int(-1)
+        rc = self._L.dtfill_run(self._h, _ptr(frames), 0, B, H, W, float(src_thr), float(val_thr), _ptr(depth),
+                                _ptr(dt), _ptr(lbl), _ptr(mask), _ptr(counts), 0, ctypes.byref(bad))
+        res = dict(depth=depth, dt=dt, lbl=lbl, mask=mask, counts=counts, first_bad=bad.value)
+        if rc == E_INDEX:
+            res["index_error"] = last_error()
+            return res
+        _check(rc, "dtfill_run")
+        return res
+
+    # ---- device path (raw pointers, e.g. torch tensors' data_ptr()) ------------------------------------
+    def run_device_async(self, in_ptr: int, B: int, H: int, W: int, src_thr: float, val_thr: float, depth_ptr: int,
+                         dt_ptr: int | None = None, lbl_ptr: int | None = None, mask_ptr: int | None = None,
+                         counts_ptr: int | None = None):
+        _check(self._L.dtfill_run_async(self._h, _ptr(in_ptr), B, H, W, float(src_thr), float(val_thr), _ptr(depth_ptr),
+                                        _ptr(dt_ptr), _ptr(lbl_ptr), _ptr(mask_ptr), _ptr(counts_ptr)),
+               "dtfill_run_async")
+
+    def status(self):
+        """Synchronise; returns (first_bad_frame or -1, kernel launches of the last run)."""
+        bad, launches = ctypes.c_int(-1), ctypes.c_int(0)
+        rc = self._L.dtfill_status(self._h, ctypes.byref(bad), ctypes.byref(launches))
+        if rc not in (0, E_INDEX):
+            _check(rc, "dtfill_status")
+        return bad.value, launches.value
+
+    def metrics(self, pred, gt, B: int, H: int, W: int, mode: int, gt_is_f64: bool, on_device: bool = False,
+                per_frame_ptr=None, sums_ptr=None):
+        """Host arrays (on_device False) -> (per_frame [B,9], sums [10]) numpy; device pointers otherwise."""
+        if not on_device:
+            per_frame = np.empty((B, METRIC_COLS), np.float64)
+            sums = np.empty(METRIC_COLS + 1, np.float64)
+            _check(self._L.dtfill_metrics(self._h, _ptr(pred), _ptr(gt), int(gt_is_f64), 0, B, H, W, mode,
+                                          _ptr(per_frame), _ptr(sums), 0), "dtfill_metrics")
+            return per_frame, sums
+        _check(self._L.dtfill_metrics(self._h, _ptr(pred), _ptr(gt), int(gt_is_f64), 1, B, H, W, mode,
+                                      _ptr(per_frame_ptr), _ptr(sums_ptr), 1), "dtfill_metrics")
+        return None
+
+
+_handles: dict[int, Handle] = {}
+
+
+def default_device() -> int:
+    for k in ("DTFILL_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(k, "") != "":
+            return int(os.environ[k])
+    return 0
+
+
+def get_handle(device: int | None = None) -> Handle:
+    d = default_device() if device is None else int(device)
+    with _lock:
+        h = _handles.get(d)
+    if h is None:
+        h = Handle(d)
+        with _lock:
+            _handles[d] = h
+    return h
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array backed by page-locked host memory (dtfill_host_alloc): fast host<->device copies."""
+    L = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    _check(L.dtfill_host_alloc(ctypes.byref(p), n), "dtfill_host_alloc")
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                L.dtfill_host_free(self.ptr)
+            except Exception:
+                pass
+
+    _owners[arr.ctypes.data] = _Owner(p)
+    return arr
+
+
+_owners: dict[int, object] = {}

@@ -1,0 +1,360 @@
+// dtfill.cu -- host side of libdtfill.so: handle, workspace, kernel launches and the C ABI of include/dtfill.h.
+#include "dtfill.h"
+
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "dtfill_kernels.cuh"
+
+using namespace dtfill;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(DTFILL_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct dtfill_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // workspace
+    Buf srcbits, valbits, wprefix, rowsrc, rowval, counts, dlist, scratch, tasks, status;
+    Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
+    Buf gt_dev, partial, per_frame, sums;
+    int* status_host = nullptr;   // pinned [2]
+    int last_launches = 0;
+    int last_B = 0;
+};
+
+namespace {
+
+int ensure(dtfill_t* h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(DTFILL_E_NOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return 0;
+}
+
+struct Plan {
+    int ppl = 0;        // 0: wide path only
+    bool pad = false;
+    int wp = 0;         // padded row width of the scratch
+};
+
+Plan make_plan(int H, int W) {
+    Plan p;
+    const int cand[3] = {10, 20, 38};
+    for (int c : cand) {
+        if (W <= 32 * c && 2 * H + W + c + 12 <= 2047) {
+            p.ppl = c;
+            p.pad = (W != 32 * c);
+            p.wp = 32 * c;
+            return p;
+        }
+    }
+    p.ppl = 0;
+    p.wp = W;
+    return p;
+}
+
+template <int PPL>
+void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FrameParams& fp, const Workspace& ws,
+               float* od, float* odt, int32_t* ol) {
+    if (pad) {
+        if (want_lbl) k2_chamfer<PPL, true, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+        else k2_chamfer<PPL, true, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+    } else {
+        if (want_lbl) k2_chamfer<PPL, false, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+        else k2_chamfer<PPL, false, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+    }
+}
+
+// Enqueue the whole path on h->stream; all pointers are device pointers.
+int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
+            float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts) {
+    if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
+    if ((long)H + W >= 60000 || (long)H * W >= (1l << 31) || W > 28000)
+        return fail(DTFILL_E_ARG, "dtfill_run: frame size not supported (H + W < 60000, W <= 28000)");
+    CU(cudaSetDevice(h->device));
+    const Plan plan = make_plan(H, W);
+    const int WW = (W + 31) / 32;
+    const size_t rows = (size_t)B * H;
+    const size_t npx = rows * W;
+
+    int rc;
+    if ((rc = ensure(h, h->srcbits, rows * WW * 4))) return rc;
+    if ((rc = ensure(h, h->valbits, rows * WW * 4))) return rc;
+    if ((rc = ensure(h, h->wprefix, rows * WW * 2))) return rc;
+    if ((rc = ensure(h, h->rowsrc, rows * 4))) return rc;
+    if ((rc = ensure(h, h->rowval, rows * 4))) return rc;
+    if ((rc = ensure(h, h->counts, (size_t)B * 8))) return rc;
+    if ((rc = ensure(h, h->dlist, npx * 4))) return rc;
+    if ((rc = ensure(h, h->scratch, rows * (size_t)(plan.ppl ? plan.wp : W) * 4))) return rc;
+    if ((rc = ensure(h, h->tasks, (size_t)B * sizeof(Task)))) return rc;
+    if ((rc = ensure(h, h->status, 16))) return rc;
+
+    FrameParams fp;
+    fp.B = B; fp.H = H; fp.W = W; fp.WW = WW;
+    fp.src_thr = src_thr; fp.val_thr = val_thr;
+    fp.init_dist = H + W + 8;
+    fp.force_wide = plan.ppl == 0;
+    Workspace ws;
+    ws.srcbits = (uint32_t*)h->srcbits.p; ws.valbits = (uint32_t*)h->valbits.p; ws.wprefix = (uint16_t*)h->wprefix.p;
+    ws.rowsrc = (uint32_t*)h->rowsrc.p; ws.rowval = (uint32_t*)h->rowval.p; ws.counts = (int32_t*)h->counts.p;
+    ws.dlist = (float*)h->dlist.p; ws.scratch = (uint32_t*)h->scratch.p; ws.tasks = (Task*)h->tasks.p;
+    ws.status = (int*)h->status.p;
+
+    cudaStream_t s = h->stream;
+    int launches = 0;
+    h->status_host[0] = INT_MAX;
+    h->status_host[1] = 0;
+    CU(cudaMemcpyAsync(ws.status, h->status_host, 8, cudaMemcpyHostToDevice, s));
+
+    {   // K1: enough warps to keep HBM busy, a whole number of waves of 8-warp blocks
+        long want = ((long)rows + 7) / 8;
+        long cap = (long)h->sm_count * 8 * 4;
+        int grid = (int)(want < cap ? want : cap);
+        k1_mask_rows<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
+        ++launches;
+    }
+    k1b_scan_compact<<<B, 256, 0, s>>>(in, fp, ws, out_counts);
+    ++launches;
+
+    const bool want_lbl = out_lbl != nullptr;
+    switch (plan.ppl) {
+        case 10: launch_k2<10>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        case 20: launch_k2<20>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        case 38: launch_k2<38>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        default: launch_k2<10>(true, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;  // NOSRC frames only
+    }
+    ++launches;
+    {   // wide fallback: returns immediately for every task the fast kernel handled
+        const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            CU(cudaFuncSetAttribute(k2_chamfer_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (smem > 227 * 1024) return fail(DTFILL_E_ARG, "dtfill_run: frame too wide for the wide path");
+        k2_chamfer_wide<<<B, 32, smem, s>>>(fp, ws, out_depth, out_dt, out_lbl);
+        ++launches;
+    }
+    CU(cudaMemcpyAsync(h->status_host, ws.status, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaGetLastError());
+    h->last_launches = launches;
+    h->last_B = B;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dtfill_abi_version(void) { return DTFILL_ABI_VERSION; }
+
+const char* dtfill_last_error(void) { return g_err.c_str(); }
+
+int dtfill_create(int device, dtfill_t** out_handle) {
+    if (!out_handle) return fail(DTFILL_E_ARG, "dtfill_create: NULL out_handle");
+    *out_handle = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(DTFILL_E_CUDA, std::string("dtfill_create: no usable CUDA device (") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                                       "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(DTFILL_E_ARG, "dtfill_create: device index out of range");
+    CU(cudaSetDevice(device));
+    dtfill_t* h = new (std::nothrow) dtfill_ctx();
+    if (!h) return fail(DTFILL_E_NOMEM, "dtfill_create: out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CU(cudaHostAlloc((void**)&h->status_host, 16, cudaHostAllocDefault));
+    h->status_host[0] = INT_MAX;
+    h->status_host[1] = 0;
+    *out_handle = h;
+    return 0;
+}
+
+void dtfill_destroy(dtfill_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    Buf* bufs[] = {&h->srcbits, &h->valbits, &h->wprefix, &h->rowsrc, &h->rowval, &h->counts, &h->dlist,
+                   &h->scratch, &h->tasks, &h->status, &h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev,
+                   &h->mask_dev, &h->counts_out_dev, &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
+    for (Buf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (h->status_host) cudaFreeHost(h->status_host);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int dtfill_set_stream(dtfill_t* h, void* cuda_stream) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return 0;
+}
+
+int dtfill_synchronize(dtfill_t* h) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_synchronize: NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int dtfill_run_async(dtfill_t* h, const float* in_dev, int B, int H, int W, float src_thr, float val_thr,
+                     float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev, uint8_t* out_mask_dev,
+                     int32_t* out_counts_dev) {
+    return enqueue(h, in_dev, B, H, W, src_thr, val_thr, out_depth_dev, out_dt_dev, out_lbl_dev, out_mask_dev,
+                   out_counts_dev);
+}
+
+int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_status: NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    const int bad = h->status_host[0];
+    if (first_bad_frame) *first_bad_frame = (bad == INT_MAX) ? -1 : bad;
+    if (bad != INT_MAX)
+        return fail(DTFILL_E_INDEX, "frame " + std::to_string(bad) +
+                                        ": labels index outside the list of valid depths (numpy IndexError)");
+    return 0;
+}
+
+int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float src_thr, float val_thr,
+               float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts,
+               int out_is_device, int* first_bad_frame) {
+    if (first_bad_frame) *first_bad_frame = -1;
+    if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
+    CU(cudaSetDevice(h->device));
+    const size_t npx = (size_t)B * H * W;
+    int rc;
+    const float* in_d = in;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, h->stream));
+        in_d = (const float*)h->in_dev.p;
+    }
+    float* od = out_depth; float* odt = out_dt; int32_t* ol = out_lbl; uint8_t* om = out_mask; int32_t* oc = out_counts;
+    if (!out_is_device) {
+        if ((rc = ensure(h, h->depth_dev, npx * 4))) return rc;
+        od = (float*)h->depth_dev.p;
+        if (out_dt) { if ((rc = ensure(h, h->dt_dev, npx * 4))) return rc; odt = (float*)h->dt_dev.p; }
+        if (out_lbl) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ol = (int32_t*)h->lbl_dev.p; }
+        if (out_mask) { if ((rc = ensure(h, h->mask_dev, npx))) return rc; om = (uint8_t*)h->mask_dev.p; }
+        if (out_counts) { if ((rc = ensure(h, h->counts_out_dev, (size_t)B * 8))) return rc; oc = (int32_t*)h->counts_out_dev.p; }
+    }
+    if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc))) return rc;
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out_depth, od, npx * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_dt) CU(cudaMemcpyAsync(out_dt, odt, npx * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_lbl) CU(cudaMemcpyAsync(out_lbl, ol, npx * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_mask) CU(cudaMemcpyAsync(out_mask, om, npx, cudaMemcpyDeviceToHost, h->stream));
+        if (out_counts) CU(cudaMemcpyAsync(out_counts, oc, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return dtfill_status(h, first_bad_frame, nullptr);
+}
+
+int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device, int B, int H, int W,
+                   int mode, double* per_frame, double* sums, int out_is_device) {
+    if (!h || !pred || !gt) return fail(DTFILL_E_ARG, "dtfill_metrics: NULL handle or input");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_metrics: B, H, W must be positive");
+    if (mode != DTFILL_METRICS_KITTI && mode != DTFILL_METRICS_NYU) return fail(DTFILL_E_ARG, "dtfill_metrics: bad mode");
+    CU(cudaSetDevice(h->device));
+    const long npx = (long)H * W;
+    const size_t tot = (size_t)B * npx;
+    const size_t gsz = gt_is_f64 ? 8 : 4;
+    int rc;
+    const float* p_d = pred;
+    const void* g_d = gt;
+    cudaStream_t s = h->stream;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, tot * 4))) return rc;
+        if ((rc = ensure(h, h->gt_dev, tot * gsz))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, pred, tot * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->gt_dev.p, gt, tot * gsz, cudaMemcpyHostToDevice, s));
+        p_d = (const float*)h->in_dev.p;
+        g_d = h->gt_dev.p;
+    }
+    int chunks = (int)((npx + 16383) / 16384);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    if ((rc = ensure(h, h->partial, (size_t)B * chunks * ACC * 8))) return rc;
+    if ((rc = ensure(h, h->per_frame, (size_t)B * 9 * 8))) return rc;
+    if ((rc = ensure(h, h->sums, 10 * 8))) return rc;
+    double* pf_d = (out_is_device && per_frame) ? per_frame : (double*)h->per_frame.p;
+    double* sm_d = (out_is_device && sums) ? sums : (double*)h->sums.p;
+    dim3 grid(chunks, B);
+    double* part = (double*)h->partial.p;
+    if (gt_is_f64) {
+        if (mode == 0) k4_metrics_partial<double, 0><<<grid, 256, 0, s>>>(p_d, (const double*)g_d, npx, chunks, part);
+        else k4_metrics_partial<double, 1><<<grid, 256, 0, s>>>(p_d, (const double*)g_d, npx, chunks, part);
+    } else {
+        if (mode == 0) k4_metrics_partial<float, 0><<<grid, 256, 0, s>>>(p_d, (const float*)g_d, npx, chunks, part);
+        else k4_metrics_partial<float, 1><<<grid, 256, 0, s>>>(p_d, (const float*)g_d, npx, chunks, part);
+    }
+    k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, mode, pf_d, sm_d);
+    CU(cudaGetLastError());
+    h->last_launches = 2;
+    if (!out_is_device) {
+        if (per_frame) CU(cudaMemcpyAsync(per_frame, pf_d, (size_t)B * 9 * 8, cudaMemcpyDeviceToHost, s));
+        if (sums) CU(cudaMemcpyAsync(sums, sm_d, 10 * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int dtfill_host_alloc(void** out_ptr, size_t bytes) {
+    if (!out_ptr) return fail(DTFILL_E_ARG, "dtfill_host_alloc: NULL out_ptr");
+    *out_ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(DTFILL_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+void dtfill_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

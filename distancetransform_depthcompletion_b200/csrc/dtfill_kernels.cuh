@@ -1,0 +1,740 @@
+// dtfill_kernels.cuh -- sm_100a kernels of the DT + nearest-neighbour fill path.
+//
+// Pipeline for a batch of frames [B,H,W] float32 (all device resident):
+//   K1  k1_mask_rows      in -> source/valid bit rows, per-word source prefix, row counts, validity mask (u8)
+//                         (reference: value_mask tools.py:8 / eval_NYU.py:115, with_value tools.py:22, net.py:131)
+//   K1b k1b_scan_compact  per frame: exclusive row bases (= raster ranks, OpenCV's label initialisation),
+//                         depth_list = in[valid] in raster order (tools.py:24), task list for K2
+//   K2  k2_chamfer<PPL>   one warp per task: OpenCV's forward/backward 5x5 chamfer scan with label
+//                         propagation (the cv2 call at tools.py:9) restructured as row-sequential,
+//                         lane-parallel (min,+) scans on packed keys kept in registers, fused with the gather
+//                         depth_list[lbl-1] (tools.py:25-27) and the dt / lbl outputs
+//   K2w k2_chamfer_wide   same scan with 64-bit keys and rows in shared memory, for frames the packed 32-bit
+//                         key cannot hold (width > 1216, 2H+W too large, or >= 2^18 sources)
+//   K4  k4_metrics_*      masked RMSE/MAE/iRMSE/iMAE(/REL/delta) reductions of evaluation.py:82-123, 196-239
+//
+// Key format of the fast path: dist:11 | order:3 | label:18.  "order" is the position
+// of a candidate in OpenCV's comparison sequence, so that OpenCV's "first candidate that is strictly smaller
+// wins" is a plain unsigned minimum (one VIADDMNMX per candidate); label is the 1-based raster rank of the
+// source, which is also what cv2 returns with DIST_LABEL_PIXEL.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dtfill {
+
+constexpr int DSH = 21;                       // dist field shift
+constexpr int OSH = 18;                       // order field shift
+constexpr uint32_t LMASK = (1u << OSH) - 1u;  // label field
+constexpr uint32_t ORDCLR = ~(7u << OSH);
+constexpr uint32_t MAX_FAST_LABEL = LMASK;    // frames with more sources take the wide path
+constexpr float UNREACHED_DT = 65533.0f;      // what OpenCV reports where no source is reachable
+
+__host__ __device__ constexpr uint32_t KC(int cost, int order) {
+    return (uint32_t(cost) << DSH) | (uint32_t(order) << OSH);
+}
+
+enum TaskKind : int { TASK_CHAMFER = 0, TASK_NOSRC = 1, TASK_WIDE = 2, TASK_SKIP = 3 };
+
+struct __align__(16) Task {
+    int frame;
+    int lo, hi;        // rows processed as if they were the whole image (band + halo)
+    int r0, r1;        // rows whose results are written (lo <= r0 < r1 <= hi)
+    int kind;
+    int scratch_row;   // first row of this task's forward-state scratch
+    int pad_;
+};
+
+struct FrameParams {
+    int B, H, W, WW;           // WW = 32-bit words per bit row
+    float src_thr, val_thr;
+    int init_dist;             // "unreached" distance of the fast path: H + W + 8
+    int force_wide;            // size not representable in the 32-bit key
+};
+
+struct Workspace {
+    uint32_t* srcbits;   // [B*H*WW]
+    uint32_t* valbits;   // [B*H*WW]
+    uint16_t* wprefix;   // [B*H*WW] sources in the row before this word
+    uint32_t* rowsrc;    // [B*H]  K1: row count, K1b: exclusive base within the frame
+    uint32_t* rowval;    // [B*H]
+    int32_t* counts;     // [B*2]  n_src, n_valid
+    float* dlist;        // [B*H*W] depth_list per frame (first n_valid entries used)
+    uint32_t* scratch;   // forward state, lane-major rows of 32*PPL keys
+    Task* tasks;         // [B * max_tasks_per_frame]
+    int* status;         // [0] first bad frame (INT_MAX if none), [1] number of wide tasks
+};
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1: predicates -> bit rows, counts, validity mask.  One warp per row, 4 words (128 px) per iteration.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                     uint8_t* __restrict__ out_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int W = fp.W, WW = fp.WW;
+    const long nrows = (long)fp.B * fp.H;
+    const bool vec_mask = (W & 3) == 0;
+    for (long row = warp; row < nrows; row += nwarps) {
+        const float* rp = in + row * W;
+        uint32_t cs = 0, cv = 0;
+        for (int w0 = 0; w0 < WW; w0 += 4) {
+            float x[4];
+            bool inb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = (w0 + k) * 32 + lane;
+                inb[k] = col < W;
+                x[k] = inb[k] ? ld_stream(rp + col) : 0.0f;
+            }
+            uint32_t sw[4], vw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = __fsub_rn(1.0f, x[k]);                 // tools.py:8  1.0 - x  (float32)
+                const bool s = inb[k] && !(d > fp.src_thr);           // value_mask == 0  <=> source
+                const bool v = inb[k] && (x[k] > fp.val_thr);         // tools.py:22 with_value
+                sw[k] = __ballot_sync(0xffffffffu, s);
+                vw[k] = __ballot_sync(0xffffffffu, v);
+            }
+            if (lane < 4 && w0 + lane < WW) {
+                const uint32_t s_sel = lane == 0 ? sw[0] : lane == 1 ? sw[1] : lane == 2 ? sw[2] : sw[3];
+                const uint32_t v_sel = lane == 0 ? vw[0] : lane == 1 ? vw[1] : lane == 2 ? vw[2] : vw[3];
+                uint32_t pre = cs;
+                if (lane > 0) pre += __popc(sw[0]);
+                if (lane > 1) pre += __popc(sw[1]);
+                if (lane > 2) pre += __popc(sw[2]);
+                const long wi = row * WW + w0 + lane;
+                ws.srcbits[wi] = s_sel;
+                ws.valbits[wi] = v_sel;
+                ws.wprefix[wi] = (uint16_t)pre;
+            }
+            if (out_mask) {
+                if (vec_mask) {
+                    const int col4 = w0 * 32 + lane * 4;
+                    if (col4 < W) {
+                        const int k = lane >> 3;
+                        const uint32_t word = k == 0 ? vw[0] : k == 1 ? vw[1] : k == 2 ? vw[2] : vw[3];
+                        const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;
+                        st_stream_u32(out_mask + row * W + col4, (nib * 0x00204081u) & 0x01010101u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (inb[k]) out_mask[row * W + (w0 + k) * 32 + lane] = (vw[k] >> lane) & 1u;
+                }
+            }
+            cs += __popc(sw[0]) + __popc(sw[1]) + __popc(sw[2]) + __popc(sw[3]);
+            cv += __popc(vw[0]) + __popc(vw[1]) + __popc(vw[2]) + __popc(vw[3]);
+        }
+        if (lane == 0) {
+            ws.rowsrc[row] = cs;
+            ws.rowval[row] = cv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1b: per frame -- exclusive scans of the row counts, depth_list compaction, task emission.
+// One 256-thread block per frame.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* smem /*[9]*/, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 8; ++i) { const uint32_t t = smem[i]; smem[i] = run; run += t; }
+        smem[8] = run;
+    }
+    __syncthreads();
+    const uint32_t base = smem[wid];
+    total = smem[8];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                         int32_t* __restrict__ out_counts)
+{
+    __shared__ uint32_t sm[9];
+    const int b = blockIdx.x;
+    const int H = fp.H, W = fp.W, WW = fp.WW;
+    const int tid = threadIdx.x;
+    const int per = (H + 255) / 256;
+    const int y0 = min(H, tid * per), y1 = min(H, y0 + per);
+    uint32_t* rs = ws.rowsrc + (long)b * H;
+    uint32_t* rv = ws.rowval + (long)b * H;
+
+    uint32_t ls = 0, lv = 0;
+    for (int y = y0; y < y1; ++y) { ls += rs[y]; lv += rv[y]; }
+    uint32_t nsrc, nval;
+    uint32_t bs = block_exclusive_scan_256(ls, sm, nsrc);
+    uint32_t bv = block_exclusive_scan_256(lv, sm, nval);
+    for (int y = y0; y < y1; ++y) {
+        const uint32_t s = rs[y], v = rv[y];
+        rs[y] = bs; rv[y] = bv;
+        bs += s; bv += v;
+    }
+    __syncthreads();
+
+    // depth_list = in[valid] in raster order (tools.py:24): one warp per non-empty row
+    const int lane = tid & 31, wid = tid >> 5;
+    float* dl = ws.dlist + (long)b * H * W;
+    const uint32_t ltmask = lanemask_lt();
+    for (int y = wid; y < H; y += 8) {
+        const uint32_t base = rv[y];
+        const uint32_t next = (y + 1 < H) ? rv[y + 1] : nval;
+        if (next == base) continue;
+        const long row = (long)b * H + y;
+        uint32_t run = base;
+        for (int w = 0; w < WW; ++w) {
+            const uint32_t vb = ws.valbits[row * WW + w];
+            if (vb == 0) continue;
+            if ((vb >> lane) & 1u) dl[run + __popc(vb & ltmask)] = in[row * W + w * 32 + lane];
+            run += __popc(vb);
+        }
+    }
+
+    if (tid == 0) {
+        ws.counts[2 * b] = (int)nsrc;
+        ws.counts[2 * b + 1] = (int)nval;
+        if (out_counts) { out_counts[2 * b] = (int)nsrc; out_counts[2 * b + 1] = (int)nval; }
+        // numpy's IndexError: empty depth_list, or a label beyond its end (tools.py:26)
+        if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b);
+        Task t;
+        t.frame = b; t.lo = 0; t.hi = H; t.r0 = 0; t.r1 = H; t.scratch_row = b * H; t.pad_ = 0;
+        t.kind = (nsrc == 0) ? TASK_NOSRC : ((fp.force_wide || nsrc > MAX_FAST_LABEL) ? TASK_WIDE : TASK_CHAMFER);
+        if (nval == 0) t.kind = TASK_SKIP;
+        if (t.kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
+        ws.tasks[b] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: the chamfer scan, fast path.  One warp per task; lane l owns columns [l*PPL, (l+1)*PPL) of every row.
+// ------------------------------------------------------------------------------------------------------
+template <int PPL>
+struct Row {
+    uint32_t v[PPL];
+    uint32_t l1, l2;   // columns -1, -2 (previous lane's last two)
+    uint32_t r0, r1;   // columns PPL, PPL+1 (next lane's first two)
+};
+
+template <int PPL>
+__device__ __forceinline__ uint32_t at(const Row<PPL>& r, int idx) {
+    // idx is a compile-time constant after unrolling
+    return idx == -2 ? r.l2 : idx == -1 ? r.l1 : idx == PPL ? r.r0 : idx == PPL + 1 ? r.r1 : r.v[idx < 0 ? 0 : (idx >= PPL ? PPL - 1 : idx)];
+}
+
+template <int PPL>
+__device__ __forceinline__ void fill_row(Row<PPL>& r, uint32_t k) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) r.v[i] = k;
+    r.l1 = r.l2 = r.r0 = r.r1 = k;
+}
+
+template <int PPL>
+__device__ __forceinline__ void refresh_halo(Row<PPL>& r, int lane, uint32_t init_key) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, r.v[PPL - 1], 1);
+    const uint32_t b = __shfl_up_sync(0xffffffffu, r.v[PPL - 2], 1);
+    const uint32_t c = __shfl_down_sync(0xffffffffu, r.v[0], 1);
+    const uint32_t d = __shfl_down_sync(0xffffffffu, r.v[1], 1);
+    r.l1 = lane == 0 ? init_key : a;
+    r.l2 = lane == 0 ? init_key : b;
+    r.r0 = lane == 31 ? init_key : c;
+    r.r1 = lane == 31 ? init_key : d;
+}
+
+// Carry entering this lane from the lanes before it (DIR=+1, forward scan) or after it (DIR=-1, backward
+// scan).  e = this lane's outgoing value (cleared key).  Works in a widened dist:14|label:18 form so that
+// adding up to 31*PPL columns cannot overflow.  Ties keep the nearer lane (OpenCV: the left neighbour is
+// the last candidate compared, so a value already held wins).
+template <int PPL, int DIR>
+__device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t clamp_dist)
+{
+    uint32_t E = ((e >> DSH) << OSH) | (e & LMASK);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, d) : __shfl_down_sync(0xffffffffu, E, d);
+        const uint32_t t = o + (uint32_t(d * PPL) << OSH);
+        E = ((t | LMASK) < E) ? t : E;
+    }
+    const uint32_t cin = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, 1) : __shfl_down_sync(0xffffffffu, E, 1);
+    const uint32_t cd = min(cin >> OSH, clamp_dist);
+    uint32_t key = (cd << DSH) | (1u << OSH) | (cin & LMASK);
+    const bool edge = DIR > 0 ? (lane == 0) : (lane == 31);
+    if (edge) key = (clamp_dist << DSH) | (1u << OSH);
+    return key;
+}
+
+// source bits of this lane's PPL columns (bit i = column x0+i) and the number of sources before x0 in the row
+template <int PPL>
+__device__ __forceinline__ void load_lane_bits(const uint32_t* __restrict__ bits_row, const uint16_t* __restrict__ pre_row,
+                                               int WW, int x0, uint64_t& bits, uint32_t& before)
+{
+    const int w = x0 >> 5, sh = x0 & 31;
+    const uint32_t a = w < WW ? bits_row[w] : 0u;
+    const uint32_t b = w + 1 < WW ? bits_row[w + 1] : 0u;
+    const uint32_t c = (PPL > 33 && w + 2 < WW) ? bits_row[w + 2] : 0u;
+    uint64_t lo = ((uint64_t)b << 32) | a;
+    lo >>= sh;
+    if (PPL > 33 && sh) lo |= (uint64_t)c << (64 - sh);
+    bits = lo & ((PPL >= 64) ? ~0ull : ((1ull << PPL) - 1ull));
+    before = (w < WW ? (uint32_t)pre_row[w] : 0u) + __popc(a & ((1u << sh) - 1u));
+}
+
+template <int PPL, bool PAD, bool WANT_LBL>
+__global__ void __launch_bounds__(32) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+                                                  float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
+{
+    __shared__ __align__(16) uint32_t stage[32 * PPL];
+    const Task task = ws.tasks[blockIdx.x];
+    if (task.kind == TASK_WIDE || task.kind == TASK_SKIP) return;
+    const int lane = threadIdx.x;
+    const int H = fp.H, W = fp.W, WW = fp.WW;
+    const int b = task.frame;
+    const long fpx = (long)b * H * W;
+
+    if (task.kind == TASK_NOSRC) {
+        // no source anywhere: OpenCV leaves dt at 65533 and lbl at 0; depth_list[0-1] is numpy's last element
+        const int nval = ws.counts[2 * b + 1];
+        const float last = ws.dlist[fpx + (nval > 0 ? nval - 1 : 0)];
+        for (long i = (long)task.r0 * W + lane; i < (long)task.r1 * W; i += 32) {
+            out_depth[fpx + i] = last;
+            if (out_dt) out_dt[fpx + i] = UNREACHED_DT;
+            if (WANT_LBL) out_lbl[fpx + i] = 0;
+        }
+        return;
+    }
+
+    const int x0 = lane * PPL;
+    const uint32_t init_key = (uint32_t)fp.init_dist << DSH;
+    const uint32_t clamp_dist = 2047u - PPL - 1u;
+    const uint32_t* bits_f = ws.srcbits + (long)b * H * WW;
+    const uint16_t* pre_f = ws.wprefix + (long)b * H * WW;
+    const uint32_t* rowbase = ws.rowsrc + (long)b * H;
+    uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_row * (16 * PPL);  // PPL/2 uint2 per lane per row
+
+    Row<PPL> ra, rb;
+    fill_row(ra, init_key);
+    fill_row(rb, init_key);
+
+    // ---------------- forward pass: rows lo .. hi-1 ----------------
+    auto fwd_step = [&](const Row<PPL>& A /*row y-1*/, Row<PPL>& Bq /*row y-2 in, row y out*/, int y) {
+        uint64_t bits; uint32_t before;
+        load_lane_bits<PPL>(bits_f + (long)y * WW, pre_f + (long)y * WW, WW, x0, bits, before);
+        uint32_t rank = rowbase[y] + before + 1u;
+        uint32_t c[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t m = at(Bq, i - 1) + KC(3, 0);                       // (-2,-1) cost 3
+            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 1), m);              // (-2,+1) cost 3
+            m = __viaddmin_u32(at(A, i - 2), KC(3, 2), m);               // (-1,-2) cost 3
+            m = __viaddmin_u32(at(A, i - 1), KC(2, 3), m);               // (-1,-1) cost 2
+            m = __viaddmin_u32(at(A, i), KC(1, 4), m);                   // (-1, 0) cost 1
+            m = __viaddmin_u32(at(A, i + 1), KC(2, 5), m);               // (-1,+1) cost 2
+            m = __viaddmin_u32(at(A, i + 2), KC(3, 6), m);               // (-1,+2) cost 3
+            c[i] = m;
+        }
+        if (__any_sync(0xffffffffu, bits != 0ull)) {                      // sources: dist 0, own raster rank
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) {
+                const bool s = (bits >> i) & 1ull;
+                c[i] = s ? rank : c[i];
+                rank += s ? 1u : 0u;
+            }
+        }
+        // in-lane scan: T[x] = min(c[x], T[x-1] + 1); the left neighbour is OpenCV's last candidate (order 7)
+        uint32_t u = c[0] & ORDCLR;
+        c[0] = u;
+#pragma unroll
+        for (int i = 1; i < PPL; ++i) {
+            u = __viaddmin_u32(u, KC(1, 7), c[i]) & ORDCLR;
+            c[i] = u;
+        }
+        const uint32_t cin = lane_carry<PPL, +1>(u, lane, clamp_dist);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t t = __viaddmin_u32(cin, uint32_t(i + 1) << DSH, c[i]) & ORDCLR;
+            if (PAD && x0 + i >= W) t = init_key;
+            Bq.v[i] = t;
+        }
+        refresh_halo(Bq, lane, init_key);
+        uint2* dst = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+#pragma unroll
+        for (int j = 0; j < PPL / 2; ++j) dst[j * 32] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+    };
+
+    for (int y = task.lo; y < task.hi; y += 2) {
+        fwd_step(ra, rb, y);
+        if (y + 1 < task.hi) fwd_step(rb, ra, y + 1);
+    }
+
+    // ---------------- backward pass: rows hi-1 .. r0 ----------------
+    fill_row(ra, init_key);
+    fill_row(rb, init_key);
+    const float* dl = ws.dlist + fpx;
+
+    auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
+        const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+        uint32_t c[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL / 2; ++j) {
+            const uint2 f = src[j * 32];
+            c[2 * j] = f.x; c[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t m = c[i];                                            // own forward value first (order 0)
+            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 1), m);              // (+2,+1)
+            m = __viaddmin_u32(at(Bq, i - 1), KC(3, 2), m);              // (+2,-1)
+            m = __viaddmin_u32(at(A, i + 2), KC(3, 3), m);               // (+1,+2)
+            m = __viaddmin_u32(at(A, i + 1), KC(2, 4), m);               // (+1,+1)
+            m = __viaddmin_u32(at(A, i), KC(1, 5), m);                   // (+1, 0)
+            m = __viaddmin_u32(at(A, i - 1), KC(2, 6), m);               // (+1,-1)
+            m = __viaddmin_u32(at(A, i - 2), KC(3, 7), m);               // (+1,-2)
+            c[i] = m & ORDCLR;
+        }
+        uint32_t u = c[PPL - 1];
+#pragma unroll
+        for (int i = PPL - 2; i >= 0; --i) {
+            u = __viaddmin_u32(u, KC(1, 1), c[i]) & ORDCLR;              // right neighbour is compared last
+            c[i] = u;
+        }
+        const uint32_t cin = lane_carry<PPL, -1>(u, lane, clamp_dist);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t t = __viaddmin_u32(cin, uint32_t(PPL - i) << DSH, c[i]) & ORDCLR;
+            if (PAD && x0 + i >= W) t = init_key;
+            Bq.v[i] = t;
+        }
+        refresh_halo(Bq, lane, init_key);
+
+        if (y >= task.r0 && y < task.r1) {
+            // transpose through shared memory so that global stores are row-contiguous
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < PPL / 2; ++j)
+                *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+            __syncwarp();
+            const long rowpx = fpx + (long)y * W;
+            if ((W & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
+                    const int col = (j * 32 + lane) * 4;
+                    if (col < W) {
+                        const uint4 k = *reinterpret_cast<const uint4*>(&stage[col]);
+                        const float d0 = dl[(k.x & LMASK) - 1u], d1 = dl[(k.y & LMASK) - 1u];
+                        const float d2 = dl[(k.z & LMASK) - 1u], d3 = dl[(k.w & LMASK) - 1u];
+                        st_stream_v4(out_depth + rowpx + col, __float_as_uint(d0), __float_as_uint(d1),
+                                     __float_as_uint(d2), __float_as_uint(d3));
+                        if (out_dt)
+                            st_stream_v4(out_dt + rowpx + col, __float_as_uint((float)(k.x >> DSH)),
+                                         __float_as_uint((float)(k.y >> DSH)), __float_as_uint((float)(k.z >> DSH)),
+                                         __float_as_uint((float)(k.w >> DSH)));
+                        if (WANT_LBL)
+                            st_stream_v4(out_lbl + rowpx + col, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
+                    }
+                }
+            } else {
+                for (int col = lane; col < W; col += 32) {
+                    const uint32_t k = stage[col];
+                    out_depth[rowpx + col] = dl[(k & LMASK) - 1u];
+                    if (out_dt) out_dt[rowpx + col] = (float)(k >> DSH);
+                    if (WANT_LBL) out_lbl[rowpx + col] = (int32_t)(k & LMASK);
+                }
+            }
+        }
+    };
+
+    for (int y = task.hi - 1; y >= task.r0; y -= 2) {
+        bwd_step(ra, rb, y);
+        if (y - 1 >= task.r0) bwd_step(rb, ra, y - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2w: wide fallback.  One warp per frame, 64-bit keys dist:29|order:3|label:32, three row buffers in shared
+// memory.  Forward state: distance plane in ws.scratch (u32 per pixel), label plane parked in out_depth
+// (same size, overwritten row by row with the final depth during the backward pass).
+// ------------------------------------------------------------------------------------------------------
+constexpr int WDSH = 35, WOSH = 32;
+__host__ __device__ constexpr uint64_t WKC(int cost, int order) {
+    return (uint64_t(cost) << WDSH) | (uint64_t(order) << WOSH);
+}
+constexpr uint64_t WORDCLR = ~(7ull << WOSH);
+constexpr uint64_t WLMASK = 0xFFFFFFFFull;
+constexpr uint32_t WINIT = 1u << 27;
+
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+__global__ void __launch_bounds__(32) k2_chamfer_wide(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+                                                       float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
+{
+    extern __shared__ __align__(16) uint64_t wsm[];
+    const Task task = ws.tasks[blockIdx.x];
+    if (task.kind != TASK_WIDE) return;
+    const int lane = threadIdx.x;
+    const int H = fp.H, W = fp.W, WW = fp.WW;
+    const int b = task.frame;
+    const long fpx = (long)b * H * W;
+    const int RW = W + 4;                              // row buffer with 2 INIT columns on each side
+    uint64_t* buf[3] = {wsm, wsm + RW, wsm + 2 * RW};
+    const uint64_t init_key = (uint64_t)WINIT << WDSH;
+    for (int i = lane; i < 3 * RW; i += 32) wsm[i] = init_key;
+    __syncwarp();
+    const int chunk = (W + 31) / 32;
+    const int xa = min(W, lane * chunk), xb = min(W, xa + chunk);
+    const uint32_t* bits_f = ws.srcbits + (long)b * H * WW;
+    const uint16_t* pre_f = ws.wprefix + (long)b * H * WW;
+    const uint32_t* rowbase = ws.rowsrc + (long)b * H;
+    uint32_t* fdist = ws.scratch + fpx;                            // forward distance plane
+    uint32_t* flab = reinterpret_cast<uint32_t*>(out_depth) + fpx;  // forward label plane (temporary)
+    const float* dl = ws.dlist + fpx;
+
+    // cross-lane carry on (dist,label) pairs; DIR>0: from lower lanes, DIR<0: from higher lanes
+    auto carry = [&](uint32_t ed, uint32_t el, bool has, int DIR, uint32_t& cd, uint32_t& cl) {
+        // lanes with an empty chunk contribute "infinite"
+        uint32_t d_ = has ? ed : 0x7FFFFFFFu, l_ = el;
+        // positions: distance between chunk ends of lane a and lane b is |xend_b - xend_a|; use explicit positions
+        int pos = DIR > 0 ? xb - 1 : xa;
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t od = DIR > 0 ? __shfl_up_sync(0xffffffffu, d_, s) : __shfl_down_sync(0xffffffffu, d_, s);
+            const uint32_t ol = DIR > 0 ? __shfl_up_sync(0xffffffffu, l_, s) : __shfl_down_sync(0xffffffffu, l_, s);
+            const int op = DIR > 0 ? __shfl_up_sync(0xffffffffu, pos, s) : __shfl_down_sync(0xffffffffu, pos, s);
+            const bool ok = DIR > 0 ? (lane >= s) : (lane + s < 32);
+            if (ok && od < 0x40000000u) {
+                const uint32_t t = od + (uint32_t)abs(pos - op);
+                if (t < d_) { d_ = t; l_ = ol; }
+            }
+        }
+        // value entering this lane = inclusive value of the neighbouring lane, measured at that lane's end
+        const uint32_t nd = DIR > 0 ? __shfl_up_sync(0xffffffffu, d_, 1) : __shfl_down_sync(0xffffffffu, d_, 1);
+        const uint32_t nl = DIR > 0 ? __shfl_up_sync(0xffffffffu, l_, 1) : __shfl_down_sync(0xffffffffu, l_, 1);
+        const int np = DIR > 0 ? __shfl_up_sync(0xffffffffu, pos, 1) : __shfl_down_sync(0xffffffffu, pos, 1);
+        const bool edge = DIR > 0 ? lane == 0 : lane == 31;
+        if (edge || nd >= 0x40000000u) { cd = 0x7FFFFFFFu; cl = 0; }
+        else { cd = nd; cl = nl; (void)np; }
+    };
+
+    // ---------------- forward ----------------
+    for (int y = 0; y < H; ++y) {
+        uint64_t* A = buf[(y + 2) % 3];   // row y-1
+        uint64_t* Bq = buf[(y + 1) % 3];  // row y-2
+        uint64_t* C = buf[y % 3];         // row y (overwrites row y-3)
+        const uint32_t* br = bits_f + (long)y * WW;
+        const uint16_t* pr = pre_f + (long)y * WW;
+        const uint32_t rb = rowbase[y];
+        uint64_t u = init_key;
+        for (int x = xa; x < xb; ++x) {
+            const int q = x + 2;
+            uint64_t m = Bq[q - 1] + WKC(3, 0);
+            m = umin64(m, Bq[q + 1] + WKC(3, 1));
+            m = umin64(m, A[q - 2] + WKC(3, 2));
+            m = umin64(m, A[q - 1] + WKC(2, 3));
+            m = umin64(m, A[q] + WKC(1, 4));
+            m = umin64(m, A[q + 1] + WKC(2, 5));
+            m = umin64(m, A[q + 2] + WKC(3, 6));
+            const uint32_t word = br[x >> 5];
+            if ((word >> (x & 31)) & 1u)
+                m = (uint64_t)(rb + pr[x >> 5] + __popc(word & ((1u << (x & 31)) - 1u)) + 1u);
+            u = (x == xa) ? (m & WORDCLR) : (umin64(m, u + WKC(1, 7)) & WORDCLR);
+            C[q] = u;
+        }
+        uint32_t cd, cl;
+        carry((uint32_t)(u >> WDSH), (uint32_t)(u & WLMASK), xb > xa, +1, cd, cl);
+        const int endprev = xa - 1;                    // column of the carried value
+        for (int x = xa; x < xb; ++x) {
+            uint64_t t = C[x + 2];
+            if (cd < 0x40000000u) {
+                const uint64_t k = ((uint64_t)(cd + (uint32_t)(x - endprev)) << WDSH) | (1ull << WOSH) | cl;
+                t = umin64(t, k) & WORDCLR;
+            }
+            C[x + 2] = t;
+            const uint32_t d = (uint32_t)(t >> WDSH);
+            fdist[(long)y * W + x] = d;
+            flab[(long)y * W + x] = (uint32_t)(t & WLMASK);
+        }
+        __syncwarp();
+    }
+    // ---------------- backward ----------------
+    for (int i = lane; i < 3 * RW; i += 32) wsm[i] = init_key;
+    __syncwarp();
+    for (int y = H - 1, it = 0; y >= 0; --y, ++it) {
+        uint64_t* A = buf[(it + 2) % 3];   // row y+1
+        uint64_t* Bq = buf[(it + 1) % 3];  // row y+2
+        uint64_t* C = buf[it % 3];
+        uint64_t u = init_key;
+        for (int x = xb - 1; x >= xa; --x) {
+            const int q = x + 2;
+            uint64_t m = ((uint64_t)fdist[(long)y * W + x] << WDSH) | flab[(long)y * W + x];
+            m = umin64(m, Bq[q + 1] + WKC(3, 1));
+            m = umin64(m, Bq[q - 1] + WKC(3, 2));
+            m = umin64(m, A[q + 2] + WKC(3, 3));
+            m = umin64(m, A[q + 1] + WKC(2, 4));
+            m = umin64(m, A[q] + WKC(1, 5));
+            m = umin64(m, A[q - 1] + WKC(2, 6));
+            m = umin64(m, A[q - 2] + WKC(3, 7));
+            m &= WORDCLR;
+            u = (x == xb - 1) ? m : (umin64(m, u + WKC(1, 1)) & WORDCLR);
+            C[q] = u;
+        }
+        uint32_t cd, cl;
+        carry((uint32_t)(u >> WDSH), (uint32_t)(u & WLMASK), xb > xa, -1, cd, cl);
+        const int endnext = xb;
+        for (int x = xa; x < xb; ++x) {
+            uint64_t t = C[x + 2];
+            if (cd < 0x40000000u) {
+                const uint64_t k = ((uint64_t)(cd + (uint32_t)(endnext - x)) << WDSH) | (1ull << WOSH) | cl;
+                t = umin64(t, k) & WORDCLR;
+            }
+            C[x + 2] = t;
+            const uint32_t d = (uint32_t)(t >> WDSH);
+            const uint32_t l = (uint32_t)(t & WLMASK);
+            const long o = fpx + (long)y * W + x;
+            out_depth[o] = dl[l - 1u];
+            if (out_dt) out_dt[o] = (float)d;
+            if (out_lbl) out_lbl[o] = (int32_t)l;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: evaluation metrics (evaluation.py:82-123 Result.evaluate, :196-239 Result_NYU.evaluate)
+// Stage 1: per (frame, chunk) partial sums in double, fixed order.  Stage 2: per-frame metrics + column sums.
+// acc: 0 sum d^2, 1 sum d, 2 sum dinv^2, 3 sum dinv, 4 count, 5 sum d/t, 6..8 delta counts
+// ------------------------------------------------------------------------------------------------------
+constexpr int ACC = 9;
+
+template <typename GT, int MODE>
+__device__ __forceinline__ void metric_accumulate(float o, GT t, double* a)
+{
+    const bool valid = (o > 0.01f) && (t > (GT)0.01);                  // evaluation.py:85-87 / :199-201
+    if (!valid) return;
+    if (MODE == 0) {
+        const float o_mm = 1e3f * o;                                   // :89 float32 product
+        const GT t_mm = (GT)1e3 * t;                                   // :90
+        const GT d = o_mm > t_mm ? (GT)o_mm - t_mm : t_mm - (GT)o_mm;  // :92
+        const GT d2 = d * d;                                           // :94 np.power(.,2)
+        const float io = 1.0f / (1e-3f * o);                           // :116
+        const GT it = (GT)1.0 / ((GT)1e-3 * t);                        // :117
+        const GT di = (GT)io > it ? (GT)io - it : it - (GT)io;         // :118
+        const GT di2 = di * di;
+        a[0] += (double)d2; a[1] += (double)d; a[2] += (double)di2; a[3] += (double)di; a[4] += 1.0;
+    } else {
+        const GT og = (GT)o;
+        const GT d = og > t ? og - t : t - og;                         // :206
+        const GT d2 = d * d;                                           // :208
+        const GT rel = d / t;                                          // :210
+        const GT r1 = og / t, r2 = t / og;                             // :217
+        const GT mr = r1 > r2 ? r1 : r2;
+        const GT io = (GT)1.0 / og, it = (GT)1.0 / t;                  // :232-233
+        const GT di = io > it ? io - it : it - io;
+        const GT di2 = di * di;
+        a[0] += (double)d2; a[1] += (double)d; a[2] += (double)di2; a[3] += (double)di; a[4] += 1.0;
+        a[5] += (double)rel;
+        a[6] += mr < (GT)1.25 ? 1.0 : 0.0;                             // :218
+        a[7] += mr < (GT)1.5625 ? 1.0 : 0.0;                           // :219  1.25**2
+        a[8] += mr < (GT)1.953125 ? 1.0 : 0.0;                         // :220  1.25**3
+    }
+}
+
+template <typename GT, int MODE>
+__global__ void __launch_bounds__(256) k4_metrics_partial(const float* __restrict__ pred, const GT* __restrict__ gt,
+                                                           long npx, int chunks, double* __restrict__ partial)
+{
+    __shared__ double sm[8][ACC];
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const long per = (npx + chunks - 1) / chunks;
+    const long i0 = ch * per, i1 = min(npx, i0 + per);
+    const float* p = pred + (long)b * npx;
+    const GT* g = gt + (long)b * npx;
+    double a[ACC];
+#pragma unroll
+    for (int k = 0; k < ACC; ++k) a[k] = 0.0;
+    for (long i = i0 + threadIdx.x; i < i1; i += 256) metric_accumulate<GT, MODE>(p[i], g[i], a);
+#pragma unroll
+    for (int k = 0; k < ACC; ++k) {
+        double v = a[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        a[k] = v;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < ACC; ++k) sm[wid][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < ACC) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+        partial[((long)b * chunks + ch) * ACC + threadIdx.x] = v;
+    }
+}
+
+// one block; thread t handles frames t, t+blockDim, ...; then a fixed-order column sum
+__global__ void __launch_bounds__(256) k4_metrics_final(const double* __restrict__ partial, int B, int chunks, int mode,
+                                                         double* __restrict__ per_frame /*[B][9]*/,
+                                                         double* __restrict__ sums /*[10]*/)
+{
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double a[ACC];
+        for (int k = 0; k < ACC; ++k) a[k] = 0.0;
+        for (int c = 0; c < chunks; ++c)
+            for (int k = 0; k < ACC; ++k) a[k] += partial[((long)b * chunks + c) * ACC + k];
+        const double n = a[4];
+        double* o = per_frame + (long)b * 9;
+        const double mse = a[0] / n;
+        o[0] = mse;
+        o[1] = sqrt(mse);
+        o[2] = (mode == 0 ? a[1] : a[5]) / n;
+        o[3] = sqrt(a[2] / n);
+        o[4] = a[3] / n;
+        o[5] = mode == 0 ? 0.0 : a[6] / n;
+        o[6] = mode == 0 ? 0.0 : a[7] / n;
+        o[7] = mode == 0 ? 0.0 : a[8] / n;
+        o[8] = n;
+    }
+    __syncthreads();
+    if (sums && threadIdx.x < 10) {
+        double s = 0.0;
+        if (threadIdx.x < 9)
+            for (int b = 0; b < B; ++b) s += per_frame[(long)b * 9 + threadIdx.x];
+        else
+            s = (double)B;
+        sums[threadIdx.x] = s;
+    }
+}
+
+}  // namespace dtfill

@@ -1,0 +1,57 @@
+"""Device-resident form of the path for callers that already hold their frames in HBM (torch tensors).
+
+PyTorch is used here only for device memory and streams; every kernel is ours (libdtfill.so).
+"""
+from __future__ import annotations
+
+from . import _lib
+
+
+class DTFillEngine:
+    """Runs DT + NN fill (+ metrics) on torch CUDA tensors, on torch's current stream, without host copies."""
+
+    def __init__(self, device: int | None = None):
+        import torch
+        self.torch = torch
+        self.device = _lib.default_device() if device is None else int(device)
+        self.handle = _lib.Handle(self.device)
+
+    def _bind_stream(self):
+        self.handle.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def fill(self, frames, src_thr: float = 0.1, val_thr: float = 0.1, want_lbl: bool = False, out=None):
+        """frames: float32 CUDA tensor [B,H,W] (contiguous).  Returns dict of CUDA tensors, enqueued only."""
+        torch = self.torch
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 3
+        B, H, W = frames.shape
+        out = out or {}
+        dev = frames.device
+        depth = out.get("depth") if out.get("depth") is not None else torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        dt = out.get("dt") if out.get("dt") is not None else torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        mask = out.get("mask") if out.get("mask") is not None else torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        lbl = None
+        if want_lbl:
+            lbl = out.get("lbl") if out.get("lbl") is not None else torch.empty((B, H, W), dtype=torch.int32, device=dev)
+        counts = out.get("counts") if out.get("counts") is not None else torch.empty((B, 2), dtype=torch.int32, device=dev)
+        self._bind_stream()
+        self.handle.run_device_async(frames.data_ptr(), B, H, W, src_thr, val_thr, depth.data_ptr(), dt.data_ptr(),
+                                     lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
+        return dict(depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
+
+    def status(self):
+        """Synchronise; (first_bad_frame or -1, kernel launches of the last fill)."""
+        return self.handle.status()
+
+    def metrics(self, pred, gt, mode: int = _lib.METRICS_KITTI):
+        """pred float32 [B,H,W], gt float32/float64 [B,H,W] CUDA tensors -> (per_frame [B,9], sums [10]) CUDA f64."""
+        torch = self.torch
+        assert pred.is_cuda and gt.is_cuda and pred.is_contiguous() and gt.is_contiguous() and pred.shape == gt.shape
+        assert pred.dtype == torch.float32 and gt.dtype in (torch.float32, torch.float64)
+        B = pred.shape[0]
+        n = pred[0].numel()
+        per_frame = torch.empty((B, _lib.METRIC_COLS), dtype=torch.float64, device=pred.device)
+        sums = torch.empty((_lib.METRIC_COLS + 1,), dtype=torch.float64, device=pred.device)
+        self._bind_stream()
+        self.handle.metrics(pred.data_ptr(), gt.data_ptr(), B, 1, n, mode, gt.dtype == torch.float64, on_device=True,
+                            per_frame_ptr=per_frame.data_ptr(), sums_ptr=sums.data_ptr())
+        return per_frame, sums

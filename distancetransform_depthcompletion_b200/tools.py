@@ -1,0 +1,68 @@
+"""Drop-in for the reference's solution_DeepNet/tools.py (same names, arguments, shapes, dtypes, exceptions),
+backed by the sm_100a kernels behind libdtfill.so.  numpy in, numpy out.
+
+    nearest_point(refined_lidar)      -> (dt float32 [H,W], lbl int32 [H,W])      tools.py:7-10
+    DT_complete_batch(lidar_batch)    -> float32 [B,352,1216,1]                     tools.py:13-35
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+KITTI_SRC_THR = 0.1     # tools.py:8   value_mask = 1.0 - x > 0.1
+VALID_THR = 0.1         # tools.py:22  with_value = x > 0.1
+_H, _W = 352, 1216      # tools.py:25,27 hard-coded frame size
+
+
+def _as_frames_f32(a: np.ndarray, what: str) -> np.ndarray:
+    if a.dtype != np.float32:
+        if a.dtype == np.float64 or a.dtype == np.float16 or np.issubdtype(a.dtype, np.integer):
+            raise TypeError(f"{what}: dtype {a.dtype} is not supported by the CUDA path (float32 only; every "
+                            "in-tree producer of the reference yields float32, data_read.py:215,371)")
+        raise TypeError(f"{what}: unsupported dtype {a.dtype}")
+    return np.ascontiguousarray(a)
+
+
+def nearest_point(refined_lidar, thr: float = KITTI_SRC_THR, device: int | None = None):
+    """tools.py:7-10.  ``thr`` is the literal 0.1 of tools.py:8 (eval_NYU.py:115 uses 0.001)."""
+    x = np.squeeze(np.asarray(refined_lidar))
+    if x.ndim != 2:
+        # cv2.distanceTransformWithLabels accepts only a single-channel 2-D image
+        raise ValueError(f"nearest_point: input must squeeze to 2-D, got shape {np.shape(refined_lidar)}")
+    x = _as_frames_f32(x, "nearest_point")
+    r = _lib.get_handle(device).run_host(x[None], thr, VALID_THR, want_dt=True, want_lbl=True, want_counts=False)
+    return r["dt"][0], r["lbl"][0]
+
+
+def DT_complete_batch(lidar_batch, device: int | None = None):
+    """tools.py:13-35: per frame, fill every pixel with the depth of its chamfer-nearest source."""
+    lidar_batch = np.asarray(lidar_batch)
+    if lidar_batch.ndim != 4:
+        raise IndexError(f"DT_complete_batch: expected [B,H,W,C], got shape {lidar_batch.shape}")   # tools.py:19
+    B, H, W, _ = lidar_batch.shape
+    if B == 0:
+        return np.expand_dims(np.asarray([]), axis=-1).astype(np.float32)                           # tools.py:30-33
+    if H * W != _H * _W:
+        raise ValueError(f"cannot reshape array of size {H * W} into shape ({_H},{_W})")            # tools.py:25-27
+    if min(H, W) < 2:
+        raise ValueError("DT_complete_batch: frames must be 2-D after squeeze")
+    frames = _as_frames_f32(lidar_batch[:, :, :, 0], "DT_complete_batch")                           # tools.py:19
+    r = _lib.get_handle(device).run_host(frames, KITTI_SRC_THR, VALID_THR)
+    if "index_error" in r:
+        raise IndexError(r["index_error"])                                                          # tools.py:26
+    return r["depth"].reshape(B, _H, _W, 1)                                                         # tools.py:27-33
+
+
+def dt_fill_batch(frames, src_thr: float = KITTI_SRC_THR, val_thr: float = VALID_THR, want_lbl: bool = False,
+                  device: int | None = None, out=None):
+    """All outputs of the path for frames float32 [B,H,W]: filled depth, distance channel, validity
+    (DT-pooling, net.py:131-132) mask, optional label map, per-frame (n_sources, n_valid)."""
+    frames = _as_frames_f32(np.asarray(frames), "dt_fill_batch")
+    if frames.ndim != 3:
+        raise ValueError("dt_fill_batch: expected [B,H,W]")
+    r = _lib.get_handle(device).run_host(frames, src_thr, val_thr, want_dt=True, want_lbl=want_lbl, want_mask=True,
+                                         out=out)
+    if "index_error" in r:
+        raise IndexError(r["index_error"])
+    return r

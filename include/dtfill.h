@@ -1,0 +1,125 @@
+/*
+ * dtfill.h -- C ABI of libdtfill.so: the B200 (sm_100a) implementation of the reference's
+ * "distance transform + nearest-neighbour fill" preprocessing path and of its evaluation metrics.
+ *
+ * The reference (placeforyiming/DistanceTransform-DepthCompletion) has no FFI layer: the boundary is the
+ * Python function signature (numpy in, numpy out).  Each entry point below names the reference interface it
+ * stands behind (file:line relative to the reference checkout); the ctypes binding a maintainer adds to the
+ * reference is shown in INTEGRATION.md and shipped as distancetransform_depthcompletion_b200/_lib.py.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative DTFILL_E_*
+ * code, with a human-readable message available from dtfill_last_error() (thread local).  No C++ exception
+ * crosses the ABI.  A handle owns one CUDA device, one stream (its own, or one lent by the caller) and a
+ * workspace that grows on demand; a handle is used from one host thread at a time.  Buffers named in/out
+ * are owned by the caller.  "is_device" flags say whether a pointer is a device pointer on the handle's
+ * device (used as is) or a host pointer (copied with cudaMemcpyAsync on the handle's stream; pinned host
+ * memory makes that copy fast, see dtfill_host_alloc).  There is no CPU fallback: without a usable CUDA
+ * device dtfill_create fails.
+ */
+#ifndef DTFILL_H_
+#define DTFILL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTFILL_ABI_VERSION 1
+
+enum {
+    DTFILL_OK = 0,
+    DTFILL_E_ARG = -1,        /* bad argument (NULL pointer, non-positive size, unsupported size)            */
+    DTFILL_E_CUDA = -2,       /* a CUDA runtime call failed; message has the CUDA error string               */
+    DTFILL_E_INDEX = -3,      /* numpy's IndexError: a frame's labels index outside its list of valid depths */
+    DTFILL_E_NOMEM = -4
+};
+
+enum { DTFILL_METRICS_KITTI = 0, DTFILL_METRICS_NYU = 1 };
+
+/* Number of doubles per frame written by dtfill_metrics (and length of the `sums` vector minus one). */
+#define DTFILL_METRIC_COLS 9   /* mse, rmse, mae, irmse, imae, delta1, delta2, delta3, valid_count */
+
+typedef struct dtfill_ctx dtfill_t;
+
+/* Create / destroy a handle bound to CUDA device `device`. */
+int  dtfill_create(int device, dtfill_t** out_handle);
+void dtfill_destroy(dtfill_t* h);
+
+/* Run all device work of this handle on `cuda_stream` (a cudaStream_t) instead of the handle's own
+ * stream; NULL restores the handle's stream.  Used to interoperate with torch.cuda streams. */
+int  dtfill_set_stream(dtfill_t* h, void* cuda_stream);
+
+/* Block until everything queued on the handle's stream has finished. */
+int  dtfill_synchronize(dtfill_t* h);
+
+/*
+ * The hot path.  For every frame b of `in` (float32 [B,H,W], dense, channel 0 already selected):
+ *
+ *   source(p)   = !( (float)(1.0f - in[p]) > src_thr )      value_mask of nearest_point,
+ *                                                            solution_DeepNet/tools.py:8 (src_thr 0.1),
+ *                                                            solution_DeepNet/eval_NYU.py:115 (src_thr 0.001)
+ *   (dt, lbl)   = cv2.distanceTransformWithLabels(mask, DIST_L1, 5, DIST_LABEL_PIXEL)
+ *                                                            tools.py:9, eval_NYU.py:116, demo.py:80 --
+ *                 bit-exact, including which of several equidistant sources wins (OpenCV scan order)
+ *   valid(p)    = in[p] > val_thr                            tools.py:22, eval_NYU.py:124, net.py:131-132
+ *   depth_list  = in[valid] in raster order                  tools.py:24, eval_NYU.py:126
+ *   out_depth   = depth_list[lbl - 1]  (numpy indexing, -1 = last element)   tools.py:25-27, eval_NYU.py:128-131
+ *
+ * Outputs (each may be NULL to skip it, except out_depth):
+ *   out_depth float32 [B,H,W]   the filled depth  (return value of DT_complete_batch tools.py:13-35 and of
+ *                               Distance_Transform eval_NYU.py:120-133)
+ *   out_dt    float32 [B,H,W]   the distance channel (first return value of nearest_point tools.py:10);
+ *                               65533.0 where no source is reachable, like OpenCV
+ *   out_lbl   int32   [B,H,W]   the label map (second return value of nearest_point)
+ *   out_mask  uint8   [B,H,W]   validity ("DT-pooling") mask in[p] > val_thr (net.py:131-132), 0/1
+ *   out_counts int32  [B,2]     per frame: number of sources, number of valid pixels (host pointer when
+ *                               out_is_device == 0, device pointer otherwise; may be NULL)
+ *
+ * dtfill_run waits for completion.  If some frame's labels index outside its depth_list (no valid pixel at
+ * all, or more sources than valid pixels) the reference raises IndexError: the call returns DTFILL_E_INDEX and
+ * stores the first such frame in *first_bad_frame (other frames' outputs are still written).
+ * dtfill_run_async only enqueues on the handle's stream (device pointers only); call dtfill_status afterwards.
+ */
+int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W,
+               float src_thr, float val_thr,
+               float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts,
+               int out_is_device, int* first_bad_frame);
+
+int dtfill_run_async(dtfill_t* h, const float* in_dev, int B, int H, int W, float src_thr, float val_thr,
+                     float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev, uint8_t* out_mask_dev,
+                     int32_t* out_counts_dev);
+
+/* Synchronise and report the outcome of the last dtfill_run_async: DTFILL_OK or DTFILL_E_INDEX
+ * (with *first_bad_frame set).  *kernel_launches receives the number of kernels launched by that call. */
+int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
+
+/*
+ * Evaluation metrics of evaluation.py for B frame pairs:
+ *   mode DTFILL_METRICS_KITTI  Result.evaluate      evaluation.py:82-123  (metres -> mm, 1/km)
+ *   mode DTFILL_METRICS_NYU    Result_NYU.evaluate  evaluation.py:196-239 (no scaling, REL, delta1..3)
+ * pred float32 [B,H,W]; gt float64 (gt_is_f64 != 0, data_read.py:223) or float32 [B,H,W].
+ * per_frame (nullable) double [B][DTFILL_METRIC_COLS] = mse, rmse, mae, irmse, imae, delta1, delta2, delta3,
+ * valid_count (delta* are 0 in KITTI mode).  sums (nullable) double [DTFILL_METRIC_COLS + 1] = column sums of
+ * per_frame over the B frames followed by B -- the running totals eval.py:212-232 / eval_NYU.py:207-229 keep
+ * (mean of per-frame metrics).  Both are host pointers unless out_is_device; the call waits for completion
+ * when they are host pointers.
+ */
+int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
+                   int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
+
+/* Pinned host memory for fast host<->device copies (cudaHostAlloc / cudaFreeHost). */
+int  dtfill_host_alloc(void** out_ptr, size_t bytes);
+void dtfill_host_free(void* ptr);
+
+/* Message describing the last error on this thread ("" if none). */
+const char* dtfill_last_error(void);
+
+/* DTFILL_ABI_VERSION the library was built with. */
+int dtfill_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTFILL_H_ */

@@ -1,0 +1,143 @@
+"""numpy model of the arithmetic the sm_100a chamfer kernel performs (csrc/dtfill_kernels.cu) -- TEST CODE.
+
+It mirrors, lane for lane, what one warp does for one task (a band of rows of one frame): packed 32-bit
+keys ``dist:11 | order:3 | label:18``, the 7-candidate stencil as unsigned minima, the in-lane sequential
+(min,+) scan, the cross-lane Hillis-Steele carry in a widened ``dist:14 | label:18`` form, and the carry
+application.  tests/test_kernel_model.py checks it against the oracle; it exists so the kernel's packing,
+tie-breaking and band/halo logic are verified on the CPU before a GPU is involved.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DSH, OSH = 21, 18
+LMASK = np.uint64((1 << 18) - 1)
+ORDMASK = np.uint64(7 << 18)
+KEYMASK = np.uint64(0xFFFFFFFF)
+D1 = np.uint64(1 << DSH)
+
+
+def _clr(k):
+    return k & ~ORDMASK & KEYMASK
+
+
+def _add(k, cost, order):
+    r = k + np.uint64((cost << DSH) | (order << OSH))
+    assert (r >> np.uint64(32)).max() == 0, "dist field overflowed 11 bits"
+    return r
+
+
+# (dy, dx, cost) in OpenCV's comparison order
+FWD = [(-2, -1, 3), (-2, +1, 3), (-1, -2, 3), (-1, -1, 2), (-1, 0, 1), (-1, +1, 2), (-1, +2, 3)]
+BWD = [(+2, +1, 3), (+2, -1, 3), (+1, +2, 3), (+1, +1, 2), (+1, 0, 1), (+1, -1, 2), (+1, -2, 3)]
+
+
+def _row_scan(c, ppl, order_scan, reverse, init_key, clamp_dist):
+    """c: uint64 [32*ppl] stencil results (order bits may be set).  Returns final cleared row."""
+    lanes = 32
+    v = c.reshape(lanes, ppl).copy()
+    if reverse:
+        v = v[::-1, ::-1].copy()            # mirror so the scan always runs towards higher index
+    U = np.empty_like(v)
+    U[:, 0] = _clr(v[:, 0])
+    step = np.uint64((1 << DSH) | (order_scan << OSH))
+    for i in range(1, ppl):
+        U[:, i] = _clr(np.minimum(v[:, i], U[:, i - 1] + step))
+    # cross-lane carry in the widened form dist:14 | label:18
+    e = U[:, ppl - 1]
+    E = ((e >> np.uint64(DSH)) << np.uint64(18)) | (e & LMASK)
+    d = 1
+    while d < lanes:
+        other = E.copy()
+        other[d:] = E[:-d]                  # shfl_up: lanes < d keep their own value
+        t = other + np.uint64((d * ppl) << 18)
+        take = (t | LMASK) < E
+        E = np.where(take, t, E)
+        d *= 2
+    cin = np.empty_like(E)
+    cin[1:] = E[:-1]
+    cin[0] = (np.uint64(clamp_dist) << np.uint64(18))
+    cd = np.minimum(cin >> np.uint64(18), np.uint64(clamp_dist))
+    cin_key = (cd << np.uint64(DSH)) | np.uint64(1 << OSH) | (cin & LMASK)
+    cin_key[0] = (np.uint64(clamp_dist) << np.uint64(DSH)) | np.uint64(1 << OSH)
+    out = np.empty_like(U)
+    for i in range(ppl):
+        t = cin_key + np.uint64((i + 1) << DSH)
+        assert (t >> np.uint64(32)).max() == 0
+        out[:, i] = _clr(np.minimum(U[:, i], t))
+    if reverse:
+        out = out[::-1, ::-1]
+    return out.reshape(-1).copy()
+
+
+def chamfer_band(src: np.ndarray, rank: np.ndarray, lo: int, hi: int, ppl: int):
+    """src bool [H,W] source map, rank int [H,W] (1-based raster rank of sources), rows [lo,hi) processed
+    as if they were the whole image.  Returns (dist [hi-lo,W], label [hi-lo,W])."""
+    H, W = src.shape
+    Wp = 32 * ppl
+    assert W <= Wp
+    init = H + W + 8
+    assert 2 * H + W + ppl + 12 <= 2047 and int(rank.max()) < (1 << 18)
+    clamp = 2047 - ppl - 1
+    INIT = np.uint64(init << DSH)
+    n = hi - lo
+    pad = np.zeros((n, Wp), bool); pad[:, :W] = src[lo:hi]
+    rk = np.zeros((n, Wp), np.uint64); rk[:, :W] = rank[lo:hi]
+    colpad = np.arange(Wp) >= W
+
+    def shifted(row, dx):
+        ext = np.concatenate([np.full(2, INIT, np.uint64), row, np.full(2, INIT, np.uint64)])
+        return ext[2 + dx: 2 + dx + Wp]
+
+    F = np.empty((n, Wp), np.uint64)
+    A = np.full(Wp, INIT, np.uint64); Bp = A.copy()          # rows y-1 and y-2
+    for y in range(n):
+        c = None
+        for o, (dy, dx, cost) in enumerate(FWD):
+            cand = _add(shifted(A if dy == -1 else Bp, dx), cost, o)
+            c = cand if c is None else np.minimum(c, cand)
+        c = np.where(pad[y], rk[y], c)
+        row = _row_scan(c, ppl, 7, False, INIT, clamp)
+        row = np.where(colpad, INIT, row)
+        F[y] = row
+        Bp, A = A, row
+    R = np.empty((n, Wp), np.uint64)
+    A = np.full(Wp, INIT, np.uint64); Bp = A.copy()          # rows y+1 and y+2
+    for y in range(n - 1, -1, -1):
+        c = F[y].copy()
+        for o, (dy, dx, cost) in enumerate(BWD):
+            cand = _add(shifted(A if dy == 1 else Bp, dx), cost, o + 1)
+            c = np.minimum(c, cand)
+        c = _clr(c)
+        row = _row_scan(c, ppl, 1, True, INIT, clamp)
+        row = np.where(colpad, INIT, row)
+        R[y] = row
+        Bp, A = A, row
+    dist = (R >> np.uint64(DSH)).astype(np.int64)[:, :W]
+    label = (R & LMASK).astype(np.int64)[:, :W]
+    dist = np.where(dist >= init, 65533, dist)
+    return dist, label
+
+
+# ---- coarse planning bound (guaranteed upper bound on the row maximum of dt) --------------------------------
+def coarse_row_bound(src: np.ndarray, ch: int, cw: int) -> np.ndarray:
+    """Upper bound U[y] >= max_x dt(y,x) from a CH x CW cell-occupancy grid: an exact anisotropic city-block
+    distance on the cell grid (vertical step ch, horizontal step cw) plus the in-cell slack."""
+    H, W = src.shape
+    nh, nw = -(-H // ch), -(-W // cw)
+    occ = np.zeros((nh, nw), bool)
+    for cy in range(nh):
+        for cx in range(nw):
+            occ[cy, cx] = src[cy * ch:(cy + 1) * ch, cx * cw:(cx + 1) * cw].any()
+    BIG = 1 << 20
+    D = np.where(occ, 0, BIG).astype(np.int64)
+    for cy in range(nh):
+        for cx in range(nw):
+            if cy: D[cy, cx] = min(D[cy, cx], D[cy - 1, cx] + ch)
+            if cx: D[cy, cx] = min(D[cy, cx], D[cy, cx - 1] + cw)
+    for cy in range(nh - 1, -1, -1):
+        for cx in range(nw - 1, -1, -1):
+            if cy < nh - 1: D[cy, cx] = min(D[cy, cx], D[cy + 1, cx] + ch)
+            if cx < nw - 1: D[cy, cx] = min(D[cy, cx], D[cy, cx + 1] + cw)
+    cellmax = D.max(axis=1) + (ch - 1) + (cw - 1)
+    return np.repeat(cellmax, ch)[:H]

@@ -1,0 +1,244 @@
+"""Parity of the CUDA path (through the C ABI / ctypes shim) with the oracle and the committed reference
+outputs.  Bit-exact for dt, lbl, mask and the filled depth (a copy of input values); metrics within the stated
+relative tolerance.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from distancetransform_depthcompletion_b200 import _lib, eval_nyu, evaluation, synth, tools
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+METRIC_RTOL_F64 = 1e-9     # float64 ground truth: both sides accumulate in float64, only the order differs
+METRIC_RTOL_F32 = 2e-5     # float32 ground truth: numpy's mean itself accumulates in float32 (pairwise)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def handle(dtfill_lib):
+    return _lib.get_handle()
+
+
+def _check_frames(handle, frames, src_thr, val_thr):
+    frames = np.ascontiguousarray(frames, np.float32)
+    r = handle.run_host(frames, src_thr, val_thr, want_dt=True, want_lbl=True, want_mask=True)
+    assert "index_error" not in r, r.get("index_error")
+    o = O.dt_fill(frames, src_thr, val_thr)
+    for b in range(frames.shape[0]):
+        assert np.array_equal(r["lbl"][b], o["lbl"][b]), f"lbl frame {b}"
+        assert np.array_equal(r["dt"][b], o["dt"][b]), f"dt frame {b}"
+        assert np.array_equal(r["mask"][b], o["mask"][b]), f"mask frame {b}"
+        assert np.array_equal(r["depth"][b].view(np.uint32), o["depth"][b].view(np.uint32)), f"depth frame {b}"
+        assert r["counts"][b, 1] == int(o["mask"][b].sum())
+    # without the optional outputs the depth must not change
+    r2 = handle.run_host(frames, src_thr, val_thr)
+    assert np.array_equal(r2["depth"], r["depth"])
+    return r
+
+
+def test_small_golden_frames(handle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "small_frames.npz"))
+    names = sorted({k.rsplit("/", 1)[0] for k in z.files if k.endswith("/in")})
+    for n in names:
+        x = z[n + "/in"]
+        r = handle.run_host(np.ascontiguousarray(x[None]), 0.1, 0.1, want_dt=True, want_lbl=True, want_mask=True)
+        assert "index_error" not in r, (n, r.get("index_error"))
+        assert np.array_equal(r["lbl"][0], z[n + "/lbl"]), n
+        assert np.array_equal(r["dt"][0], z[n + "/dt"]), n
+        assert np.array_equal(r["depth"][0], z[n + "/depth"]), n
+
+
+def test_random_small_frames_all_paths(handle):
+    rng = np.random.default_rng(5)
+    for t in range(60):
+        H, W = int(rng.integers(1, 70)), int(rng.integers(1, 400))
+        dens = rng.choice([0.003, 0.02, 0.1, 0.5, 0.95])
+        x = ((rng.random((2, H, W)) < dens) * rng.uniform(1, 50, (2, H, W))).astype(np.float32)
+        x[:, H // 2, W // 2] = 3.0
+        _check_frames(handle, x, 0.1, 0.1)
+
+
+@pytest.mark.parametrize("W", [320, 640, 1216, 319, 321, 641, 1215, 100, 37])
+def test_lane_layouts(handle, W):
+    """Exact multiples of 32*PPL (no padding) and ragged widths for each lane layout (PPL 10/20/38)."""
+    rng = np.random.default_rng(W)
+    x = ((rng.random((3, 50, W)) < 0.03) * rng.uniform(1, 50, (3, 50, W))).astype(np.float32)
+    x[:, 0, 0] = 2.0
+    _check_frames(handle, x, 0.1, 0.1)
+
+
+def test_wide_path_by_size(handle):
+    """Frames the 32-bit key cannot hold (wider than 1216, or 2H+W too large) take the 64-bit-key kernel."""
+    rng = np.random.default_rng(8)
+    for H, W in ((40, 1300), (20, 3000), (900, 300), (5, 2049)):
+        x = ((rng.random((2, H, W)) < 0.01) * rng.uniform(1, 50, (2, H, W))).astype(np.float32)
+        x[:, H - 1, 0] = 2.0
+        _check_frames(handle, x, 0.1, 0.1)
+
+
+def test_wide_path_by_source_count(handle):
+    """More than 2^18-1 sources in a frame that otherwise fits the fast path."""
+    rng = np.random.default_rng(9)
+    x = rng.uniform(1, 50, (2, 352, 1216)).astype(np.float32)
+    x[1] *= (rng.random((352, 1216)) < 0.7)
+    x[0, 100:140, 200:900] = 0.0
+    r = _check_frames(handle, x, 0.1, 0.1)
+    assert r["counts"][0, 0] > (1 << 18) and r["counts"][1, 0] > (1 << 18)
+
+
+def test_golden_full_frames(handle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "full_frames.npz"))
+    for name, x, thr in (("kitti64_seed0", synth.kitti_frame(0), 0.1),
+                         ("kitti8_seed5", synth.kitti_frame(5, beam_step=8), 0.1),
+                         ("nyu_seed3", synth.nyu_frame(3), 0.001)):
+        r = handle.run_host(np.ascontiguousarray(x[None]), thr, 0.1, want_dt=True, want_lbl=True)
+        assert np.array_equal(r["lbl"][0], z[name + "/lbl"]), name
+        assert np.array_equal(r["dt"][0].astype(np.uint16), z[name + "/dt_u16"]), name
+
+
+def test_golden_checksums_all_configs(handle, golden_dir):
+    """Reference outputs (tools.DT_complete_batch / eval_NYU.Distance_Transform run in the build container)
+    for 64/32/16/8-beam KITTI frames and NYU frames, compared by SHA-256."""
+    z = np.load(os.path.join(golden_dir, "checksums.npz"))
+    for step in (1, 2, 4, 8):
+        xb = synth.kitti_batch(range(4), beam_step=step)
+        depth = tools.DT_complete_batch(xb)
+        assert depth.shape == (4, 352, 1216, 1) and depth.dtype == np.float32
+        for seed in range(4):
+            dt, lbl = tools.nearest_point(xb[seed])
+            want = z[f"kitti_b{64 // step}_s{seed}"]
+            assert [sha(depth[seed, :, :, 0]), sha(dt), sha(lbl)] == list(want), (step, seed)
+    for seed in range(4):
+        x = synth.nyu_frame(seed)
+        d = eval_nyu.Distance_Transform(x[None, :, :, None])
+        dt, lbl = eval_nyu.nearest_point(x)
+        assert d.dtype == np.float32 and d.shape == (480, 640)
+        assert [sha(d), sha(dt), sha(lbl)] == list(z[f"nyu_s{seed}"]), seed
+    x = synth.nyu_frame(9, 240, 320)
+    dt, lbl = eval_nyu.nearest_point(x)
+    assert [sha(eval_nyu.Distance_Transform(x)), sha(dt), sha(lbl)] == list(z["nyu240_s9"])
+
+
+def test_batch_vs_oracle_kitti(handle):
+    x = np.stack([synth.kitti_frame(100 + i, beam_step=s) for i, s in enumerate((1, 1, 2, 4, 8, 1))])
+    _check_frames(handle, x, 0.1, 0.1)
+
+
+def test_batch_vs_oracle_nyu(handle):
+    x = np.stack([synth.nyu_frame(200 + i) for i in range(4)])
+    _check_frames(handle, x, 0.001, 0.1)
+
+
+def test_reference_quirks(handle):
+    adv = synth.adversarial_frames()
+    # valid pixels but no source: lbl == 0 -> whole frame is the LAST valid depth, dt == 65533 (Appendix B)
+    f = adv["valid_no_source"]
+    r = handle.run_host(np.ascontiguousarray(f[None]), 0.1, 0.1, want_dt=True, want_lbl=True)
+    assert np.all(r["lbl"] == 0) and np.all(r["dt"] == 65533.0) and np.all(r["depth"] == np.float32(0.25))
+    # no valid pixel at all -> IndexError from both fill functions (tools.py:26)
+    z = np.zeros((1, 352, 1216, 1), np.float32)
+    with pytest.raises(IndexError):
+        tools.DT_complete_batch(z)
+    with pytest.raises(IndexError):
+        eval_nyu.Distance_Transform(z[0, :, :, 0])
+    # only the second frame is bad: IndexError names it, like the reference's per-frame loop would hit it
+    xb = synth.kitti_batch([0, 1])
+    xb[1] = 0
+    with pytest.raises(IndexError, match="frame 1"):
+        tools.DT_complete_batch(xb)
+    # exactly one valid pixel: tools.py:24 handles it, eval_NYU.py:126's squeeze makes it an IndexError
+    one = np.zeros((352, 1216), np.float32)
+    one[10, 10] = 5.0
+    out = tools.DT_complete_batch(one[None, :, :, None])
+    assert np.all(out == 5.0)
+    with pytest.raises(IndexError):
+        eval_nyu.Distance_Transform(one)
+    # NaN is a source (1 - nan > thr is False) but not valid: more sources than valid depths -> IndexError
+    f = np.zeros((1, 16, 16), np.float32)
+    f[0, 3, 3] = np.nan
+    r = handle.run_host(f, 0.1, 0.1)
+    assert "index_error" in r and r["first_bad"] == 0
+    # extra channels are ignored (tools.py:19 reads channel 0)
+    xb2 = np.concatenate([synth.kitti_batch([3]), np.full((1, 352, 1216, 1), 9.0, np.float32)], axis=-1)
+    assert np.array_equal(tools.DT_complete_batch(xb2), tools.DT_complete_batch(xb2[..., :1]))
+    # input untouched, output is a new array
+    xb3 = synth.kitti_batch([4])
+    keep = xb3.copy()
+    out = tools.DT_complete_batch(xb3)
+    assert np.array_equal(xb3, keep) and not np.shares_memory(out, xb3)
+
+
+def test_idempotence_and_source_preservation(handle):
+    """Size-independent properties at full size: sources keep their own depth and label; filling a filled
+    frame changes nothing (every pixel is then its own source)."""
+    x = np.stack([synth.kitti_frame(300 + i) for i in range(8)])
+    r = handle.run_host(x, 0.1, 0.1, want_dt=True, want_lbl=True)
+    src = x >= 1.0
+    assert np.array_equal(r["depth"][src], x[src])
+    assert np.all(r["dt"][src] == 0) and np.all(r["dt"][~src] >= 1)
+    for b in range(x.shape[0]):
+        assert np.array_equal(r["lbl"][b][src[b]], np.arange(1, int(src[b].sum()) + 1))
+    r2 = handle.run_host(r["depth"], 0.1, 0.1, want_dt=True)
+    assert np.array_equal(r2["depth"], r["depth"]) and np.all(r2["dt"] == 0)
+
+
+def test_metrics_golden_and_oracle(handle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for seed in range(3):
+        x = synth.kitti_frame(seed)
+        fill = tools.DT_complete_batch(x[None, :, :, None])[0, :, :, 0]
+        gt = synth.kitti_gt(seed)
+        R = evaluation.Result()
+        assert R.evaluate(fill, gt) is None
+        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_s{seed}"], rtol=METRIC_RTOL_F64)
+        R.evaluate(np.maximum(fill, np.float32(0.9)), gt.astype(np.float32))
+        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_f32gt_s{seed}"],
+                                   rtol=METRIC_RTOL_F32)
+        xn, g = synth.nyu_frame(seed, return_dense=True)
+        fill = eval_nyu.Distance_Transform(xn)
+        R = evaluation.Result_NYU()
+        R.evaluate(fill, g)
+        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae, R.delta1, R.delta2, R.delta3],
+                                   z[f"nyu_s{seed}"], rtol=METRIC_RTOL_F32)
+    # empty valid set -> nan like numpy's mean of an empty array
+    R = evaluation.Result()
+    R.evaluate(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float64))
+    assert np.isnan(R.rmse) and np.isnan(R.mae)
+
+
+def test_metrics_batch_sums(handle):
+    B = 6
+    fills = np.stack([O.dt_fill(synth.kitti_frame(400 + i))["depth"] for i in range(B)])
+    gts = np.stack([synth.kitti_gt(400 + i) for i in range(B)])
+    per_frame, sums = evaluation.evaluate_batch(fills, gts, _lib.METRICS_KITTI)
+    want = np.array([[m["mse"], m["rmse"], m["mae"], m["irmse"], m["imae"], 0, 0, 0, m["count"]]
+                     for m in (O.result_kitti(fills[i], gts[i]) for i in range(B))])
+    np.testing.assert_allclose(per_frame, want, rtol=METRIC_RTOL_F64)
+    np.testing.assert_allclose(sums[:9], want.sum(axis=0), rtol=METRIC_RTOL_F64)
+    assert sums[9] == B
+
+
+def test_device_resident_engine_matches_host_path(handle):
+    import torch
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    eng = DTFillEngine(0)
+    x = np.stack([synth.kitti_frame(500 + i) for i in range(4)])
+    xd = torch.from_numpy(x).cuda()
+    out = eng.fill(xd, want_lbl=True)
+    bad, launches = eng.status()
+    assert bad == -1 and launches >= 3
+    o = O.dt_fill(x)
+    assert np.array_equal(out["depth"].cpu().numpy(), o["depth"])
+    assert np.array_equal(out["dt"].cpu().numpy(), o["dt"])
+    assert np.array_equal(out["lbl"].cpu().numpy(), o["lbl"])
+    assert np.array_equal(out["mask"].cpu().numpy(), o["mask"])
+    gt = torch.from_numpy(np.stack([synth.kitti_gt(500 + i) for i in range(4)])).cuda()
+    per_frame, sums = eng.metrics(out["depth"], gt)
+    want = [O.result_kitti(o["depth"][i], gt[i].cpu().numpy())["rmse"] for i in range(4)]
+    np.testing.assert_allclose(per_frame[:, 1].cpu().numpy(), want, rtol=METRIC_RTOL_F64)

@@ -1,0 +1,79 @@
+"""Host-side logic that needs no GPU: argument contracts of the drop-in functions, sharding arithmetic, the
+rule that the product never touches oracle/."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from distancetransform_depthcompletion_b200 import sharding, synth, tools, eval_nyu, evaluation
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dt_complete_batch_shape_errors():
+    with pytest.raises(ValueError):                       # tools.py:25-27 hard-coded 352 x 1216
+        tools.DT_complete_batch(np.ones((1, 100, 100, 1), np.float32))
+    with pytest.raises(IndexError):                       # tools.py:19 indexes four axes
+        tools.DT_complete_batch(np.ones((352, 1216), np.float32))
+    with pytest.raises(TypeError):
+        tools.DT_complete_batch(np.ones((1, 352, 1216, 1), np.float64))
+
+
+def test_nearest_point_and_distance_transform_shape_errors():
+    with pytest.raises(ValueError):
+        tools.nearest_point(np.ones((2, 3, 4), np.float32))
+    with pytest.raises(ValueError):
+        eval_nyu.Distance_Transform(np.ones((2, 3, 4), np.float32))
+
+
+def test_evaluate_contract_errors():
+    with pytest.raises(IndexError):
+        evaluation.Result().evaluate(np.ones((3, 3), np.float32), np.ones((3, 4), np.float32))
+    with pytest.raises(TypeError):
+        evaluation.Result().evaluate(np.ones((3, 3), np.float64), np.ones((3, 3), np.float64))
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 256, 8192, 1000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+def test_finalize_means():
+    s = np.array([2.0, 4.0, 6.0, 8.0, 10.0, 1.0, 1.5, 2.0, 1234.0, 2.0])
+    m = sharding.finalize_means(s)
+    assert m["rmse"] == 2.0 and m["imae"] == 5.0 and m["frames"] == 2 and m["valid_pixels"] == 1234.0
+
+
+def test_synth_inputs_match_the_configs():
+    x = synth.kitti_frame(0)
+    assert x.shape == (352, 1216) and x.dtype == np.float32
+    d = float((x > 0).mean())
+    assert 0.045 < d < 0.056                               # ~5 % density (BASELINE configs[0])
+    assert x[x > 0].min() >= 1.0                           # source and valid predicates agree
+    assert np.all(x * 256 == np.rint(x * 256))             # KITTI grid k/256 (data_read.py:215)
+    for step, frac in ((2, 0.5), (4, 0.25), (8, 0.125)):
+        assert abs((synth.kitti_frame(0, beam_step=step) > 0).sum() / (x > 0).sum() - frac) < 0.03
+    n = synth.nyu_frame(0)
+    assert n.shape == (480, 640) and 450 <= int((n > 0).sum()) <= 500
+    assert synth.kitti_gt(0).dtype == np.float64
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distancetransform_depthcompletion_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|dtfill_oracle|libdtfill_oracle", src, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, f"product files reference the oracle: {bad}"
