@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- DT + NN-fill throughput on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's CPU path on host cores
+
+A step = one pass of the hot path over one batch of synthetic KITTI-shaped frames (BASELINE.json configs[1]:
+256 frames of 352x1216, 64-beam pattern, ~5 % density; outputs filled depth + distance channel + validity mask).
+Weak scaling: every rank processes its own batch of 256 frames per step; `value` = total frames of all ranks /
+max-over-ranks device time.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PX = 13          # read input f32 4 + filled depth 4 + dt 4 + mask u8 1
+H, W = 352, 1216
+METRIC = "DT+NN-fill frames/s @1216x352 (64-beam KITTI-shaped frames, batch 256 per GPU)"
+UNIT = "frames/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference CPU path (the reference's own lines with the real cv2 call; C oracle if cv2 is absent)
+# ------------------------------------------------------------------------------------------------------------
+_CPU_FRAMES = None      # frames shared with the forked workers (no pickling of pixel data)
+
+
+def _cpu_worker(args):
+    kind, lo, hi = args
+    from oracle import oracle as O
+    frames = _CPU_FRAMES[lo:hi]
+    if kind == "cv2":
+        import cv2
+        cv2.setNumThreads(1)
+        acc = 0.0
+        for i in range(frames.shape[0]):
+            # one cv2 call per frame yields the filled depth (tools.py:19-27), dt (tools.py:10) and the mask
+            depth, dt, valid = O.cv2_port_fill_frame(frames[i], 0.1, 0.1)
+            acc += float(depth[0, 0]) + float(dt[0, 0]) + float(valid[0, 0])
+        return acc
+    r = O.dt_fill(frames)
+    return float(r["depth"][0, 0, 0])
+
+
+class CpuReference:
+    """The reference's per-frame work (tools.py:7-35: mask, cv2 DT with labels, compaction, gather) restated in
+    oracle/oracle.py, frames split evenly over a fork()ed process pool with one cv2 thread each."""
+
+    def __init__(self, frames: np.ndarray):
+        global _CPU_FRAMES
+        from oracle import oracle as O
+        O.build()
+        self.kind = "cv2" if O.have_cv2() else "c_oracle"
+        self.cores = os.cpu_count() or 1
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except Exception:
+            pass
+        _CPU_FRAMES = frames
+        import multiprocessing as mp
+        self.pool = mp.get_context("fork").Pool(self.cores)
+
+    def run(self, n: int) -> float:
+        """Process the first n frames; returns seconds."""
+        edges = np.linspace(0, n, self.cores + 1).astype(int)
+        jobs = [(self.kind, int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, jobs)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.terminate()
+
+    def describe(self):
+        if self.kind == "cv2":
+            return ("port", "reference lines tools.py:7-35 restated with the real cv2.distanceTransformWithLabels "
+                            "(oracle/oracle.py cv2_port_fill_frame), one process per core")
+        return ("port", "C restatement oracle/dtfill_oracle.c (cv2 not importable here), one process per core")
+
+
+def make_frames(n: int, seed0: int) -> np.ndarray:
+    from distancetransform_depthcompletion_b200 import synth
+    distinct = min(n, 64)
+    base = np.stack([synth.kitti_frame(seed0 + i) for i in range(distinct)])
+    if distinct == n:
+        return base
+    reps = -(-n // distinct)
+    out = np.concatenate([base] * reps)[:n].copy()
+    # make repeated frames differ (shift columns) so no two frames of the batch are identical
+    for i in range(distinct, n):
+        out[i] = np.roll(out[i], (i // distinct) * 7, axis=1)
+    return out
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = args.batch
+    cores = os.cpu_count() or 1
+    sample = min(batch, max(cores * 4, 32))
+    ref = CpuReference(make_frames(sample, 0))
+    for _ in range(args.warmup):
+        ref.run(min(sample, max(ref.cores, 8)))
+    t = 0.0
+    for _ in range(args.steps):
+        t += ref.run(sample)
+    ref.close()
+    fps = sample * args.steps / t
+    kind, how = ref.describe()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 keys (integer chamfer) + f32 copy", "data": "synthetic",
+        "config": {"workload": f"kitti64 352x1216 ~5% density, {sample}-frame sample of the {batch}-frame batch per step",
+                   "outputs": "filled depth + distance channel + validity mask", "host_cores": ref.cores},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ref.cores, "kind": kind,
+                         "sample": f"{sample} frames x {args.steps} steps; {how}"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from distancetransform_depthcompletion_b200 import _lib
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    frames_np = make_frames(B, 1000 * rank)
+    pin_in = _lib.pinned_empty((B, H, W), np.float32)
+    pin_in[...] = frames_np
+    x = torch.from_numpy(frames_np).to(dev)
+    eng = DTFillEngine(local_rank)
+    out = dict(depth=torch.empty((B, H, W), dtype=torch.float32, device=dev),
+               dt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
+               mask=torch.empty((B, H, W), dtype=torch.uint8, device=dev),
+               counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        eng.fill(x, out=out)
+    bad, launches_per_step = eng.status()
+    assert bad == -1, f"unexpected bad frame {bad}"
+
+    # ---- device-resident timing: exactly K steps between two events on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.fill(x, out=out)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel shares (CUDA events between the launches, same stream), separate untimed steps ----
+    eng.handle.set_profiling(True)
+    kt = {}
+    reps = min(args.steps, 5)
+    for _ in range(reps):
+        eng.fill(x, out=out)
+        for k, v in eng.handle.kernel_times().items():
+            kt[k] = kt.get(k, 0.0) + v / reps
+    eng.handle.set_profiling(False)
+    ktot = sum(kt.values())
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    h = eng.handle
+    h.set_stream(None)
+    pin_out = dict(depth=_lib.pinned_empty((B, H, W), np.float32), dt=_lib.pinned_empty((B, H, W), np.float32),
+                   mask=_lib.pinned_empty((B, H, W), np.uint8))
+    e2e_steps = max(2, min(args.steps, 5))
+    h.run_host(pin_in, 0.1, 0.1, want_dt=True, want_mask=True, out=pin_out)      # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = h.run_host(pin_in, 0.1, 0.1, want_dt=True, want_mask=True, out=pin_out)
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * B * e2e_steps / t_e2e
+    assert np.array_equal(r["depth"], out["depth"].cpu().numpy()), "host path and device path disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    px_step = B * H * W
+    achieved = ALG_BYTES_PER_PX * px_step / (ms_per_step * 1e-3) / 1e9 * 1.0      # per GPU (rank-0 clock = max)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "what": "whole fused path of one step (k1_mask_rows + k1b_scan_compact + k2_chamfer [+ k2_chamfer_wide no-op]): "
+                f"{ALG_BYTES_PER_PX} B/px x {px_step} px per step / step time; dominant kernel k2_chamfer",
+        "kernel_ms": kt, "kernel_share": {k: (v / ktot if ktot else None) for k, v in kt.items()},
+        "dominant_kernel": {"name": "k2_chamfer", "ms": kt.get("k2_chamfer"),
+                            "alg_bytes": 8 * px_step,
+                            "achieved_gbs": (8 * px_step / (kt["k2_chamfer"] * 1e-3) / 1e9) if kt.get("k2_chamfer") else None},
+    }
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(frames_np)
+        sample = min(B, max(ref.cores * 4, 32))
+        ref.run(min(sample, max(ref.cores, 8)))
+        reps_cpu, t_cpu = 0, 0.0
+        while t_cpu < 8.0 and reps_cpu < 20:
+            t_cpu += ref.run(sample)
+            reps_cpu += 1
+        ref.close()
+        kind, how = ref.describe()
+        cpu = {"value": sample * reps_cpu / t_cpu, "unit": UNIT, "cores": ref.cores, "kind": kind,
+               "sample": f"{sample} frames x {reps_cpu} repeats ({t_cpu:.1f} s); {how}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 keys (integer chamfer) + f32 copy", "data": "synthetic",
+        "config": {"workload": f"kitti64: batch of {B} synthetic KITTI 64-beam frames 352x1216 (~5% density) per GPU "
+                               "(BASELINE.json configs[1])",
+                   "outputs": "filled depth f32 + distance channel f32 + validity mask u8 (13 B/px algorithmic)",
+                   "l2": f"inputs+outputs per step {ALG_BYTES_PER_PX * px_step / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                   "frames_per_step_per_gpu": B},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W * 4),
+                "d2h_bytes_per_step": int(B * H * W * 9), "steps": e2e_steps,
+                "what": "dtfill_run (C ABI) with pinned host numpy buffers in and out, synchronous"},
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

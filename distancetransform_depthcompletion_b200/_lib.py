@@ -52,11 +52,14 @@ def load() -> ctypes.CDLL:
         L.dtfill_run_async.argtypes = [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp]
         L.dtfill_status.argtypes = [vp, _c_int_p, _c_int_p]
         L.dtfill_metrics.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
+        L.dtfill_set_profiling.argtypes = [vp, ci]
+        L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
-                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc"):
+                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling",
+                     "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -152,6 +155,17 @@ class Handle:
         if rc not in (0, E_INDEX):
             _check(rc, "dtfill_status")
         return bad.value, launches.value
+
+    KERNEL_NAMES = ("k1_mask_rows", "k1b_scan_compact", "k2_chamfer", "k2_chamfer_wide")
+
+    def set_profiling(self, enabled: bool):
+        _check(self._L.dtfill_set_profiling(self._h, int(bool(enabled))), "dtfill_set_profiling")
+
+    def kernel_times(self) -> dict:
+        """Milliseconds of each kernel of the last run (CUDA events on the handle's stream); profiling must be on."""
+        ms = (ctypes.c_float * 4)()
+        _check(self._L.dtfill_kernel_times(self._h, ms), "dtfill_kernel_times")
+        return dict(zip(self.KERNEL_NAMES, (float(v) for v in ms)))
 
     def metrics(self, pred, gt, B: int, H: int, W: int, mode: int, gt_is_f64: bool, on_device: bool = False,
                 per_frame_ptr=None, sums_ptr=None):

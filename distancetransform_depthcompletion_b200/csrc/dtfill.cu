@@ -46,6 +46,8 @@ struct dtfill_ctx {
     int* status_host = nullptr;   // pinned [2]
     int last_launches = 0;
     int last_B = 0;
+    bool profiling = false;
+    cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
 };
 
 namespace {
@@ -144,6 +146,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     h->status_host[1] = 0;
     CU(cudaMemcpyAsync(ws.status, h->status_host, 8, cudaMemcpyHostToDevice, s));
 
+    if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
     {   // K1: enough warps to keep HBM busy, a whole number of waves of 8-warp blocks
         long want = ((long)rows + 7) / 8;
         long cap = (long)h->sm_count * 8 * 4;
@@ -151,8 +154,10 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
         k1_mask_rows<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
         ++launches;
     }
+    if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
     k1b_scan_compact<<<B, 256, 0, s>>>(in, fp, ws, out_counts);
     ++launches;
+    if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
     const bool want_lbl = out_lbl != nullptr;
     switch (plan.ppl) {
@@ -162,6 +167,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
         default: launch_k2<10>(true, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;  // NOSRC frames only
     }
     ++launches;
+    if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
     {   // wide fallback: returns immediately for every task the fast kernel handled
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
         static size_t configured = 0;
@@ -173,6 +179,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
         k2_chamfer_wide<<<B, 32, smem, s>>>(fp, ws, out_depth, out_dt, out_lbl);
         ++launches;
     }
+    if (h->profiling) CU(cudaEventRecord(h->ev[4], s));
     CU(cudaMemcpyAsync(h->status_host, ws.status, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     h->last_launches = launches;
@@ -208,6 +215,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     CU(cudaHostAlloc((void**)&h->status_host, 16, cudaHostAllocDefault));
+    for (auto& e : h->ev) CU(cudaEventCreate(&e));
     h->status_host[0] = INT_MAX;
     h->status_host[1] = 0;
     *out_handle = h;
@@ -224,6 +232,8 @@ void dtfill_destroy(dtfill_t* h) {
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->status_host) cudaFreeHost(h->status_host);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -342,6 +352,21 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
         if (sums) CU(cudaMemcpyAsync(sums, sm_d, 10 * 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
+    return 0;
+}
+
+int dtfill_set_profiling(dtfill_t* h, int enabled) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_profiling: NULL handle");
+    h->profiling = enabled != 0;
+    return 0;
+}
+
+int dtfill_kernel_times(dtfill_t* h, float* ms) {
+    if (!h || !ms) return fail(DTFILL_E_ARG, "dtfill_kernel_times: NULL argument");
+    if (!h->profiling) return fail(DTFILL_E_ARG, "dtfill_kernel_times: profiling is off");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->ev[DTFILL_NUM_KERNELS]));
+    for (int i = 0; i < DTFILL_NUM_KERNELS; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     return 0;
 }
 

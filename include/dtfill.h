@@ -109,6 +109,13 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
 
+/* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
+ * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
+ * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide into ms[0..3]. */
+#define DTFILL_NUM_KERNELS 4
+int dtfill_set_profiling(dtfill_t* h, int enabled);
+int dtfill_kernel_times(dtfill_t* h, float* ms);
+
 /* Pinned host memory for fast host<->device copies (cudaHostAlloc / cudaFreeHost). */
 int  dtfill_host_alloc(void** out_ptr, size_t bytes);
 void dtfill_host_free(void* ptr);
