@@ -17,7 +17,8 @@ class DTFillEngine:
         self.handle = _lib.Handle(self.device)
 
     def _bind_stream(self):
-        self.handle.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        # torch reports the legacy default stream as handle 0; CUDA's explicit handle for it is cudaStreamLegacy (0x1)
+        self.handle.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream or 0x1)
 
     def fill(self, frames, src_thr: float = 0.1, val_thr: float = 0.1, want_lbl: bool = False, out=None):
         """frames: float32 CUDA tensor [B,H,W] (contiguous).  Returns dict of CUDA tensors, enqueued only."""
