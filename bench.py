@@ -206,6 +206,8 @@ def run_ours(args, rank, world, local_rank):
     pin_in[...] = frames_np
     x = torch.from_numpy(frames_np).to(dev)
     eng = DTFillEngine(local_rank)
+    if args.band_cap is not None:
+        eng.handle.set_band_cap(args.band_cap)
     out = dict(depth=torch.empty((B, H, W), dtype=torch.float32, device=dev),
                dt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
                mask=torch.empty((B, H, W), dtype=torch.uint8, device=dev),
@@ -340,6 +342,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

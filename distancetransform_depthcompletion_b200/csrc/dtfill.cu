@@ -40,13 +40,14 @@ struct dtfill_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     // workspace
-    Buf srcbits, valbits, wprefix, rowsrc, rowval, counts, dlist, scratch, tasks, status;
+    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
     int* status_host = nullptr;   // pinned [2]
     int last_launches = 0;
     int last_B = 0;
     bool profiling = false;
+    int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
 };
 
@@ -121,12 +122,15 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, h->srcbits, rows * WW * 4))) return rc;
     if ((rc = ensure(h, h->valbits, rows * WW * 4))) return rc;
     if ((rc = ensure(h, h->wprefix, rows * WW * 2))) return rc;
+    if ((rc = ensure(h, h->rowcell, rows * WW))) return rc;
     if ((rc = ensure(h, h->rowsrc, rows * 4))) return rc;
     if ((rc = ensure(h, h->rowval, rows * 4))) return rc;
     if ((rc = ensure(h, h->counts, (size_t)B * 8))) return rc;
     if ((rc = ensure(h, h->dlist, npx * 4))) return rc;
-    if ((rc = ensure(h, h->scratch, rows * (size_t)(plan.ppl ? plan.wp : W) * 4))) return rc;
-    if ((rc = ensure(h, h->tasks, (size_t)B * sizeof(Task)))) return rc;
+    // forward-state scratch: bands overlap by their halos, so allow up to 2 H rows per frame
+    const int scratch_rows_per_frame = plan.ppl ? 2 * H : H;
+    if ((rc = ensure(h, h->scratch, (size_t)B * scratch_rows_per_frame * (size_t)(plan.ppl ? plan.wp : W) * 4))) return rc;
+    if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, h->status, 16))) return rc;
 
     FrameParams fp;
@@ -134,8 +138,20 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     fp.src_thr = src_thr; fp.val_thr = val_thr;
     fp.init_dist = H + W + 8;
     fp.force_wide = plan.ppl == 0;
+    fp.scratch_rows_per_frame = scratch_rows_per_frame;
+    {   // band planner target: enough independent tasks to give every SM ~16 warps
+        int cap = h->band_cap;
+        if (cap < 0) {
+            const long want_tasks = (long)h->sm_count * 16;
+            const long per_frame = (want_tasks + B - 1) / B;
+            cap = per_frame <= 1 ? 0 : (int)((2L * H * 5 / 4) / per_frame);
+            if (cap > 0 && cap < 96) cap = 96;
+        }
+        fp.band_cap = plan.ppl ? cap : 0;
+    }
     Workspace ws;
     ws.srcbits = (uint32_t*)h->srcbits.p; ws.valbits = (uint32_t*)h->valbits.p; ws.wprefix = (uint16_t*)h->wprefix.p;
+    ws.rowcell = (uint8_t*)h->rowcell.p;
     ws.rowsrc = (uint32_t*)h->rowsrc.p; ws.rowval = (uint32_t*)h->rowval.p; ws.counts = (int32_t*)h->counts.p;
     ws.dlist = (float*)h->dlist.p; ws.scratch = (uint32_t*)h->scratch.p; ws.tasks = (Task*)h->tasks.p;
     ws.status = (int*)h->status.p;
@@ -161,10 +177,10 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
 
     const bool want_lbl = out_lbl != nullptr;
     switch (plan.ppl) {
-        case 10: launch_k2<10>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        case 20: launch_k2<20>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        case 38: launch_k2<38>(plan.pad, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        default: launch_k2<10>(true, want_lbl, B, s, fp, ws, out_depth, out_dt, out_lbl); break;  // NOSRC frames only
+        case 10: launch_k2<10>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        case 20: launch_k2<20>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        case 38: launch_k2<38>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
+        default: launch_k2<10>(true, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;  // NOSRC frames only
     }
     ++launches;
     if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
@@ -218,6 +234,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
     h->status_host[0] = INT_MAX;
     h->status_host[1] = 0;
+    if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     *out_handle = h;
     return 0;
 }
@@ -226,7 +243,7 @@ void dtfill_destroy(dtfill_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    Buf* bufs[] = {&h->srcbits, &h->valbits, &h->wprefix, &h->rowsrc, &h->rowval, &h->counts, &h->dlist,
+    Buf* bufs[] = {&h->srcbits, &h->valbits, &h->wprefix, &h->rowcell, &h->rowsrc, &h->rowval, &h->counts, &h->dlist,
                    &h->scratch, &h->tasks, &h->status, &h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev,
                    &h->mask_dev, &h->counts_out_dev, &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
     for (Buf* b : bufs)
@@ -352,6 +369,12 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
         if (sums) CU(cudaMemcpyAsync(sums, sm_d, 10 * 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
+    return 0;
+}
+
+int dtfill_set_band_cap(dtfill_t* h, int cap) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_band_cap: NULL handle");
+    h->band_cap = cap;
     return 0;
 }
 

@@ -45,17 +45,25 @@ struct __align__(16) Task {
     int pad_;
 };
 
+constexpr int MAXT = 16;      // task slots per frame (bands); slot-major layout tasks[slot * B + frame]
+constexpr int CELL_H = 4;     // coarse occupancy cells used by the band planner
+constexpr int CELL_W = 8;
+constexpr int MAX_CELLS = 15360;   // planner grid limit (30 KB of shared memory); larger frames are not banded
+
 struct FrameParams {
     int B, H, W, WW;           // WW = 32-bit words per bit row
     float src_thr, val_thr;
     int init_dist;             // "unreached" distance of the fast path: H + W + 8
     int force_wide;            // size not representable in the 32-bit key
+    int band_cap;              // planner: target cost (row steps) of one task; <= 0 disables banding
+    int scratch_rows_per_frame;  // capacity of the forward-state scratch per frame (rows)
 };
 
 struct Workspace {
     uint32_t* srcbits;   // [B*H*WW]
     uint32_t* valbits;   // [B*H*WW]
     uint16_t* wprefix;   // [B*H*WW] sources in the row before this word
+    uint8_t* rowcell;    // [B*H*WW] per word: bit j = some source among its pixels 8j..8j+7
     uint32_t* rowsrc;    // [B*H]  K1: row count, K1b: exclusive base within the frame
     uint32_t* rowval;    // [B*H]
     int32_t* counts;     // [B*2]  n_src, n_valid
@@ -87,7 +95,8 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1: predicates -> bit rows, counts, validity mask.  One warp per row, 4 words (128 px) per iteration.
+// K1: predicates -> bit rows, counts, validity mask.  One warp per row; 16 words (512 px) of loads in flight
+// per lane so that the HBM pipe stays full.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
                                                      uint8_t* __restrict__ out_mask)
@@ -101,53 +110,52 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in
     for (long row = warp; row < nrows; row += nwarps) {
         const float* rp = in + row * W;
         uint32_t cs = 0, cv = 0;
-        for (int w0 = 0; w0 < WW; w0 += 4) {
-            float x[4];
-            bool inb[4];
+        for (int c0 = 0; c0 < WW; c0 += 16) {
+            float x[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = (w0 + k) * 32 + lane;
-                inb[k] = col < W;
-                x[k] = inb[k] ? ld_stream(rp + col) : 0.0f;
+            for (int k = 0; k < 16; ++k) {
+                const int col = (c0 + k) * 32 + lane;
+                x[k] = col < W ? ld_stream(rp + col) : 0.0f;
             }
-            uint32_t sw[4], vw[4];
+            uint32_t mys = 0, myv = 0, mypre = 0;
+            uint32_t vq[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 16; ++k) {
+                const int col = (c0 + k) * 32 + lane;
+                const bool inb = col < W;
                 const float d = __fsub_rn(1.0f, x[k]);                 // tools.py:8  1.0 - x  (float32)
-                const bool s = inb[k] && !(d > fp.src_thr);           // value_mask == 0  <=> source
-                const bool v = inb[k] && (x[k] > fp.val_thr);         // tools.py:22 with_value
-                sw[k] = __ballot_sync(0xffffffffu, s);
-                vw[k] = __ballot_sync(0xffffffffu, v);
-            }
-            if (lane < 4 && w0 + lane < WW) {
-                const uint32_t s_sel = lane == 0 ? sw[0] : lane == 1 ? sw[1] : lane == 2 ? sw[2] : sw[3];
-                const uint32_t v_sel = lane == 0 ? vw[0] : lane == 1 ? vw[1] : lane == 2 ? vw[2] : vw[3];
-                uint32_t pre = cs;
-                if (lane > 0) pre += __popc(sw[0]);
-                if (lane > 1) pre += __popc(sw[1]);
-                if (lane > 2) pre += __popc(sw[2]);
-                const long wi = row * WW + w0 + lane;
-                ws.srcbits[wi] = s_sel;
-                ws.valbits[wi] = v_sel;
-                ws.wprefix[wi] = (uint16_t)pre;
-            }
-            if (out_mask) {
-                if (vec_mask) {
-                    const int col4 = w0 * 32 + lane * 4;
-                    if (col4 < W) {
-                        const int k = lane >> 3;
-                        const uint32_t word = k == 0 ? vw[0] : k == 1 ? vw[1] : k == 2 ? vw[2] : vw[3];
-                        const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;
-                        st_stream_u32(out_mask + row * W + col4, (nib * 0x00204081u) & 0x01010101u);
+                const bool sp = inb && !(d > fp.src_thr);             // value_mask == 0  <=> source
+                const bool vp = inb && (x[k] > fp.val_thr);           // tools.py:22 with_value
+                const uint32_t sw = __ballot_sync(0xffffffffu, sp);
+                const uint32_t vw = __ballot_sync(0xffffffffu, vp);
+                if (lane == k) { mys = sw; myv = vw; mypre = cs; }
+                cs += __popc(sw);
+                cv += __popc(vw);
+                vq[k & 3] = vw;
+                if (out_mask) {
+                    if (vec_mask) {
+                        if ((k & 3) == 3) {
+                            const int col4 = (c0 + k - 3) * 32 + lane * 4;
+                            if (col4 < W) {
+                                const int q = lane >> 3;
+                                const uint32_t word = q == 0 ? vq[0] : q == 1 ? vq[1] : q == 2 ? vq[2] : vq[3];
+                                const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;
+                                st_stream_u32(out_mask + row * W + col4, (nib * 0x00204081u) & 0x01010101u);
+                            }
+                        }
+                    } else if (inb) {
+                        out_mask[row * W + col] = (uint8_t)vp;
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (inb[k]) out_mask[row * W + (w0 + k) * 32 + lane] = (vw[k] >> lane) & 1u;
                 }
             }
-            cs += __popc(sw[0]) + __popc(sw[1]) + __popc(sw[2]) + __popc(sw[3]);
-            cv += __popc(vw[0]) + __popc(vw[1]) + __popc(vw[2]) + __popc(vw[3]);
+            if (lane < 16 && c0 + lane < WW) {
+                const long wi = row * WW + c0 + lane;
+                ws.srcbits[wi] = mys;
+                ws.valbits[wi] = myv;
+                ws.wprefix[wi] = (uint16_t)mypre;
+                ws.rowcell[wi] = (uint8_t)(((mys & 0xFFu) != 0) | (((mys & 0xFF00u) != 0) << 1) |
+                                           (((mys & 0xFF0000u) != 0) << 2) | (((mys & 0xFF000000u) != 0) << 3));
+            }
         }
         if (lane == 0) {
             ws.rowsrc[row] = cs;
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict_
                                                          int32_t* __restrict__ out_counts)
 {
     __shared__ uint32_t sm[9];
+    __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
+    __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
     const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
@@ -201,28 +211,79 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict_
     uint32_t bs = block_exclusive_scan_256(ls, sm, nsrc);
     uint32_t bv = block_exclusive_scan_256(lv, sm, nval);
     for (int y = y0; y < y1; ++y) {
-        const uint32_t s = rs[y], v = rv[y];
+        const uint32_t s_ = rs[y], v_ = rv[y];
         rs[y] = bs; rv[y] = bv;
-        bs += s; bv += v;
+        bs += s_; bv += v_;
     }
     __syncthreads();
 
-    // depth_list = in[valid] in raster order (tools.py:24): one warp per non-empty row
+    // depth_list = in[valid] in raster order (tools.py:24): one warp per non-empty row, lanes over the words
     const int lane = tid & 31, wid = tid >> 5;
     float* dl = ws.dlist + (long)b * H * W;
-    const uint32_t ltmask = lanemask_lt();
     for (int y = wid; y < H; y += 8) {
         const uint32_t base = rv[y];
         const uint32_t next = (y + 1 < H) ? rv[y + 1] : nval;
         if (next == base) continue;
         const long row = (long)b * H + y;
         uint32_t run = base;
-        for (int w = 0; w < WW; ++w) {
-            const uint32_t vb = ws.valbits[row * WW + w];
-            if (vb == 0) continue;
-            if ((vb >> lane) & 1u) dl[run + __popc(vb & ltmask)] = in[row * W + w * 32 + lane];
-            run += __popc(vb);
+        for (int w0 = 0; w0 < WW; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t vb = w < WW ? ws.valbits[row * WW + w] : 0u;
+            const uint32_t cnt = __popc(vb);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t dst = run + inc - cnt;
+            const float* src = in + row * W + w * 32;
+            while (vb) {
+                const int bit = __ffs(vb) - 1;
+                vb &= vb - 1;
+                dl[dst++] = src[bit];
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
         }
+    }
+
+    // ---- task emission -------------------------------------------------------------------------------
+    const int B = fp.B;
+    int kind = (nsrc == 0) ? TASK_NOSRC : ((fp.force_wide || nsrc > MAX_FAST_LABEL) ? TASK_WIDE : TASK_CHAMFER);
+    if (nval == 0) kind = TASK_SKIP;
+    const int nh = (H + CELL_H - 1) / CELL_H, nw = (W + CELL_W - 1) / CELL_W;
+    const bool plan = kind == TASK_CHAMFER && fp.band_cap > 0 && nh * nw <= MAX_CELLS && nh <= 1024 &&
+                      2 * H > fp.band_cap;
+    if (plan) {
+        // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
+        const uint8_t* rc = ws.rowcell + (long)b * H * WW;
+        for (int i = tid; i < nh * nw; i += 256) {
+            const int cy = i / nw, cx = i - cy * nw;
+            uint32_t occ = 0;
+#pragma unroll
+            for (int r = 0; r < CELL_H; ++r) {
+                const int y = cy * CELL_H + r;
+                if (y < H) occ |= (rc[(long)y * WW + (cx >> 2)] >> (cx & 3)) & 1u;
+            }
+            cellD[i] = occ ? 0 : 60000;
+        }
+        __syncthreads();
+        for (int cx = tid; cx < nw; cx += 256) {
+            uint32_t d = 60000;
+            for (int cy = 0; cy < nh; ++cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+            d = 60000;
+            for (int cy = nh - 1; cy >= 0; --cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+        }
+        __syncthreads();
+        for (int cy = tid; cy < nh; cy += 256) {
+            uint32_t d = 60000;
+            for (int cx = 0; cx < nw; ++cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+            d = 60000;
+            uint32_t mx = 0;
+            for (int cx = nw - 1; cx >= 0; --cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); mx = max(mx, d); }
+            cellU[cy] = (int)min(mx, 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
+        }
+        __syncthreads();
     }
 
     if (tid == 0) {
@@ -231,12 +292,60 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict_
         if (out_counts) { out_counts[2 * b] = (int)nsrc; out_counts[2 * b + 1] = (int)nval; }
         // numpy's IndexError: empty depth_list, or a label beyond its end (tools.py:26)
         if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b);
-        Task t;
-        t.frame = b; t.lo = 0; t.hi = H; t.r0 = 0; t.r1 = H; t.scratch_row = b * H; t.pad_ = 0;
-        t.kind = (nsrc == 0) ? TASK_NOSRC : ((fp.force_wide || nsrc > MAX_FAST_LABEL) ? TASK_WIDE : TASK_CHAMFER);
-        if (nval == 0) t.kind = TASK_SKIP;
-        if (t.kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
-        ws.tasks[b] = t;
+        if (kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
+
+        Task t[MAXT];
+        int cost[MAXT];
+        int nt = 0;
+        if (plan) {
+            int cy = 0, scr = 0;
+            bool ok = true;
+            while (cy < nh && ok) {
+                const int r0 = cy * CELL_H;
+                int lo = 1 << 30, hi = 0, prev = 0, end = cy, best_lo = 0, best_hi = 0;
+                for (int c = cy; c < nh; ++c) {
+                    lo = min(lo, c * CELL_H - cellU[c]);
+                    hi = max(hi, min(H, (c + 1) * CELL_H) + cellU[c]);
+                    const int L = max(0, lo), Hh = min(H, hi);
+                    const int cst = (Hh - L) + (Hh - r0);
+                    const bool take = c == cy || nt == MAXT - 1 || cst <= fp.band_cap || cst - prev <= CELL_H;
+                    if (!take) break;
+                    prev = cst; end = c + 1; best_lo = L; best_hi = Hh;
+                }
+                Task q;
+                q.frame = b; q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
+                q.kind = TASK_CHAMFER; q.scratch_row = scr; q.pad_ = 0;
+                scr += best_hi - best_lo;
+                if (scr > fp.scratch_rows_per_frame) ok = false;
+                cost[nt] = prev;
+                t[nt++] = q;
+                cy = end;
+            }
+            if (!ok) nt = 0;
+        }
+        if (nt == 0) {
+            Task q;
+            q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = kind; q.scratch_row = 0; q.pad_ = 0;
+            cost[0] = 2 * H;
+            t[nt++] = q;
+        }
+        // longest task first: the block scheduler hands out blocks in index order (slot-major task array)
+        for (int i = 1; i < nt; ++i) {
+            const Task q = t[i]; const int c = cost[i];
+            int j = i - 1;
+            while (j >= 0 && cost[j] < c) { t[j + 1] = t[j]; cost[j + 1] = cost[j]; --j; }
+            t[j + 1] = q; cost[j + 1] = c;
+        }
+        for (int i = 0; i < MAXT; ++i) {
+            if (i < nt) {
+                t[i].scratch_row += b * fp.scratch_rows_per_frame;
+                ws.tasks[(long)i * B + b] = t[i];
+            } else {
+                Task q;
+                q.frame = b; q.lo = q.hi = q.r0 = q.r1 = 0; q.kind = TASK_SKIP; q.scratch_row = 0; q.pad_ = 0;
+                ws.tasks[(long)i * B + b] = q;
+            }
+        }
     }
 }
 
@@ -297,28 +406,44 @@ __device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t cl
     return key;
 }
 
-// source bits of this lane's PPL columns (bit i = column x0+i) and the number of sources before x0 in the row
+// Raw words holding this lane's PPL source bits of one row, fetched one row ahead of their use.
+struct RowBits {
+    uint32_t a, b, c, pre, base;
+};
+
 template <int PPL>
-__device__ __forceinline__ void load_lane_bits(const uint32_t* __restrict__ bits_row, const uint16_t* __restrict__ pre_row,
-                                               int WW, int x0, uint64_t& bits, uint32_t& before)
+__device__ __forceinline__ RowBits fetch_row_bits(const uint32_t* __restrict__ bits_f, const uint16_t* __restrict__ pre_f,
+                                                  const uint32_t* __restrict__ rowbase, int WW, int x0, int y)
 {
-    const int w = x0 >> 5, sh = x0 & 31;
-    const uint32_t a = w < WW ? bits_row[w] : 0u;
-    const uint32_t b = w + 1 < WW ? bits_row[w + 1] : 0u;
-    const uint32_t c = (PPL > 33 && w + 2 < WW) ? bits_row[w + 2] : 0u;
-    uint64_t lo = ((uint64_t)b << 32) | a;
+    RowBits r;
+    const int w = x0 >> 5;
+    const uint32_t* br = bits_f + (long)y * WW;
+    r.a = w < WW ? br[w] : 0u;
+    r.b = w + 1 < WW ? br[w + 1] : 0u;
+    r.c = (PPL > 33 && w + 2 < WW) ? br[w + 2] : 0u;
+    r.pre = w < WW ? (uint32_t)pre_f[(long)y * WW + w] : 0u;
+    r.base = rowbase[y];
+    return r;
+}
+
+// bit i of `bits` = column x0+i is a source; rank = 1-based raster rank of the first source of this lane
+template <int PPL>
+__device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, uint64_t& bits, uint32_t& rank)
+{
+    const int sh = x0 & 31;
+    uint64_t lo = ((uint64_t)r.b << 32) | r.a;
     lo >>= sh;
-    if (PPL > 33 && sh) lo |= (uint64_t)c << (64 - sh);
+    if (PPL > 33 && sh) lo |= (uint64_t)r.c << (64 - sh);
     bits = lo & ((PPL >= 64) ? ~0ull : ((1ull << PPL) - 1ull));
-    before = (w < WW ? (uint32_t)pre_row[w] : 0u) + __popc(a & ((1u << sh) - 1u));
+    rank = r.base + r.pre + __popc(r.a & ((1u << sh) - 1u)) + 1u;
 }
 
 template <int PPL, bool PAD, bool WANT_LBL>
-__global__ void __launch_bounds__(32) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+__global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
 {
     __shared__ __align__(16) uint32_t stage[32 * PPL];
-    const Task task = ws.tasks[blockIdx.x];
+    const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind == TASK_WIDE || task.kind == TASK_SKIP) return;
     const int lane = threadIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
@@ -350,10 +475,11 @@ __global__ void __launch_bounds__(32) k2_chamfer(FrameParams fp, Workspace ws, f
     fill_row(rb, init_key);
 
     // ---------------- forward pass: rows lo .. hi-1 ----------------
+    RowBits nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, task.lo);
     auto fwd_step = [&](const Row<PPL>& A /*row y-1*/, Row<PPL>& Bq /*row y-2 in, row y out*/, int y) {
-        uint64_t bits; uint32_t before;
-        load_lane_bits<PPL>(bits_f + (long)y * WW, pre_f + (long)y * WW, WW, x0, bits, before);
-        uint32_t rank = rowbase[y] + before + 1u;
+        uint64_t bits; uint32_t rank;
+        decode_row_bits<PPL>(nextbits, x0, bits, rank);
+        nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, min(y + 1, task.hi - 1));   // one row ahead
         uint32_t c[PPL];
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {

@@ -109,6 +109,11 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
 
+/* Frames are split into bands of rows that one warp each processes independently (exact: every band is
+ * extended by a halo derived from a guaranteed upper bound of the distances inside it).  cap > 0: target cost of
+ * one band in row steps; 0: never split; -1 (default): chosen from the batch size and the SM count. */
+int dtfill_set_band_cap(dtfill_t* h, int cap);
+
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
  * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide into ms[0..3]. */

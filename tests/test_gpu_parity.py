@@ -92,6 +92,31 @@ def test_wide_path_by_source_count(handle):
     assert r["counts"][0, 0] > (1 << 18) and r["counts"][1, 0] > (1 << 18)
 
 
+@pytest.mark.parametrize("cap", [0, 8, 24, 64, 150, 400])
+def test_band_splitting_is_exact(handle, cap):
+    """Frames split into independently processed bands of rows (+ halo from the coarse bound) must give the
+    very same labels as the whole-frame scan, whatever the band size."""
+    handle.set_band_cap(cap)
+    try:
+        x = np.stack([synth.kitti_frame(600 + i, beam_step=s) for i, s in enumerate((1, 2, 8))])
+        _check_frames(handle, x, 0.1, 0.1)
+        _check_frames(handle, np.stack([synth.nyu_frame(610), synth.nyu_frame(611, samples=50)]), 0.001, 0.1)
+        rng = np.random.default_rng(cap)
+        for t in range(12):
+            H, W = int(rng.integers(5, 120)), int(rng.integers(5, 500))
+            dens = rng.choice([0.002, 0.02, 0.2])
+            f = ((rng.random((2, H, W)) < dens) * rng.uniform(1, 50, (2, H, W))).astype(np.float32)
+            f[:, rng.integers(0, H), rng.integers(0, W)] = 3.0
+            _check_frames(handle, f, 0.1, 0.1)
+        # a frame whose only sources sit in one corner: bounds as large as the frame
+        f = np.zeros((1, 352, 1216), np.float32)
+        f[0, 350, 3] = 4.0
+        f[0, 351, 1200] = 6.0
+        _check_frames(handle, f, 0.1, 0.1)
+    finally:
+        handle.set_band_cap(-1)
+
+
 def test_golden_full_frames(handle, golden_dir):
     z = np.load(os.path.join(golden_dir, "full_frames.npz"))
     for name, x, thr in (("kitti64_seed0", synth.kitti_frame(0), 0.1),
