@@ -81,12 +81,22 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// Streaming stores to the caller's output buffers: nothing on this path reads them back, so they carry no
+// "memory" clobber and the compiler may keep loads in flight across them.
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
-    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ void st_stream_v2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
 }
 __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ float4 ld_stream_v4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -95,8 +105,105 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1: predicates -> bit rows, counts, validity mask.  One warp per row; 16 words (512 px) of loads in flight
-// per lane so that the HBM pipe stays full.
+// K1 (W % 4 == 0): predicates -> bit rows, per-word source prefix, coarse cells, row counts, validity mask,
+// and the row-local compaction of the valid depths (into ws.scratch, which K2 only uses later).
+// One warp per row; a lane owns 8 consecutive pixels of every 256-pixel chunk (two 128-bit loads), four
+// chunks of loads in flight.  Words of the bit rows are assembled from the lanes' bytes with two butterflies.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_mask_rows_v8(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                        uint8_t* __restrict__ out_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int W = fp.W, WW = fp.WW;
+    const long nrows = (long)fp.B * fp.H;
+    const int nchunks = (W + 255) >> 8;
+    float* rowvals = reinterpret_cast<float*>(ws.scratch);
+    for (long row = warp; row < nrows; row += nwarps) {
+        const float* rp = in + row * W;
+        uint32_t cs = 0, cv = 0;
+        for (int ch0 = 0; ch0 < nchunks; ch0 += 4) {
+            float4 xa[4], xb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int col = ((ch0 + u) << 8) + lane * 8;
+                xa[u] = col < W ? ld_stream_v4(rp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[u] = col + 4 < W ? ld_stream_v4(rp + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ch0 + u >= nchunks) break;
+                const int col = ((ch0 + u) << 8) + lane * 8;
+                const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+                uint32_t sb = 0, vb = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool inb = col + (j & 4) < W;                 // whole float4 groups are in or out
+                    const float d = __fsub_rn(1.0f, x[j]);              // tools.py:8  1.0 - x  (float32)
+                    if (inb && !(d > fp.src_thr)) sb |= 1u << j;        // value_mask == 0  <=> source
+                    if (inb && (x[j] > fp.val_thr)) vb |= 1u << j;      // tools.py:22 with_value
+                }
+                if (out_mask && col < W) {
+                    const uint32_t lo = ((vb & 0xFu) * 0x00204081u) & 0x01010101u;
+                    const uint32_t hi = ((vb >> 4) * 0x00204081u) & 0x01010101u;
+                    if (col + 4 < W) st_stream_v2(out_mask + row * W + col, lo, hi);
+                    else st_stream_u32(out_mask + row * W + col, lo);
+                }
+                // 32-bit words from the bytes of 4 neighbouring lanes
+                uint32_t sw = sb << ((lane & 3) * 8), vw = vb << ((lane & 3) * 8);
+                sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
+                vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
+                sw |= __shfl_xor_sync(0xffffffffu, sw, 2);
+                vw |= __shfl_xor_sync(0xffffffffu, vw, 2);
+                const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);   // bit l: lane l's 8 pixels hold a source
+                const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
+                uint32_t spre = 0, stot = 0;
+                if (sany) {
+                    const uint32_t c = __popc(sb);
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += o;
+                    }
+                    spre = inc - c;
+                    stot = __shfl_sync(0xffffffffu, inc, 31);
+                }
+                const int w = ((ch0 + u) << 3) + (lane >> 2);
+                if ((lane & 3) == 0 && w < WW) {
+                    const long wi = row * WW + w;
+                    ws.srcbits[wi] = sw;
+                    ws.valbits[wi] = vw;
+                    ws.wprefix[wi] = (uint16_t)(cs + spre);
+                    ws.rowcell[wi] = (uint8_t)((sany >> lane) & 0xFu);
+                }
+                cs += stot;
+                if (vany) {
+                    const uint32_t c = __popc(vb);
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += o;
+                    }
+                    float* dst = rowvals + row * W + cv + (inc - c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((vb >> j) & 1u) *dst++ = x[j];
+                    cv += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+        }
+        if (lane == 0) {
+            ws.rowsrc[row] = cs;
+            ws.rowval[row] = cv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1 for widths that are not a multiple of 4 (no 128-bit row alignment): same outputs, scalar loads + ballots.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
                                                      uint8_t* __restrict__ out_mask)
@@ -107,6 +214,8 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in
     const int W = fp.W, WW = fp.WW;
     const long nrows = (long)fp.B * fp.H;
     const bool vec_mask = (W & 3) == 0;
+    const uint32_t ltmask = lanemask_lt();
+    float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
         const float* rp = in + row * W;
         uint32_t cs = 0, cv = 0;
@@ -129,6 +238,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in
                 const uint32_t sw = __ballot_sync(0xffffffffu, sp);
                 const uint32_t vw = __ballot_sync(0xffffffffu, vp);
                 if (lane == k) { mys = sw; myv = vw; mypre = cs; }
+                if (vp) rowvals[row * W + cv + __popc(vw & ltmask)] = x[k];
                 cs += __popc(sw);
                 cv += __popc(vw);
                 vq[k & 3] = vw;
@@ -191,7 +301,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict__ in, FrameParams fp, Workspace ws,
+__global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspace ws,
                                                          int32_t* __restrict__ out_counts)
 {
     __shared__ uint32_t sm[9];
@@ -217,34 +327,16 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(const float* __restrict_
     }
     __syncthreads();
 
-    // depth_list = in[valid] in raster order (tools.py:24): one warp per non-empty row, lanes over the words
+    // depth_list = in[valid] in raster order (tools.py:24): K1 left every row's valid depths compacted at the
+    // start of the row's slot in ws.scratch; concatenate the non-empty rows.
     const int lane = tid & 31, wid = tid >> 5;
     float* dl = ws.dlist + (long)b * H * W;
+    const float* rowvals = reinterpret_cast<const float*>(ws.scratch) + (long)b * H * W;
     for (int y = wid; y < H; y += 8) {
         const uint32_t base = rv[y];
         const uint32_t next = (y + 1 < H) ? rv[y + 1] : nval;
-        if (next == base) continue;
-        const long row = (long)b * H + y;
-        uint32_t run = base;
-        for (int w0 = 0; w0 < WW; w0 += 32) {
-            const int w = w0 + lane;
-            uint32_t vb = w < WW ? ws.valbits[row * WW + w] : 0u;
-            const uint32_t cnt = __popc(vb);
-            uint32_t inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            uint32_t dst = run + inc - cnt;
-            const float* src = in + row * W + w * 32;
-            while (vb) {
-                const int bit = __ffs(vb) - 1;
-                vb &= vb - 1;
-                dl[dst++] = src[bit];
-            }
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
+        const uint32_t cnt = next - base;
+        for (uint32_t i = lane; i < cnt; i += 32) dl[base + i] = rowvals[(long)y * W + i];
     }
 
     // ---- task emission -------------------------------------------------------------------------------
@@ -567,38 +659,58 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
         refresh_halo(Bq, lane, init_key);
 
         if (y >= task.r0 && y < task.r1) {
-            // transpose through shared memory so that global stores are row-contiguous
+            // gather depth_list[lbl-1] (tools.py:26) for this lane's own pixels first: PPL independent loads in
+            // flight, neighbouring pixels mostly share a label so they hit the same L1 lines
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) c[i] = __float_as_uint(dl[(Bq.v[i] & LMASK) - 1u]);
+            const long rowpx = fpx + (long)y * W;
+            // transpose through shared memory so that global stores are row-contiguous: keys, then depths
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < PPL / 2; ++j)
                 *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
-            const long rowpx = fpx + (long)y * W;
             if ((W & 3) == 0) {
+                if (out_dt || WANT_LBL) {
+#pragma unroll
+                    for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
+                        const int col = (j * 32 + lane) * 4;
+                        if (col < W) {
+                            const uint4 k = *reinterpret_cast<const uint4*>(&stage[col]);
+                            if (out_dt)
+                                st_stream_v4(out_dt + rowpx + col, __float_as_uint((float)(k.x >> DSH)),
+                                             __float_as_uint((float)(k.y >> DSH)), __float_as_uint((float)(k.z >> DSH)),
+                                             __float_as_uint((float)(k.w >> DSH)));
+                            if (WANT_LBL)
+                                st_stream_v4(out_lbl + rowpx + col, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < PPL / 2; ++j)
+                    *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
                     const int col = (j * 32 + lane) * 4;
                     if (col < W) {
                         const uint4 k = *reinterpret_cast<const uint4*>(&stage[col]);
-                        const float d0 = dl[(k.x & LMASK) - 1u], d1 = dl[(k.y & LMASK) - 1u];
-                        const float d2 = dl[(k.z & LMASK) - 1u], d3 = dl[(k.w & LMASK) - 1u];
-                        st_stream_v4(out_depth + rowpx + col, __float_as_uint(d0), __float_as_uint(d1),
-                                     __float_as_uint(d2), __float_as_uint(d3));
-                        if (out_dt)
-                            st_stream_v4(out_dt + rowpx + col, __float_as_uint((float)(k.x >> DSH)),
-                                         __float_as_uint((float)(k.y >> DSH)), __float_as_uint((float)(k.z >> DSH)),
-                                         __float_as_uint((float)(k.w >> DSH)));
-                        if (WANT_LBL)
-                            st_stream_v4(out_lbl + rowpx + col, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
+                        st_stream_v4(out_depth + rowpx + col, k.x, k.y, k.z, k.w);
                     }
                 }
             } else {
                 for (int col = lane; col < W; col += 32) {
                     const uint32_t k = stage[col];
-                    out_depth[rowpx + col] = dl[(k & LMASK) - 1u];
                     if (out_dt) out_dt[rowpx + col] = (float)(k >> DSH);
                     if (WANT_LBL) out_lbl[rowpx + col] = (int32_t)(k & LMASK);
                 }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < PPL / 2; ++j)
+                    *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
+                __syncwarp();
+                for (int col = lane; col < W; col += 32) out_depth[rowpx + col] = __uint_as_float(stage[col]);
             }
         }
     };
