@@ -662,7 +662,11 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
             // gather depth_list[lbl-1] (tools.py:26) for this lane's own pixels first: PPL independent loads in
             // flight, neighbouring pixels mostly share a label so they hit the same L1 lines
 #pragma unroll
-            for (int i = 0; i < PPL; ++i) c[i] = __float_as_uint(dl[(Bq.v[i] & LMASK) - 1u]);
+            for (int i = 0; i < PPL; ++i) {
+                uint32_t l = Bq.v[i] & LMASK;
+                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) load in range
+                c[i] = __float_as_uint(dl[l - 1u]);
+            }
             const long rowpx = fpx + (long)y * W;
             // transpose through shared memory so that global stores are row-contiguous: keys, then depths
             __syncwarp();
