@@ -147,8 +147,13 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v8(const float* __restrict__
                 if (out_mask && col < W) {
                     const uint32_t lo = ((vb & 0xFu) * 0x00204081u) & 0x01010101u;
                     const uint32_t hi = ((vb >> 4) * 0x00204081u) & 0x01010101u;
-                    if (col + 4 < W) st_stream_v2(out_mask + row * W + col, lo, hi);
-                    else st_stream_u32(out_mask + row * W + col, lo);
+                    uint8_t* mp = out_mask + row * W + col;          // 4-byte aligned; 8-byte only if W % 8 == 0
+                    if ((W & 7) == 0) {
+                        st_stream_v2(mp, lo, hi);
+                    } else {
+                        st_stream_u32(mp, lo);
+                        if (col + 4 < W) st_stream_u32(mp + 4, hi);
+                    }
                 }
                 // 32-bit words from the bytes of 4 neighbouring lanes
                 uint32_t sw = sb << ((lane & 3) * 8), vw = vb << ((lane & 3) * 8);
