@@ -93,15 +93,23 @@ Plan make_plan(int H, int W) {
     return p;
 }
 
+template <int PPL, bool PAD, bool LBL>
+void launch_k2b(bool vec, int grid, cudaStream_t s, const FrameParams& fp, const Workspace& ws, float* od, float* odt,
+                int32_t* ol) {
+    if (vec) k2_chamfer<PPL, PAD, LBL, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+    else k2_chamfer<PPL, PAD, LBL, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+}
+
 template <int PPL>
 void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FrameParams& fp, const Workspace& ws,
                float* od, float* odt, int32_t* ol) {
+    const bool vec = (fp.W & 3) == 0;      // row starts 16-byte aligned: 128-bit output stores
     if (pad) {
-        if (want_lbl) k2_chamfer<PPL, true, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
-        else k2_chamfer<PPL, true, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+        if (want_lbl) launch_k2b<PPL, true, true>(vec, grid, s, fp, ws, od, odt, ol);
+        else launch_k2b<PPL, true, false>(vec, grid, s, fp, ws, od, odt, ol);
     } else {
-        if (want_lbl) k2_chamfer<PPL, false, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
-        else k2_chamfer<PPL, false, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+        if (want_lbl) launch_k2b<PPL, false, true>(vec, grid, s, fp, ws, od, odt, ol);
+        else launch_k2b<PPL, false, false>(vec, grid, s, fp, ws, od, odt, ol);
     }
 }
 
@@ -142,7 +150,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     {   // band planner target: enough independent tasks to give every SM ~16 warps
         int cap = h->band_cap;
         if (cap < 0) {
-            const long want_tasks = (long)h->sm_count * 16;
+            const long want_tasks = (long)h->sm_count * 8;
             const long per_frame = (want_tasks + B - 1) / B;
             cap = per_frame <= 1 ? 0 : (int)((2L * H * 5 / 4) / per_frame);
             if (cap > 0 && cap < 96) cap = 96;

@@ -42,7 +42,7 @@ struct __align__(16) Task {
     int r0, r1;        // rows whose results are written (lo <= r0 < r1 <= hi)
     int kind;
     int scratch_row;   // first row of this task's forward-state scratch
-    int pad_;
+    int fstart;        // first row >= lo holding a source: the forward pass starts here (rows above stay "unreached")
 };
 
 constexpr int MAXT = 16;      // task slots per frame (bands); slot-major layout tasks[slot * B + frame]
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
                 }
                 Task q;
                 q.frame = b; q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
-                q.kind = TASK_CHAMFER; q.scratch_row = scr; q.pad_ = 0;
+                q.kind = TASK_CHAMFER; q.scratch_row = scr; q.fstart = best_lo;
                 scr += best_hi - best_lo;
                 if (scr > fp.scratch_rows_per_frame) ok = false;
                 cost[nt] = prev;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         }
         if (nt == 0) {
             Task q;
-            q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = kind; q.scratch_row = 0; q.pad_ = 0;
+            q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = kind; q.scratch_row = 0; q.fstart = 0;
             cost[0] = 2 * H;
             t[nt++] = q;
         }
@@ -433,13 +433,19 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
             while (j >= 0 && cost[j] < c) { t[j + 1] = t[j]; cost[j + 1] = cost[j]; --j; }
             t[j + 1] = q; cost[j + 1] = c;
         }
+        for (int i = 0; i < nt; ++i) {
+            // rows without any source above them stay unreached in the forward pass: skip them
+            int f = t[i].lo;
+            while (f < t[i].hi - 1 && ((f + 1 < H ? rs[f + 1] : nsrc) == rs[f])) ++f;
+            t[i].fstart = f;
+        }
         for (int i = 0; i < MAXT; ++i) {
             if (i < nt) {
                 t[i].scratch_row += b * fp.scratch_rows_per_frame;
                 ws.tasks[(long)i * B + b] = t[i];
             } else {
                 Task q;
-                q.frame = b; q.lo = q.hi = q.r0 = q.r1 = 0; q.kind = TASK_SKIP; q.scratch_row = 0; q.pad_ = 0;
+                q.frame = b; q.lo = q.hi = q.r0 = q.r1 = 0; q.kind = TASK_SKIP; q.scratch_row = 0; q.fstart = 0;
                 ws.tasks[(long)i * B + b] = q;
             }
         }
@@ -535,7 +541,7 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, uint64
     rank = r.base + r.pre + __popc(r.a & ((1u << sh) - 1u)) + 1u;
 }
 
-template <int PPL, bool PAD, bool WANT_LBL>
+template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
 __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
 {
@@ -572,7 +578,7 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
     fill_row(rb, init_key);
 
     // ---------------- forward pass: rows lo .. hi-1 ----------------
-    RowBits nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, task.lo);
+    RowBits nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, task.fstart);
     auto fwd_step = [&](const Row<PPL>& A /*row y-1*/, Row<PPL>& Bq /*row y-2 in, row y out*/, int y) {
         uint64_t bits; uint32_t rank;
         decode_row_bits<PPL>(nextbits, x0, bits, rank);
@@ -618,9 +624,12 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
         for (int j = 0; j < PPL / 2; ++j) dst[j * 32] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
     };
 
-    for (int y = task.lo; y < task.hi; y += 2) {
+    // one copy of the step in the instruction stream (the unrolled step is ~13 KB of code); the two live rows
+    // are rotated with register moves, which go to the otherwise idle FMA pipe
+#pragma unroll 1
+    for (int y = task.fstart; y < task.hi; ++y) {
         fwd_step(ra, rb, y);
-        if (y + 1 < task.hi) fwd_step(rb, ra, y + 1);
+        const Row<PPL> t = ra; ra = rb; rb = t;
     }
 
     // ---------------- backward pass: rows hi-1 .. r0 ----------------
@@ -631,10 +640,15 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
     auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
         const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
         uint32_t c[PPL];
+        if (y >= task.fstart) {
 #pragma unroll
-        for (int j = 0; j < PPL / 2; ++j) {
-            const uint2 f = src[j * 32];
-            c[2 * j] = f.x; c[2 * j + 1] = f.y;
+            for (int j = 0; j < PPL / 2; ++j) {
+                const uint2 f = src[j * 32];
+                c[2 * j] = f.x; c[2 * j + 1] = f.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) c[i] = init_key;      // rows the forward pass skipped: unreached
         }
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
@@ -679,7 +693,7 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
             for (int j = 0; j < PPL / 2; ++j)
                 *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
-            if ((W & 3) == 0) {
+            if (VEC) {
                 if (out_dt || WANT_LBL) {
 #pragma unroll
                     for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
@@ -724,9 +738,10 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
         }
     };
 
-    for (int y = task.hi - 1; y >= task.r0; y -= 2) {
+#pragma unroll 1
+    for (int y = task.hi - 1; y >= task.r0; --y) {
         bwd_step(ra, rb, y);
-        if (y - 1 >= task.r0) bwd_step(rb, ra, y - 1);
+        const Row<PPL> t = ra; ra = rb; rb = t;
     }
 }
 
