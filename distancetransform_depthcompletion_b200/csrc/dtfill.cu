@@ -175,7 +175,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
         long want = ((long)rows + 7) / 8;
         long cap = (long)h->sm_count * 8 * 4;
         int grid = (int)(want < cap ? want : cap);
-        if ((W & 3) == 0) k1_mask_rows_v8<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
+        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
         else k1_mask_rows<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
         ++launches;
     }

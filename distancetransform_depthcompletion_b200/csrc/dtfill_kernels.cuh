@@ -107,97 +107,114 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // ------------------------------------------------------------------------------------------------------
 // K1 (W % 4 == 0): predicates -> bit rows, per-word source prefix, coarse cells, row counts, validity mask,
 // and the row-local compaction of the valid depths (into ws.scratch, which K2 only uses later).
-// One warp per row; a lane owns 8 consecutive pixels of every 256-pixel chunk (two 128-bit loads), four
-// chunks of loads in flight.  Words of the bit rows are assembled from the lanes' bytes with two butterflies.
+// One warp per row; a lane owns 16 consecutive pixels of every 512-pixel chunk (four 128-bit loads).
+// The predicates are evaluated without branches: a > b  <=>  sign(b - a) for IEEE floats (a NaN operand gives
+// the canonical positive NaN, i.e. "false", like the comparison), and the sign bits of four differences are
+// gathered into a nibble with byte permutes and one multiply.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k1_mask_rows_v8(const float* __restrict__ in, FrameParams fp, Workspace ws,
-                                                        uint8_t* __restrict__ out_mask)
+__device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, float t3)
+{
+    // top bytes of the four floats -> one word -> bits 7,15,23,31 -> nibble (multiply gathers them into 28..31)
+    const uint32_t p01 = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0073);   // [t0.b3, t1.b3, 0, 0]
+    const uint32_t p23 = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0073);
+    const uint32_t w = __byte_perm(p01, p23, 0x5410) & 0x80808080u;
+    return (w * 0x00204081u) >> 28;
+}
+
+__global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                         uint8_t* __restrict__ out_mask)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = fp.W, WW = fp.WW;
     const long nrows = (long)fp.B * fp.H;
-    const int nchunks = (W + 255) >> 8;
+    const int nchunks = (W + 511) >> 9;
+    const float sthr = fp.src_thr, vthr = fp.val_thr;
+    const bool mask16 = (W & 15) == 0;
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
         const float* rp = in + row * W;
         uint32_t cs = 0, cv = 0;
-        for (int ch0 = 0; ch0 < nchunks; ch0 += 4) {
-            float4 xa[4], xb[4];
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int col = (ch << 9) + lane * 16;
+            float4 q[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int col = ((ch0 + u) << 8) + lane * 8;
-                xa[u] = col < W ? ld_stream_v4(rp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[u] = col + 4 < W ? ld_stream_v4(rp + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int g = 0; g < 4; ++g)
+                q[g] = col + 4 * g < W ? __ldg(reinterpret_cast<const float4*>(rp + col + 4 * g))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t sb = 0, vb = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr
+                const float d0 = __fsub_rn(1.0f, q[g].x), d1 = __fsub_rn(1.0f, q[g].y);
+                const float d2 = __fsub_rn(1.0f, q[g].z), d3 = __fsub_rn(1.0f, q[g].w);
+                const uint32_t ns = sign_nibble(__fsub_rn(sthr, d0), __fsub_rn(sthr, d1), __fsub_rn(sthr, d2),
+                                                __fsub_rn(sthr, d3));                       // bit = d > src_thr
+                const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
+                                                __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
+                const uint32_t inb = col + 4 * g < W ? 0xFu : 0u;
+                sb |= ((ns ^ 0xFu) & inb) << (4 * g);
+                vb |= (nv & inb) << (4 * g);
             }
+            if (out_mask && col < W) {
+                uint32_t m[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (ch0 + u >= nchunks) break;
-                const int col = ((ch0 + u) << 8) + lane * 8;
-                const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
-                uint32_t sb = 0, vb = 0;
+                for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                uint8_t* mp = out_mask + row * W + col;
+                if (mask16) {
+                    st_stream_v4(mp, m[0], m[1], m[2], m[3]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool inb = col + (j & 4) < W;                 // whole float4 groups are in or out
-                    const float d = __fsub_rn(1.0f, x[j]);              // tools.py:8  1.0 - x  (float32)
-                    if (inb && !(d > fp.src_thr)) sb |= 1u << j;        // value_mask == 0  <=> source
-                    if (inb && (x[j] > fp.val_thr)) vb |= 1u << j;      // tools.py:22 with_value
+                    for (int g = 0; g < 4; ++g)
+                        if (col + 4 * g < W) st_stream_u32(mp + 4 * g, m[g]);
                 }
-                if (out_mask && col < W) {
-                    const uint32_t lo = ((vb & 0xFu) * 0x00204081u) & 0x01010101u;
-                    const uint32_t hi = ((vb >> 4) * 0x00204081u) & 0x01010101u;
-                    uint8_t* mp = out_mask + row * W + col;          // 4-byte aligned; 8-byte only if W % 8 == 0
-                    if ((W & 7) == 0) {
-                        st_stream_v2(mp, lo, hi);
-                    } else {
-                        st_stream_u32(mp, lo);
-                        if (col + 4 < W) st_stream_u32(mp + 4, hi);
-                    }
-                }
-                // 32-bit words from the bytes of 4 neighbouring lanes
-                uint32_t sw = sb << ((lane & 3) * 8), vw = vb << ((lane & 3) * 8);
-                sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
-                vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
-                sw |= __shfl_xor_sync(0xffffffffu, sw, 2);
-                vw |= __shfl_xor_sync(0xffffffffu, vw, 2);
-                const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);   // bit l: lane l's 8 pixels hold a source
-                const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
-                uint32_t spre = 0, stot = 0;
-                if (sany) {
-                    const uint32_t c = __popc(sb);
-                    uint32_t inc = c;
+            }
+            // 32-bit words from the halves of 2 neighbouring lanes
+            uint32_t sw = sb << ((lane & 1) * 16), vw = vb << ((lane & 1) * 16);
+            sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
+            vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
+            // coarse cells: bit j of the word's nibble = some source among its pixels 8j..8j+7
+            const uint32_t cell = ((sw & 0xFFu) != 0) | (((sw & 0xFF00u) != 0) << 1) | (((sw & 0xFF0000u) != 0) << 2) |
+                                  (((sw & 0xFF000000u) != 0) << 3);
+            const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);
+            const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
+            uint32_t spre = 0, stot = 0;
+            if (sany) {
+                const uint32_t c = __popc(sb);
+                uint32_t inc = c;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                        if (lane >= d) inc += o;
-                    }
-                    spre = inc - c;
-                    stot = __shfl_sync(0xffffffffu, inc, 31);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
                 }
-                const int w = ((ch0 + u) << 3) + (lane >> 2);
-                if ((lane & 3) == 0 && w < WW) {
-                    const long wi = row * WW + w;
-                    ws.srcbits[wi] = sw;
-                    ws.valbits[wi] = vw;
-                    ws.wprefix[wi] = (uint16_t)(cs + spre);
-                    ws.rowcell[wi] = (uint8_t)((sany >> lane) & 0xFu);
-                }
-                cs += stot;
-                if (vany) {
-                    const uint32_t c = __popc(vb);
-                    uint32_t inc = c;
+                spre = inc - c;
+                stot = __shfl_sync(0xffffffffu, inc, 31);
+            }
+            const int w = (ch << 4) + (lane >> 1);
+            if ((lane & 1) == 0 && w < WW) {
+                const long wi = row * WW + w;
+                ws.srcbits[wi] = sw;
+                ws.valbits[wi] = vw;
+                ws.wprefix[wi] = (uint16_t)(cs + spre);
+                ws.rowcell[wi] = (uint8_t)cell;
+            }
+            cs += stot;
+            if (vany) {
+                const uint32_t c = __popc(vb);
+                uint32_t inc = c;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                        if (lane >= d) inc += o;
-                    }
-                    float* dst = rowvals + row * W + cv + (inc - c);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if ((vb >> j) & 1u) *dst++ = x[j];
-                    cv += __shfl_sync(0xffffffffu, inc, 31);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
                 }
+                float* dst = rowvals + row * W + cv + (inc - c);
+                const float x[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                                     q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if ((vb >> j) & 1u) *dst++ = x[j];
+                cv += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         if (lane == 0) {
@@ -312,6 +329,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
     __shared__ uint32_t sm[9];
     __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
     __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
+    __shared__ uint8_t occw[MAX_CELLS / 4 + 1024];   // planner: per cell-row and word, occupancy nibble
     const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
@@ -341,7 +359,20 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         const uint32_t base = rv[y];
         const uint32_t next = (y + 1 < H) ? rv[y + 1] : nval;
         const uint32_t cnt = next - base;
-        for (uint32_t i = lane; i < cnt; i += 32) dl[base + i] = rowvals[(long)y * W + i];
+        const float* src = rowvals + (long)y * W;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32 * 12) {       // 12 loads in flight per lane
+            float v[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const uint32_t i = i0 + k * 32 + lane;
+                v[k] = i < cnt ? src[i] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const uint32_t i = i0 + k * 32 + lane;
+                if (i < cnt) dl[base + i] = v[k];
+            }
+        }
     }
 
     // ---- task emission -------------------------------------------------------------------------------
@@ -353,16 +384,22 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
                       2 * H > fp.band_cap;
     if (plan) {
         // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
+        // rowcell nibbles of CELL_H consecutive rows OR-ed per word, then one distance cell per bit
         const uint8_t* rc = ws.rowcell + (long)b * H * WW;
-        for (int i = tid; i < nh * nw; i += 256) {
-            const int cy = i / nw, cx = i - cy * nw;
-            uint32_t occ = 0;
+        for (int i = tid; i < nh * WW; i += 256) {
+            const int cy = i / WW, w = i - cy * WW;
+            uint32_t o = 0;
 #pragma unroll
             for (int r = 0; r < CELL_H; ++r) {
                 const int y = cy * CELL_H + r;
-                if (y < H) occ |= (rc[(long)y * WW + (cx >> 2)] >> (cx & 3)) & 1u;
+                if (y < H) o |= rc[(long)y * WW + w];
             }
-            cellD[i] = occ ? 0 : 60000;
+            occw[i] = (uint8_t)o;
+        }
+        __syncthreads();
+        for (int i = tid; i < nh * nw; i += 256) {
+            const int cy = i / nw, cx = i - cy * nw;
+            cellD[i] = ((occw[cy * WW + (cx >> 2)] >> (cx & 3)) & 1u) ? 0 : 60000;
         }
         __syncthreads();
         for (int cx = tid; cx < nw; cx += 256) {
