@@ -208,6 +208,8 @@ def run_ours(args, rank, world, local_rank):
     eng = DTFillEngine(local_rank)
     if args.band_cap is not None:
         eng.handle.set_band_cap(args.band_cap)
+    if args.subbatches is not None:
+        eng.handle.set_subbatches(args.subbatches)
     out = dict(depth=torch.empty((B, H, W), dtype=torch.float32, device=dev),
                dt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
                mask=torch.empty((B, H, W), dtype=torch.uint8, device=dev),
@@ -343,6 +345,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
+    ap.add_argument("--subbatches", type=int, default=None, help="override the number of sub-batch streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -54,12 +54,13 @@ def load() -> ctypes.CDLL:
         L.dtfill_metrics.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
+        L.dtfill_set_subbatches.argtypes = [vp, ci]
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
-                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap",
+                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
@@ -162,6 +163,10 @@ class Handle:
     def set_band_cap(self, cap: int):
         """Band planner target (row steps per task): >0 explicit, 0 never split frames, -1 automatic."""
         _check(self._L.dtfill_set_band_cap(self._h, int(cap)), "dtfill_set_band_cap")
+
+    def set_subbatches(self, n: int):
+        """Number of sub-batches run on forked streams (<= 0: automatic)."""
+        _check(self._L.dtfill_set_subbatches(self._h, int(n)), "dtfill_set_subbatches")
 
     def set_profiling(self, enabled: bool):
         _check(self._L.dtfill_set_profiling(self._h, int(bool(enabled))), "dtfill_set_profiling")

@@ -47,6 +47,10 @@ struct dtfill_ctx {
     int last_launches = 0;
     int last_B = 0;
     bool profiling = false;
+    static const int MAX_SUB = 8;
+    cudaStream_t sub[MAX_SUB] = {};     // sub-batch streams: K2 (ALU bound) of one sub-batch overlaps K1 (HBM bound) of the next
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
+    int nsub = -1;                // -1: automatic
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
 };
@@ -113,6 +117,82 @@ void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FramePar
     }
 }
 
+// Enqueue the path for frames [b0, b0+nb) of the batch on stream s; all pointers are device pointers to the whole
+// batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
+int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
+                  float src_thr, float val_thr, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
+                  int32_t* out_counts, int scratch_rows_per_frame, int* launches) {
+    const int WW = (W + 31) / 32;
+    const size_t rows0 = (size_t)b0 * H, npx0 = rows0 * W;
+    const size_t rows = (size_t)nb * H;
+    FrameParams fp;
+    fp.B = nb; fp.H = H; fp.W = W; fp.WW = WW;
+    fp.src_thr = src_thr; fp.val_thr = val_thr;
+    fp.init_dist = H + W + 8;
+    fp.force_wide = plan.ppl == 0;
+    fp.scratch_rows_per_frame = scratch_rows_per_frame;
+    fp.frame0 = b0;
+    {   // band planner target: enough independent tasks to give every SM ~8 warps over the whole batch
+        int cap = h->band_cap;
+        if (cap < 0) {
+            const long want_tasks = (long)h->sm_count * 8;
+            const long per_frame = (want_tasks + Btot - 1) / Btot;
+            cap = per_frame <= 1 ? 0 : (int)((2L * H * 5 / 4) / per_frame);
+            if (cap > 0 && cap < 96) cap = 96;
+        }
+        fp.band_cap = plan.ppl ? cap : 0;
+    }
+    const size_t scratch_row_words = (size_t)(plan.ppl ? plan.wp : W);
+    Workspace ws;
+    ws.srcbits = (uint32_t*)h->srcbits.p + rows0 * WW;
+    ws.valbits = (uint32_t*)h->valbits.p + rows0 * WW;
+    ws.wprefix = (uint16_t*)h->wprefix.p + rows0 * WW;
+    ws.rowcell = (uint8_t*)h->rowcell.p + rows0 * WW;
+    ws.rowsrc = (uint32_t*)h->rowsrc.p + rows0;
+    ws.rowval = (uint32_t*)h->rowval.p + rows0;
+    ws.counts = (int32_t*)h->counts.p + 2 * (size_t)b0;
+    ws.dlist = (float*)h->dlist.p + npx0;
+    ws.scratch = (uint32_t*)h->scratch.p + (size_t)b0 * scratch_rows_per_frame * scratch_row_words;
+    ws.tasks = (Task*)h->tasks.p + (size_t)b0 * MAXT;
+    ws.status = (int*)h->status.p;
+    const float* in_s = in + npx0;
+    float* od = out_depth + npx0;
+    float* odt = out_dt ? out_dt + npx0 : nullptr;
+    int32_t* ol = out_lbl ? out_lbl + npx0 : nullptr;
+    uint8_t* om = out_mask ? out_mask + npx0 : nullptr;
+    int32_t* oc = out_counts ? out_counts + 2 * (size_t)b0 : nullptr;
+
+    if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
+    {   // K1: one warp per row
+        long want = ((long)rows + 7) / 8;
+        int grid = (int)(want < 1 ? 1 : want);
+        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
+        else k1_mask_rows<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
+        ++*launches;
+    }
+    if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
+    k1b_scan_compact<<<nb, 256, 0, s>>>(fp, ws, oc);
+    ++*launches;
+    if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
+
+    const bool want_lbl = ol != nullptr;
+    switch (plan.ppl) {
+        case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
+        case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
+        case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
+        default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;  // NOSRC frames only
+    }
+    ++*launches;
+    if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
+    {   // wide fallback: returns immediately for every task the fast kernel handled
+        const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
+        k2_chamfer_wide<<<nb, 32, smem, s>>>(fp, ws, od, odt, ol);
+        ++*launches;
+    }
+    if (h->profiling) CU(cudaEventRecord(h->ev[4], s));
+    return 0;
+}
+
 // Enqueue the whole path on h->stream; all pointers are device pointers.
 int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
             float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts) {
@@ -140,72 +220,43 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, h->scratch, (size_t)B * scratch_rows_per_frame * (size_t)(plan.ppl ? plan.wp : W) * 4))) return rc;
     if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, h->status, 16))) return rc;
-
-    FrameParams fp;
-    fp.B = B; fp.H = H; fp.W = W; fp.WW = WW;
-    fp.src_thr = src_thr; fp.val_thr = val_thr;
-    fp.init_dist = H + W + 8;
-    fp.force_wide = plan.ppl == 0;
-    fp.scratch_rows_per_frame = scratch_rows_per_frame;
-    {   // band planner target: enough independent tasks to give every SM ~16 warps
-        int cap = h->band_cap;
-        if (cap < 0) {
-            const long want_tasks = (long)h->sm_count * 8;
-            const long per_frame = (want_tasks + B - 1) / B;
-            cap = per_frame <= 1 ? 0 : (int)((2L * H * 5 / 4) / per_frame);
-            if (cap > 0 && cap < 96) cap = 96;
+    {
+        const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
+        static size_t configured = 0;
+        if (smem > 227 * 1024) return fail(DTFILL_E_ARG, "dtfill_run: frame too wide for the wide path");
+        if (smem > 48 * 1024 && smem > configured) {
+            CU(cudaFuncSetAttribute(k2_chamfer_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
         }
-        fp.band_cap = plan.ppl ? cap : 0;
     }
-    Workspace ws;
-    ws.srcbits = (uint32_t*)h->srcbits.p; ws.valbits = (uint32_t*)h->valbits.p; ws.wprefix = (uint16_t*)h->wprefix.p;
-    ws.rowcell = (uint8_t*)h->rowcell.p;
-    ws.rowsrc = (uint32_t*)h->rowsrc.p; ws.rowval = (uint32_t*)h->rowval.p; ws.counts = (int32_t*)h->counts.p;
-    ws.dlist = (float*)h->dlist.p; ws.scratch = (uint32_t*)h->scratch.p; ws.tasks = (Task*)h->tasks.p;
-    ws.status = (int*)h->status.p;
 
     cudaStream_t s = h->stream;
     int launches = 0;
     h->status_host[0] = INT_MAX;
     h->status_host[1] = 0;
-    CU(cudaMemcpyAsync(ws.status, h->status_host, 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->status.p, h->status_host, 8, cudaMemcpyHostToDevice, s));
 
-    if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
-    {   // K1: enough warps to keep HBM busy, a whole number of waves of 8-warp blocks
-        long want = ((long)rows + 7) / 8;
-        long cap = (long)h->sm_count * 8 * 4;
-        int grid = (int)(want < cap ? want : cap);
-        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
-        else k1_mask_rows<<<grid, 256, 0, s>>>(in, fp, ws, out_mask);
-        ++launches;
-    }
-    if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
-    k1b_scan_compact<<<B, 256, 0, s>>>(fp, ws, out_counts);
-    ++launches;
-    if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
-
-    const bool want_lbl = out_lbl != nullptr;
-    switch (plan.ppl) {
-        case 10: launch_k2<10>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        case 20: launch_k2<20>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        case 38: launch_k2<38>(plan.pad, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;
-        default: launch_k2<10>(true, want_lbl, B * MAXT, s, fp, ws, out_depth, out_dt, out_lbl); break;  // NOSRC frames only
-    }
-    ++launches;
-    if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
-    {   // wide fallback: returns immediately for every task the fast kernel handled
-        const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            CU(cudaFuncSetAttribute(k2_chamfer_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+    // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
+    int nsub = h->nsub;
+    if (nsub < 0) nsub = B >= 64 ? 4 : (B >= 16 ? 2 : 1);
+    if (nsub > dtfill_ctx::MAX_SUB) nsub = dtfill_ctx::MAX_SUB;
+    if (nsub > B) nsub = B;
+    if (h->profiling || nsub < 1) nsub = 1;
+    if (nsub == 1) {
+        if ((rc = enqueue_range(h, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
+                                out_counts, scratch_rows_per_frame, &launches))) return rc;
+    } else {
+        CU(cudaEventRecord(h->fork_ev, s));
+        for (int i = 0; i < nsub; ++i) {
+            const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
+            CU(cudaStreamWaitEvent(h->sub[i], h->fork_ev, 0));
+            if ((rc = enqueue_range(h, h->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
+                                    out_lbl, out_mask, out_counts, scratch_rows_per_frame, &launches))) return rc;
+            CU(cudaEventRecord(h->join_ev[i], h->sub[i]));
+            CU(cudaStreamWaitEvent(s, h->join_ev[i], 0));
         }
-        if (smem > 227 * 1024) return fail(DTFILL_E_ARG, "dtfill_run: frame too wide for the wide path");
-        k2_chamfer_wide<<<B, 32, smem, s>>>(fp, ws, out_depth, out_dt, out_lbl);
-        ++launches;
     }
-    if (h->profiling) CU(cudaEventRecord(h->ev[4], s));
-    CU(cudaMemcpyAsync(h->status_host, ws.status, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->status_host, h->status.p, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     h->last_launches = launches;
     h->last_B = B;
@@ -241,6 +292,12 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     h->stream = h->own_stream;
     CU(cudaHostAlloc((void**)&h->status_host, 16, cudaHostAllocDefault));
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
+        CU(cudaStreamCreateWithFlags(&h->sub[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
     h->status_host[0] = INT_MAX;
     h->status_host[1] = 0;
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
@@ -260,6 +317,11 @@ void dtfill_destroy(dtfill_t* h) {
     if (h->status_host) cudaFreeHost(h->status_host);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
+        if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
+        if (h->sub[i]) cudaStreamDestroy(h->sub[i]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -384,6 +446,12 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
 int dtfill_set_band_cap(dtfill_t* h, int cap) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_band_cap: NULL handle");
     h->band_cap = cap;
+    return 0;
+}
+
+int dtfill_set_subbatches(dtfill_t* h, int n) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_subbatches: NULL handle");
+    h->nsub = n;
     return 0;
 }
 

@@ -57,6 +57,7 @@ struct FrameParams {
     int force_wide;            // size not representable in the 32-bit key
     int band_cap;              // planner: target cost (row steps) of one task; <= 0 disables banding
     int scratch_rows_per_frame;  // capacity of the forward-state scratch per frame (rows)
+    int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
 };
 
 struct Workspace {
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         ws.counts[2 * b + 1] = (int)nval;
         if (out_counts) { out_counts[2 * b] = (int)nsrc; out_counts[2 * b + 1] = (int)nval; }
         // numpy's IndexError: empty depth_list, or a label beyond its end (tools.py:26)
-        if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b);
+        if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b + fp.frame0);
         if (kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
 
         Task t[MAXT];

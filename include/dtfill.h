@@ -114,6 +114,11 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
  * one band in row steps; 0: never split; -1 (default): chosen from the batch size and the SM count. */
 int dtfill_set_band_cap(dtfill_t* h, int cap);
 
+/* A batch is processed as n sub-batches on forked streams so that the ALU-bound scan of one overlaps the
+ * HBM-bound predicate pass of the next (joined back into the handle's stream before the call returns / the
+ * async call's work is complete).  n <= 0: automatic (4 for batches of 64 frames or more). */
+int dtfill_set_subbatches(dtfill_t* h, int n);
+
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
  * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide into ms[0..3]. */

@@ -117,6 +117,21 @@ def test_band_splitting_is_exact(handle, cap):
         handle.set_band_cap(-1)
 
 
+@pytest.mark.parametrize("nsub", [1, 2, 3, 8])
+def test_subbatch_streams(handle, nsub):
+    """Sub-batches on forked streams: same results, and a bad frame is reported with its index in the batch."""
+    handle.set_subbatches(nsub)
+    try:
+        x = np.stack([synth.kitti_frame(700 + i, beam_step=(1, 2, 4, 8)[i % 4])[100:228, :640] for i in range(11)])
+        _check_frames(handle, np.ascontiguousarray(x), 0.1, 0.1)
+        x[9] = 0.0
+        x[10] = 0.0
+        r = handle.run_host(np.ascontiguousarray(x), 0.1, 0.1)
+        assert "index_error" in r and r["first_bad"] == 9
+    finally:
+        handle.set_subbatches(-1)
+
+
 def test_golden_full_frames(handle, golden_dir):
     z = np.load(os.path.join(golden_dir, "full_frames.npz"))
     for name, x, thr in (("kitti64_seed0", synth.kitti_frame(0), 0.1),
