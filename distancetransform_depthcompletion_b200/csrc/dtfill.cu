@@ -50,6 +50,9 @@ struct dtfill_ctx {
     static const int MAX_SUB = 8;
     cudaStream_t sub[MAX_SUB] = {};     // sub-batch streams: K2 (ALU bound) of one sub-batch overlaps K1 (HBM bound) of the next
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
+    cudaStream_t side[MAX_SUB] = {};    // half-width tiles run next to the full-width tasks of the same sub-batch
+    cudaEvent_t side_fork[MAX_SUB] = {}, side_join[MAX_SUB] = {};
+    bool tiles2d = true;
     int nsub = -1;                // -1: automatic
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
@@ -76,9 +79,10 @@ int ensure(dtfill_t* h, Buf& b, size_t bytes) {
 }
 
 struct Plan {
-    int ppl = 0;        // 0: wide path only
+    int ppl = 0;        // pixels per lane of the full-width instance; 0: 64-bit-key path only
     bool pad = false;
     int wp = 0;         // padded row width of the scratch
+    int narrow = 0;     // pixels per lane of the half-width instance (two overlapping tiles per band), 0: none
 };
 
 Plan make_plan(int H, int W) {
@@ -89,6 +93,9 @@ Plan make_plan(int H, int W) {
             p.ppl = c;
             p.pad = (W != 32 * c);
             p.wp = 32 * c;
+            // half-width tiles need an overlap: two tiles of 32*narrow columns must cover W with room for halos
+            if (c == 38 && W > 640 + 16 && (W & 3) == 0) p.narrow = 20;
+            if (c == 20 && W > 320 + 16 && W <= 640 - 48 && (W & 3) == 0) p.narrow = 10;
             return p;
         }
     }
@@ -99,21 +106,21 @@ Plan make_plan(int H, int W) {
 
 template <int PPL, bool PAD, bool LBL>
 void launch_k2b(bool vec, int grid, cudaStream_t s, const FrameParams& fp, const Workspace& ws, float* od, float* odt,
-                int32_t* ol) {
-    if (vec) k2_chamfer<PPL, PAD, LBL, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
-    else k2_chamfer<PPL, PAD, LBL, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol);
+                int32_t* ol, int kind) {
+    if (vec) k2_chamfer<PPL, PAD, LBL, true><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol, kind);
+    else k2_chamfer<PPL, PAD, LBL, false><<<grid, 32, 0, s>>>(fp, ws, od, odt, ol, kind);
 }
 
 template <int PPL>
 void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FrameParams& fp, const Workspace& ws,
-               float* od, float* odt, int32_t* ol) {
+               float* od, float* odt, int32_t* ol, int kind) {
     const bool vec = (fp.W & 3) == 0;      // row starts 16-byte aligned: 128-bit output stores
     if (pad) {
-        if (want_lbl) launch_k2b<PPL, true, true>(vec, grid, s, fp, ws, od, odt, ol);
-        else launch_k2b<PPL, true, false>(vec, grid, s, fp, ws, od, odt, ol);
+        if (want_lbl) launch_k2b<PPL, true, true>(vec, grid, s, fp, ws, od, odt, ol, kind);
+        else launch_k2b<PPL, true, false>(vec, grid, s, fp, ws, od, odt, ol, kind);
     } else {
-        if (want_lbl) launch_k2b<PPL, false, true>(vec, grid, s, fp, ws, od, odt, ol);
-        else launch_k2b<PPL, false, false>(vec, grid, s, fp, ws, od, odt, ol);
+        if (want_lbl) launch_k2b<PPL, false, true>(vec, grid, s, fp, ws, od, odt, ol, kind);
+        else launch_k2b<PPL, false, false>(vec, grid, s, fp, ws, od, odt, ol, kind);
     }
 }
 
@@ -121,7 +128,7 @@ void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FramePar
 // batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
 int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
                   float src_thr, float val_thr, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
-                  int32_t* out_counts, int scratch_rows_per_frame, int* launches) {
+                  int32_t* out_counts, int scratch_units_per_frame, int sub_index, int* launches) {
     const int WW = (W + 31) / 32;
     const size_t rows0 = (size_t)b0 * H, npx0 = rows0 * W;
     const size_t rows = (size_t)nb * H;
@@ -130,7 +137,9 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     fp.src_thr = src_thr; fp.val_thr = val_thr;
     fp.init_dist = H + W + 8;
     fp.force_wide = plan.ppl == 0;
-    fp.scratch_rows_per_frame = scratch_rows_per_frame;
+    fp.scratch_units_per_frame = scratch_units_per_frame;
+    fp.wide_ppl = plan.ppl ? plan.ppl : 1;
+    fp.narrow_ppl = (h->tiles2d && plan.ppl) ? plan.narrow : 0;
     fp.frame0 = b0;
     {   // band planner target: enough independent tasks to give every SM ~8 warps over the whole batch
         int cap = h->band_cap;
@@ -142,7 +151,6 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
         }
         fp.band_cap = plan.ppl ? cap : 0;
     }
-    const size_t scratch_row_words = (size_t)(plan.ppl ? plan.wp : W);
     Workspace ws;
     ws.srcbits = (uint32_t*)h->srcbits.p + rows0 * WW;
     ws.valbits = (uint32_t*)h->valbits.p + rows0 * WW;
@@ -152,7 +160,7 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     ws.rowval = (uint32_t*)h->rowval.p + rows0;
     ws.counts = (int32_t*)h->counts.p + 2 * (size_t)b0;
     ws.dlist = (float*)h->dlist.p + npx0;
-    ws.scratch = (uint32_t*)h->scratch.p + (size_t)b0 * scratch_rows_per_frame * scratch_row_words;
+    ws.scratch = (uint32_t*)h->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
     ws.tasks = (Task*)h->tasks.p + (size_t)b0 * MAXT;
     ws.status = (int*)h->status.p;
     const float* in_s = in + npx0;
@@ -176,13 +184,25 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
     const bool want_lbl = ol != nullptr;
+    // half-width tiles run on a side stream next to the full-width tasks (different kernel instances)
+    cudaStream_t s2 = s;
+    if (fp.narrow_ppl) {
+        s2 = h->side[sub_index];
+        CU(cudaEventRecord(h->side_fork[sub_index], s));
+        CU(cudaStreamWaitEvent(s2, h->side_fork[sub_index], 0));
+        if (fp.narrow_ppl == 20) launch_k2<20>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
+        else launch_k2<10>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
+        ++*launches;
+        CU(cudaEventRecord(h->side_join[sub_index], s2));
+    }
     switch (plan.ppl) {
-        case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
-        case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
-        case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;
-        default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol); break;  // NOSRC frames only
+        case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;  // NOSRC only
     }
     ++*launches;
+    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, h->side_join[sub_index], 0));
     if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
     {   // wide fallback: returns immediately for every task the fast kernel handled
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
@@ -215,9 +235,10 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, h->rowval, rows * 4))) return rc;
     if ((rc = ensure(h, h->counts, (size_t)B * 8))) return rc;
     if ((rc = ensure(h, h->dlist, npx * 4))) return rc;
-    // forward-state scratch: bands overlap by their halos, so allow up to 2 H rows per frame
-    const int scratch_rows_per_frame = plan.ppl ? 2 * H : H;
-    if ((rc = ensure(h, h->scratch, (size_t)B * scratch_rows_per_frame * (size_t)(plan.ppl ? plan.wp : W) * 4))) return rc;
+    // forward-state scratch in units of 32 keys: tiles overlap by their halos, so allow 2.5 H full-width rows per
+    // frame (the 64-bit-key path keeps one u32 per pixel there; K1 parks H*W floats there as well)
+    const int scratch_units_per_frame = plan.ppl ? (5 * H * plan.ppl + 1) / 2 : (int)(((size_t)H * W + 31) / 32);
+    if ((rc = ensure(h, h->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, h->status, 16))) return rc;
     {
@@ -238,20 +259,20 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
-    if (nsub < 0) nsub = B >= 64 ? 4 : (B >= 16 ? 2 : 1);
+    if (nsub <= 0) nsub = 1;      // measured: sub-batches do not pay, the scan is bound by per-task latency
     if (nsub > dtfill_ctx::MAX_SUB) nsub = dtfill_ctx::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
     if (nsub == 1) {
         if ((rc = enqueue_range(h, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
-                                out_counts, scratch_rows_per_frame, &launches))) return rc;
+                                out_counts, scratch_units_per_frame, 0, &launches))) return rc;
     } else {
         CU(cudaEventRecord(h->fork_ev, s));
         for (int i = 0; i < nsub; ++i) {
             const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
             CU(cudaStreamWaitEvent(h->sub[i], h->fork_ev, 0));
             if ((rc = enqueue_range(h, h->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
-                                    out_lbl, out_mask, out_counts, scratch_rows_per_frame, &launches))) return rc;
+                                    out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return rc;
             CU(cudaEventRecord(h->join_ev[i], h->sub[i]));
             CU(cudaStreamWaitEvent(s, h->join_ev[i], 0));
         }
@@ -296,7 +317,11 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
         CU(cudaStreamCreateWithFlags(&h->sub[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->side_fork[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->side_join[i], cudaEventDisableTiming));
     }
+    if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
     h->status_host[0] = INT_MAX;
     h->status_host[1] = 0;
@@ -321,6 +346,9 @@ void dtfill_destroy(dtfill_t* h) {
     for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
         if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
         if (h->sub[i]) cudaStreamDestroy(h->sub[i]);
+        if (h->side_fork[i]) cudaEventDestroy(h->side_fork[i]);
+        if (h->side_join[i]) cudaEventDestroy(h->side_join[i]);
+        if (h->side[i]) cudaStreamDestroy(h->side[i]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;

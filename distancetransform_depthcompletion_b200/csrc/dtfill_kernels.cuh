@@ -34,18 +34,26 @@ __host__ __device__ constexpr uint32_t KC(int cost, int order) {
     return (uint32_t(cost) << DSH) | (uint32_t(order) << OSH);
 }
 
-enum TaskKind : int { TASK_CHAMFER = 0, TASK_NOSRC = 1, TASK_WIDE = 2, TASK_SKIP = 3 };
+// TASK_CHAMFER: full-width tile, the kernel instance with the frame's PPL.  TASK_NARROW: half-width tile, the
+// instance with the narrow PPL.  TASK_WIDE: 64-bit-key fallback.  TASK_NOSRC: frame without sources.
+enum TaskKind : int { TASK_CHAMFER = 0, TASK_NOSRC = 1, TASK_WIDE = 2, TASK_SKIP = 3, TASK_NARROW = 4 };
 
+// A tile of one frame: the sub-image rows [lo,hi) x columns [clo, clo + 32*PPL) is scanned as if it were the whole
+// image; results are written for rows [r0,r1) x columns [c0,c1) only.  Exact because every written pixel's
+// city-block ball of radius dt lies inside the sub-image (halo >= a guaranteed bound of dt).
 struct __align__(16) Task {
     int frame;
-    int lo, hi;        // rows processed as if they were the whole image (band + halo)
+    int lo, hi;        // sub-image rows (band + halo)
     int r0, r1;        // rows whose results are written (lo <= r0 < r1 <= hi)
     int kind;
-    int scratch_row;   // first row of this task's forward-state scratch
+    int scratch_off;   // start of this task's forward-state scratch, in units of 32 keys
     int fstart;        // first row >= lo holding a source: the forward pass starts here (rows above stay "unreached")
+    int clo;           // first column of the sub-image
+    int c0, c1;        // columns whose results are written
+    int pad_;
 };
 
-constexpr int MAXT = 16;      // task slots per frame (bands); slot-major layout tasks[slot * B + frame]
+constexpr int MAXT = 32;      // task slots per frame; slot-major layout tasks[slot * B + frame]
 constexpr int CELL_H = 4;     // coarse occupancy cells used by the band planner
 constexpr int CELL_W = 8;
 constexpr int MAX_CELLS = 15360;   // planner grid limit (30 KB of shared memory); larger frames are not banded
@@ -56,7 +64,9 @@ struct FrameParams {
     int init_dist;             // "unreached" distance of the fast path: H + W + 8
     int force_wide;            // size not representable in the 32-bit key
     int band_cap;              // planner: target cost (row steps) of one task; <= 0 disables banding
-    int scratch_rows_per_frame;  // capacity of the forward-state scratch per frame (rows)
+    int scratch_units_per_frame; // capacity of the forward-state scratch per frame, in units of 32 keys
+    int wide_ppl;              // pixels per lane of the full-width kernel instance (scratch units per row)
+    int narrow_ppl;            // pixels per lane of the half-width instance, 0 if frames are never split in columns
     int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
 };
 
@@ -432,37 +442,57 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         Task t[MAXT];
         int cost[MAXT];
         int nt = 0;
+        auto blank = [&](int knd) {
+            Task q;
+            q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = knd; q.scratch_off = 0; q.fstart = 0;
+            q.clo = 0; q.c0 = 0; q.c1 = W; q.pad_ = 0;
+            return q;
+        };
         if (plan) {
+            const int nwid = fp.narrow_ppl * 32;                 // width of a half-width tile (0: never split)
+            const int csplit = (W / 2) & ~3;
             int cy = 0, scr = 0;
             bool ok = true;
             while (cy < nh && ok) {
                 const int r0 = cy * CELL_H;
-                int lo = 1 << 30, hi = 0, prev = 0, end = cy, best_lo = 0, best_hi = 0;
+                int lo = 1 << 30, hi = 0, prev = 0, end = cy, best_lo = 0, best_hi = 0, umax = 0, best_u = 0;
                 for (int c = cy; c < nh; ++c) {
                     lo = min(lo, c * CELL_H - cellU[c]);
                     hi = max(hi, min(H, (c + 1) * CELL_H) + cellU[c]);
+                    umax = max(umax, cellU[c]);
                     const int L = max(0, lo), Hh = min(H, hi);
                     const int cst = (Hh - L) + (Hh - r0);
-                    const bool take = c == cy || nt == MAXT - 1 || cst <= fp.band_cap || cst - prev <= CELL_H;
+                    const bool take = c == cy || nt >= MAXT - 2 || cst <= fp.band_cap || cst - prev <= CELL_H;
                     if (!take) break;
-                    prev = cst; end = c + 1; best_lo = L; best_hi = Hh;
+                    prev = cst; end = c + 1; best_lo = L; best_hi = Hh; best_u = umax;
                 }
-                Task q;
-                q.frame = b; q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
-                q.kind = TASK_CHAMFER; q.scratch_row = scr; q.fstart = best_lo;
-                scr += best_hi - best_lo;
-                if (scr > fp.scratch_rows_per_frame) ok = false;
-                cost[nt] = prev;
-                t[nt++] = q;
+                Task q = blank(TASK_CHAMFER);
+                q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
+                // two overlapping half-width tiles when the bound leaves every written pixel's ball inside its tile
+                const bool split = nwid > 0 && W > nwid && 2 * nwid >= W && csplit + best_u <= nwid &&
+                                   csplit - best_u >= W - nwid && nt + 2 <= MAXT;
+                if (split) {
+                    q.kind = TASK_NARROW;
+                    q.clo = 0; q.c0 = 0; q.c1 = csplit; q.scratch_off = scr;
+                    scr += (best_hi - best_lo) * fp.narrow_ppl;
+                    cost[nt] = prev; t[nt++] = q;
+                    q.clo = W - nwid; q.c0 = csplit; q.c1 = W; q.scratch_off = scr;
+                    scr += (best_hi - best_lo) * fp.narrow_ppl;
+                    cost[nt] = prev; t[nt++] = q;
+                } else {
+                    q.scratch_off = scr;
+                    scr += (best_hi - best_lo) * fp.wide_ppl;
+                    cost[nt] = 2 * prev;                      // twice the work per row step of a half-width tile
+                    t[nt++] = q;
+                }
+                if (scr > fp.scratch_units_per_frame) ok = false;
                 cy = end;
             }
             if (!ok) nt = 0;
         }
         if (nt == 0) {
-            Task q;
-            q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = kind; q.scratch_row = 0; q.fstart = 0;
-            cost[0] = 2 * H;
-            t[nt++] = q;
+            cost[0] = 4 * H;
+            t[nt++] = blank(kind);
         }
         // longest task first: the block scheduler hands out blocks in index order (slot-major task array)
         for (int i = 1; i < nt; ++i) {
@@ -479,11 +509,11 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         }
         for (int i = 0; i < MAXT; ++i) {
             if (i < nt) {
-                t[i].scratch_row += b * fp.scratch_rows_per_frame;
+                t[i].scratch_off += b * fp.scratch_units_per_frame;
                 ws.tasks[(long)i * B + b] = t[i];
             } else {
-                Task q;
-                q.frame = b; q.lo = q.hi = q.r0 = q.r1 = 0; q.kind = TASK_SKIP; q.scratch_row = 0; q.fstart = 0;
+                Task q = blank(TASK_SKIP);
+                q.hi = q.r1 = 0;
                 ws.tasks[(long)i * B + b] = q;
             }
         }
@@ -580,12 +610,12 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, uint64
 }
 
 template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
-__global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
-                                                  float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
+__global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+                                                  float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
     __shared__ __align__(16) uint32_t stage[32 * PPL];
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
-    if (task.kind == TASK_WIDE || task.kind == TASK_SKIP) return;
+    if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
     const int lane = threadIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int b = task.frame;
@@ -603,13 +633,14 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
         return;
     }
 
-    const int x0 = lane * PPL;
+    const int x0 = task.clo + lane * PPL;        // first image column of this lane
+    const int xl = lane * PPL;                   // same, relative to the tile
     const uint32_t init_key = (uint32_t)fp.init_dist << DSH;
     const uint32_t clamp_dist = 2047u - PPL - 1u;
     const uint32_t* bits_f = ws.srcbits + (long)b * H * WW;
     const uint16_t* pre_f = ws.wprefix + (long)b * H * WW;
     const uint32_t* rowbase = ws.rowsrc + (long)b * H;
-    uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_row * (16 * PPL);  // PPL/2 uint2 per lane per row
+    uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_off * 16;   // PPL/2 uint2 per lane per row
 
     Row<PPL> ra, rb;
     fill_row(ra, init_key);
@@ -729,15 +760,16 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < PPL / 2; ++j)
-                *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+                *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
             if (VEC) {
                 if (out_dt || WANT_LBL) {
 #pragma unroll
                     for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
-                        const int col = (j * 32 + lane) * 4;
-                        if (col < W) {
-                            const uint4 k = *reinterpret_cast<const uint4*>(&stage[col]);
+                        const int lc = (j * 32 + lane) * 4;
+                        const int col = task.clo + lc;
+                        if (lc < 32 * PPL && col >= task.c0 && col < task.c1) {
+                            const uint4 k = *reinterpret_cast<const uint4*>(&stage[lc]);
                             if (out_dt)
                                 st_stream_v4(out_dt + rowpx + col, __float_as_uint((float)(k.x >> DSH)),
                                              __float_as_uint((float)(k.y >> DSH)), __float_as_uint((float)(k.z >> DSH)),
@@ -750,28 +782,35 @@ __global__ void __launch_bounds__(32, 16) k2_chamfer(FrameParams fp, Workspace w
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < PPL / 2; ++j)
-                    *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
+                    *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
-                    const int col = (j * 32 + lane) * 4;
-                    if (col < W) {
-                        const uint4 k = *reinterpret_cast<const uint4*>(&stage[col]);
+                    const int lc = (j * 32 + lane) * 4;
+                    const int col = task.clo + lc;
+                    if (lc < 32 * PPL && col >= task.c0 && col < task.c1) {
+                        const uint4 k = *reinterpret_cast<const uint4*>(&stage[lc]);
                         st_stream_v4(out_depth + rowpx + col, k.x, k.y, k.z, k.w);
                     }
                 }
             } else {
-                for (int col = lane; col < W; col += 32) {
-                    const uint32_t k = stage[col];
-                    if (out_dt) out_dt[rowpx + col] = (float)(k >> DSH);
-                    if (WANT_LBL) out_lbl[rowpx + col] = (int32_t)(k & LMASK);
+                for (int lc = lane; lc < 32 * PPL; lc += 32) {
+                    const int col = task.clo + lc;
+                    if (col >= task.c0 && col < task.c1) {
+                        const uint32_t k = stage[lc];
+                        if (out_dt) out_dt[rowpx + col] = (float)(k >> DSH);
+                        if (WANT_LBL) out_lbl[rowpx + col] = (int32_t)(k & LMASK);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < PPL / 2; ++j)
-                    *reinterpret_cast<uint2*>(&stage[x0 + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
+                    *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
                 __syncwarp();
-                for (int col = lane; col < W; col += 32) out_depth[rowpx + col] = __uint_as_float(stage[col]);
+                for (int lc = lane; lc < 32 * PPL; lc += 32) {
+                    const int col = task.clo + lc;
+                    if (col >= task.c0 && col < task.c1) out_depth[rowpx + col] = __uint_as_float(stage[lc]);
+                }
             }
         }
     };

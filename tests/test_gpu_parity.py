@@ -117,6 +117,22 @@ def test_band_splitting_is_exact(handle, cap):
         handle.set_band_cap(-1)
 
 
+@pytest.mark.parametrize("W", [660, 800, 1000, 1212, 1216, 400, 500, 592])
+def test_half_width_tiles_are_exact(handle, W):
+    """Bands split into two overlapping half-width tiles (narrow kernel instance) whenever the distance bound
+    allows it: dense-ish frames split, sparse ones do not; both must match the oracle bit for bit."""
+    rng = np.random.default_rng(W)
+    handle.set_band_cap(60)
+    try:
+        for dens in (0.3, 0.08, 0.02, 0.004):
+            x = ((rng.random((2, 96, W)) < dens) * rng.uniform(1, 50, (2, 96, W))).astype(np.float32)
+            x[:, 40, W // 2] = 2.0
+            x[0, 20:60, W // 2 - 40: W // 2 + 40] = 0.0          # a hole right at the tile seam
+            _check_frames(handle, x, 0.1, 0.1)
+    finally:
+        handle.set_band_cap(-1)
+
+
 @pytest.mark.parametrize("nsub", [1, 2, 3, 8])
 def test_subbatch_streams(handle, nsub):
     """Sub-batches on forked streams: same results, and a bad frame is reported with its index in the batch."""
