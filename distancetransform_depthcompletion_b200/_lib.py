@@ -55,6 +55,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
         L.dtfill_set_subbatches.argtypes = [vp, ci]
+        L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
+        L.dtfill_debug_get_tasks.restype = ci
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
@@ -167,6 +169,17 @@ class Handle:
     def set_subbatches(self, n: int):
         """Number of sub-batches run on forked streams (<= 0: automatic)."""
         _check(self._L.dtfill_set_subbatches(self._h, int(n)), "dtfill_set_subbatches")
+
+    TASK_FIELDS = ("frame", "lo", "hi", "r0", "r1", "kind", "scratch_off", "fstart", "clo", "c0", "c1", "reserved")
+
+    def debug_tasks(self, max_tasks: int = 1 << 16) -> np.ndarray:
+        """Tiles the planner produced for the last run: int32 [n, 12] (TASK_FIELDS), unused slots removed."""
+        buf = np.zeros((max_tasks, 12), np.int32)
+        n = self._L.dtfill_debug_get_tasks(self._h, _ptr(buf), max_tasks)
+        if n < 0:
+            _check(n, "dtfill_debug_get_tasks")
+        t = buf[:n]
+        return t[t[:, 5] != 3]
 
     def set_profiling(self, enabled: bool):
         _check(self._L.dtfill_set_profiling(self._h, int(bool(enabled))), "dtfill_set_profiling")

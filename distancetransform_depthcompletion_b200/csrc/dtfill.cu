@@ -477,6 +477,17 @@ int dtfill_set_band_cap(dtfill_t* h, int cap) {
     return 0;
 }
 
+int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks) {
+    if (!h || !out || max_tasks < 0) return fail(DTFILL_E_ARG, "dtfill_debug_get_tasks: bad argument");
+    static_assert(sizeof(Task) == 48, "Task layout is part of the debug ABI");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    long n = (long)h->last_B * MAXT;
+    if (n > max_tasks) n = max_tasks;
+    if (n > 0) CU(cudaMemcpy(out, h->tasks.p, (size_t)n * sizeof(Task), cudaMemcpyDeviceToHost));
+    return (int)n;
+}
+
 int dtfill_set_subbatches(dtfill_t* h, int n) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_subbatches: NULL handle");
     h->nsub = n;

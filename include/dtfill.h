@@ -119,6 +119,12 @@ int dtfill_set_band_cap(dtfill_t* h, int cap);
  * async call's work is complete).  n <= 0: automatic (4 for batches of 64 frames or more). */
 int dtfill_set_subbatches(dtfill_t* h, int n);
 
+/* Introspection for tests and tuning: copies the task list (tiles) the planner produced for the last run.
+ * Each task is 12 int32: frame, lo, hi, r0, r1, kind, scratch_off, fstart, clo, c0, c1, reserved (see
+ * dtfill_kernels.cuh struct Task; kind 3 = unused slot).  Returns the number of tasks written (<= max_tasks),
+ * or a negative error code. */
+int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks);
+
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
  * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide into ms[0..3]. */

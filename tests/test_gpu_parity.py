@@ -117,6 +117,28 @@ def test_band_splitting_is_exact(handle, cap):
         handle.set_band_cap(-1)
 
 
+def test_planner_tiles_cover_every_pixel_once(handle):
+    """The tiles of a frame partition its pixels (written regions disjoint and complete), each written region
+    lies inside its sub-image, and KITTI-like frames do get split (rows and columns)."""
+    for cap in (-1, 60, 150):
+        handle.set_band_cap(cap)
+        x = np.stack([synth.kitti_frame(800 + i, beam_step=(1, 8)[i % 2]) for i in range(4)])
+        handle.run_host(x, 0.1, 0.1)
+        t = handle.debug_tasks()
+        handle.set_band_cap(-1)
+        for b in range(4):
+            cover = np.zeros((352, 1216), np.int32)
+            tb = t[t[:, 0] == b]
+            for (_, lo, hi, r0, r1, kind, _, fstart, clo, c0, c1, _) in tb:
+                assert kind in (0, 4) and 0 <= lo <= r0 < r1 <= hi <= 352 and lo <= fstart < hi
+                width = 1216 if kind == 0 else 640
+                assert clo % 4 == 0 and clo <= c0 < c1 <= min(1216, clo + width)
+                cover[r0:r1, c0:c1] += 1
+            assert np.all(cover == 1)
+        if cap != 0:
+            assert len(t) > 4 and np.any(t[:, 5] == 4), "KITTI frames should be tiled in rows and columns"
+
+
 @pytest.mark.parametrize("W", [660, 800, 1000, 1212, 1216, 400, 500, 592])
 def test_half_width_tiles_are_exact(handle, W):
     """Bands split into two overlapping half-width tiles (narrow kernel instance) whenever the distance bound
