@@ -235,9 +235,9 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, h->rowval, rows * 4))) return rc;
     if ((rc = ensure(h, h->counts, (size_t)B * 8))) return rc;
     if ((rc = ensure(h, h->dlist, npx * 4))) return rc;
-    // forward-state scratch in units of 32 keys: tiles overlap by their halos, so allow 2.5 H full-width rows per
+    // forward-state scratch in units of 32 keys: tiles overlap by their halos, so allow 3 H full-width rows per
     // frame (the 64-bit-key path keeps one u32 per pixel there; K1 parks H*W floats there as well)
-    const int scratch_units_per_frame = plan.ppl ? (5 * H * plan.ppl + 1) / 2 : (int)(((size_t)H * W + 31) / 32);
+    const int scratch_units_per_frame = plan.ppl ? 3 * H * plan.ppl : (int)(((size_t)H * W + 31) / 32);
     if ((rc = ensure(h, h->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, h->status, 16))) return rc;

@@ -450,7 +450,6 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         };
         if (plan) {
             const int nwid = fp.narrow_ppl * 32;                 // width of a half-width tile (0: never split)
-            const int csplit = (W / 2) & ~3;
             int cy = 0, scr = 0;
             bool ok = true;
             while (cy < nh && ok) {
@@ -462,27 +461,38 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
                     umax = max(umax, cellU[c]);
                     const int L = max(0, lo), Hh = min(H, hi);
                     const int cst = (Hh - L) + (Hh - r0);
-                    const bool take = c == cy || nt >= MAXT - 2 || cst <= fp.band_cap || cst - prev <= CELL_H;
+                    const bool take = c == cy || nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H;
                     if (!take) break;
                     prev = cst; end = c + 1; best_lo = L; best_hi = Hh; best_u = umax;
                 }
                 Task q = blank(TASK_CHAMFER);
                 q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
-                // two overlapping half-width tiles when the bound leaves every written pixel's ball inside its tile
-                const bool split = nwid > 0 && W > nwid && 2 * nwid >= W && csplit + best_u <= nwid &&
-                                   csplit - best_u >= W - nwid && nt + 2 <= MAXT;
-                if (split) {
+                // n overlapping narrow tiles when the bound leaves every written pixel's ball inside its tile and the
+                // extra columns stay below ~60 % (n * nwid <= 1.6 W)
+                int ntile = 0;
+                if (nwid > 0 && W > nwid && (W & 3) == 0) {
+                    for (int n = 2; n <= 4 && !ntile; ++n)
+                        if ((long)n * nwid - 2L * (n - 1) * (best_u + 4) >= W && 5 * n * nwid <= 8 * W &&
+                            nt + n <= MAXT) ntile = n;
+                }
+                if (ntile) {
                     q.kind = TASK_NARROW;
-                    q.clo = 0; q.c0 = 0; q.c1 = csplit; q.scratch_off = scr;
-                    scr += (best_hi - best_lo) * fp.narrow_ppl;
-                    cost[nt] = prev; t[nt++] = q;
-                    q.clo = W - nwid; q.c0 = csplit; q.c1 = W; q.scratch_off = scr;
-                    scr += (best_hi - best_lo) * fp.narrow_ppl;
-                    cost[nt] = prev; t[nt++] = q;
+                    int prev_split = 0;
+                    for (int k = 0; k < ntile; ++k) {
+                        const int s0 = (int)(((long)(W - nwid) * k / (ntile - 1)) & ~3L);           // sub-image start
+                        const int s1 = (int)(((long)(W - nwid) * (k + 1) / (ntile - 1)) & ~3L);     // next tile's start
+                        const int split = k == ntile - 1 ? W : ((s1 + s0 + nwid) / 2) & ~3;        // middle of the overlap
+                        q.clo = s0; q.c0 = prev_split; q.c1 = split; q.scratch_off = scr;
+                        // halo check (the sizes above guarantee it; keep the planner honest)
+                        if ((k > 0 && q.c0 - s0 < best_u) || (k < ntile - 1 && s0 + nwid - split < best_u)) ok = false;
+                        scr += (best_hi - best_lo) * fp.narrow_ppl;
+                        cost[nt] = prev; t[nt++] = q;
+                        prev_split = split;
+                    }
                 } else {
                     q.scratch_off = scr;
                     scr += (best_hi - best_lo) * fp.wide_ppl;
-                    cost[nt] = 2 * prev;                      // twice the work per row step of a half-width tile
+                    cost[nt] = 2 * prev;                      // twice the work per row step of a narrow tile
                     t[nt++] = q;
                 }
                 if (scr > fp.scratch_units_per_frame) ok = false;
