@@ -141,6 +141,10 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     fp.wide_ppl = plan.ppl ? plan.ppl : 1;
     fp.narrow_ppl = (h->tiles2d && plan.ppl) ? plan.narrow : 0;
     fp.frame0 = b0;
+    fp.mul_dist = 1u << (32 - DSH);
+    fp.mul_ord = 1u << (32 - OSH);
+    fp.neg_ord = 0u - (1u << OSH);
+    fp.four = 4u;
     {   // band planner target: enough independent tasks to give every SM ~8 warps over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {

@@ -13,10 +13,12 @@
 //                         key cannot hold (width > 1216, 2H+W too large, or >= 2^18 sources)
 //   K4  k4_metrics_*      masked RMSE/MAE/iRMSE/iMAE(/REL/delta) reductions of evaluation.py:82-123, 196-239
 //
-// Key format of the fast path: dist:11 | order:3 | label:18.  "order" is the position
+// Key format of the fast path: dist:11 | order:4 | label:17.  "order" is the position
 // of a candidate in OpenCV's comparison sequence, so that OpenCV's "first candidate that is strictly smaller
 // wins" is a plain unsigned minimum (one VIADDMNMX per candidate); label is the 1-based raster rank of the
-// source, which is also what cv2 returns with DIST_LABEL_PIXEL.
+// source, which is also what cv2 returns with DIST_LABEL_PIXEL.  Stencil candidates use even order values:
+// a stored key may then keep the 0/1 order bit left by the carry application (which is not cleared) without
+// changing the outcome of any later comparison.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,9 +26,9 @@
 namespace dtfill {
 
 constexpr int DSH = 21;                       // dist field shift
-constexpr int OSH = 18;                       // order field shift
+constexpr int OSH = 17;                       // order field shift
 constexpr uint32_t LMASK = (1u << OSH) - 1u;  // label field
-constexpr uint32_t ORDCLR = ~(7u << OSH);
+constexpr uint32_t ORDCLR = ~(15u << OSH);
 constexpr uint32_t MAX_FAST_LABEL = LMASK;    // frames with more sources take the wide path
 constexpr float UNREACHED_DT = 65533.0f;      // what OpenCV reports where no source is reachable
 
@@ -68,6 +70,12 @@ struct FrameParams {
     int wide_ppl;              // pixels per lane of the full-width kernel instance (scratch units per row)
     int narrow_ppl;            // pixels per lane of the half-width instance, 0 if frames are never split in columns
     int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
+    // Multipliers handed over at run time so that ptxas keeps the multiply-adds below on the FMA pipe instead of
+    // strength-reducing them to shifts/LEAs on the ALU pipe, which is the pipe the scan kernel saturates.
+    uint32_t mul_dist;         // 1 << (32 - DSH):  umulhi(key, mul_dist)  == key >> DSH
+    uint32_t mul_ord;          // 1 << (32 - OSH):  umulhi(key, mul_ord)   == key >> OSH
+    uint32_t neg_ord;          // -(1 << OSH):      key + (key >> OSH) * neg_ord == key & LMASK
+    uint32_t four;             // sizeof(float)
 };
 
 struct Workspace {
@@ -587,6 +595,21 @@ __device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t cl
     return key;
 }
 
+// dist field of a key as float, on the FMA pipe (the ALU pipe is the one this kernel saturates):
+// (key >> 21) + 2^23 as the high half of a multiply-add, then the float with that bit pattern minus 2^23.
+__device__ __forceinline__ float key_dist_f32(uint32_t key, uint32_t mul_dist) {
+    uint32_t t;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(key), "r"(mul_dist), "r"(0x4B000000u));
+    return __uint_as_float(t) - 8388608.0f;
+}
+// label field of a key, two multiply-adds on the FMA pipe
+__device__ __forceinline__ uint32_t key_label(uint32_t key, uint32_t mul_ord, uint32_t neg_ord) {
+    uint32_t hi, l;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(key), "r"(mul_ord));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(l) : "r"(hi), "r"(neg_ord), "r"(key));
+    return l;
+}
+
 // Raw words holding this lane's PPL source bits of one row, fetched one row ahead of their use.
 struct RowBits {
     uint32_t a, b, c, pre, base;
@@ -609,13 +632,23 @@ __device__ __forceinline__ RowBits fetch_row_bits(const uint32_t* __restrict__ b
 
 // bit i of `bits` = column x0+i is a source; rank = 1-based raster rank of the first source of this lane
 template <int PPL>
-__device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, uint64_t& bits, uint32_t& rank)
+struct LaneBits { typedef uint64_t type; };
+template <> struct LaneBits<10> { typedef uint32_t type; };
+template <> struct LaneBits<20> { typedef uint32_t type; };
+
+template <int PPL>
+__device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typename LaneBits<PPL>::type& bits,
+                                                uint32_t& rank)
 {
     const int sh = x0 & 31;
-    uint64_t lo = ((uint64_t)r.b << 32) | r.a;
-    lo >>= sh;
-    if (PPL > 33 && sh) lo |= (uint64_t)r.c << (64 - sh);
-    bits = lo & ((PPL >= 64) ? ~0ull : ((1ull << PPL) - 1ull));
+    if (sizeof(typename LaneBits<PPL>::type) == 4) {
+        bits = __funnelshift_r(r.a, r.b, sh) & ((1u << (PPL & 31)) - 1u);     // PPL <= 32 bits from two words
+    } else {
+        uint64_t lo = ((uint64_t)r.b << 32) | r.a;
+        lo >>= sh;
+        if (PPL > 33 && sh) lo |= (uint64_t)r.c << (64 - sh);
+        bits = (typename LaneBits<PPL>::type)(lo & ((PPL >= 64) ? ~0ull : ((1ull << PPL) - 1ull)));
+    }
     rank = r.base + r.pre + __popc(r.a & ((1u << sh) - 1u)) + 1u;
 }
 
@@ -659,41 +692,41 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     // ---------------- forward pass: rows lo .. hi-1 ----------------
     RowBits nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, task.fstart);
     auto fwd_step = [&](const Row<PPL>& A /*row y-1*/, Row<PPL>& Bq /*row y-2 in, row y out*/, int y) {
-        uint64_t bits; uint32_t rank;
+        typename LaneBits<PPL>::type bits; uint32_t rank;
         decode_row_bits<PPL>(nextbits, x0, bits, rank);
         nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, min(y + 1, task.hi - 1));   // one row ahead
         uint32_t c[PPL];
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
             uint32_t m = at(Bq, i - 1) + KC(3, 0);                       // (-2,-1) cost 3
-            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 1), m);              // (-2,+1) cost 3
-            m = __viaddmin_u32(at(A, i - 2), KC(3, 2), m);               // (-1,-2) cost 3
-            m = __viaddmin_u32(at(A, i - 1), KC(2, 3), m);               // (-1,-1) cost 2
-            m = __viaddmin_u32(at(A, i), KC(1, 4), m);                   // (-1, 0) cost 1
-            m = __viaddmin_u32(at(A, i + 1), KC(2, 5), m);               // (-1,+1) cost 2
-            m = __viaddmin_u32(at(A, i + 2), KC(3, 6), m);               // (-1,+2) cost 3
+            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 2), m);              // (-2,+1) cost 3
+            m = __viaddmin_u32(at(A, i - 2), KC(3, 4), m);               // (-1,-2) cost 3
+            m = __viaddmin_u32(at(A, i - 1), KC(2, 6), m);               // (-1,-1) cost 2
+            m = __viaddmin_u32(at(A, i), KC(1, 8), m);                   // (-1, 0) cost 1
+            m = __viaddmin_u32(at(A, i + 1), KC(2, 10), m);              // (-1,+1) cost 2
+            m = __viaddmin_u32(at(A, i + 2), KC(3, 12), m);              // (-1,+2) cost 3
             c[i] = m;
         }
-        if (__any_sync(0xffffffffu, bits != 0ull)) {                      // sources: dist 0, own raster rank
+        if (__any_sync(0xffffffffu, bits != 0)) {                         // sources: dist 0, own raster rank
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
-                const bool s = (bits >> i) & 1ull;
+                const bool s = (bits & ((typename LaneBits<PPL>::type)1 << i)) != 0;
                 c[i] = s ? rank : c[i];
                 rank += s ? 1u : 0u;
             }
         }
-        // in-lane scan: T[x] = min(c[x], T[x-1] + 1); the left neighbour is OpenCV's last candidate (order 7)
+        // in-lane scan: T[x] = min(c[x], T[x-1] + 1); the left neighbour is OpenCV's last candidate (order 14)
         uint32_t u = c[0] & ORDCLR;
         c[0] = u;
 #pragma unroll
         for (int i = 1; i < PPL; ++i) {
-            u = __viaddmin_u32(u, KC(1, 7), c[i]) & ORDCLR;
+            u = __viaddmin_u32(u, KC(1, 14), c[i]) & ORDCLR;
             c[i] = u;
         }
         const uint32_t cin = lane_carry<PPL, +1>(u, lane, clamp_dist);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-            uint32_t t = __viaddmin_u32(cin, uint32_t(i + 1) << DSH, c[i]) & ORDCLR;
+            uint32_t t = __viaddmin_u32(cin, uint32_t(i + 1) << DSH, c[i]);   // order bit 0/1 stays (see header)
             if (PAD && x0 + i >= W) t = init_key;
             Bq.v[i] = t;
         }
@@ -715,9 +748,24 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     fill_row(ra, init_key);
     fill_row(rb, init_key);
     const float* dl = ws.dlist + fpx;
+    const char* dlm1_bytes = reinterpret_cast<const char*>(dl - 1);       // depth_list[lbl - 1]
+    // output addressing that does not depend on the row: which 4-pixel groups of the transposed row this lane
+    // writes (inside [c0,c1)), and where
+    constexpr int NJ = (32 * PPL + 127) / 128;
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int lc = (j * 32 + lane) * 4, col = task.clo + lc;
+        if (lc < 32 * PPL && col >= task.c0 && col < task.c1) okmask |= 1u << j;
+    }
+    const long colbase = fpx + task.clo + lane * 4;
+    const uint4* sread = reinterpret_cast<const uint4*>(&stage[lane * 4]);
+    uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
 
     auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
         const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+        if (lane < PPL && y - 2 >= task.fstart)      // forward row two steps ahead -> L2 (one 128 B line per lane)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(scr + (long)(y - 2 - task.lo) * (16 * PPL) + lane * 16));
         uint32_t c[PPL];
         if (y >= task.fstart) {
 #pragma unroll
@@ -731,15 +779,16 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         }
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-            uint32_t m = c[i];                                            // own forward value first (order 0)
-            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 1), m);              // (+2,+1)
-            m = __viaddmin_u32(at(Bq, i - 1), KC(3, 2), m);              // (+2,-1)
-            m = __viaddmin_u32(at(A, i + 2), KC(3, 3), m);               // (+1,+2)
-            m = __viaddmin_u32(at(A, i + 1), KC(2, 4), m);               // (+1,+1)
-            m = __viaddmin_u32(at(A, i), KC(1, 5), m);                   // (+1, 0)
-            m = __viaddmin_u32(at(A, i - 1), KC(2, 6), m);               // (+1,-1)
-            m = __viaddmin_u32(at(A, i - 2), KC(3, 7), m);               // (+1,-2)
-            c[i] = m & ORDCLR;
+            // own forward value is OpenCV's first operand (order <= 1); it is folded in last so that its load
+            // from the scratch has the whole stencil to complete
+            uint32_t m = at(Bq, i + 1) + KC(3, 2);                       // (+2,+1)
+            m = __viaddmin_u32(at(Bq, i - 1), KC(3, 4), m);              // (+2,-1)
+            m = __viaddmin_u32(at(A, i + 2), KC(3, 6), m);               // (+1,+2)
+            m = __viaddmin_u32(at(A, i + 1), KC(2, 8), m);               // (+1,+1)
+            m = __viaddmin_u32(at(A, i), KC(1, 10), m);                  // (+1, 0)
+            m = __viaddmin_u32(at(A, i - 1), KC(2, 12), m);              // (+1,-1)
+            m = __viaddmin_u32(at(A, i - 2), KC(3, 14), m);              // (+1,-2)
+            c[i] = min(m, c[i]) & ORDCLR;
         }
         uint32_t u = c[PPL - 1];
 #pragma unroll
@@ -750,7 +799,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         const uint32_t cin = lane_carry<PPL, -1>(u, lane, clamp_dist);
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-            uint32_t t = __viaddmin_u32(cin, uint32_t(PPL - i) << DSH, c[i]) & ORDCLR;
+            uint32_t t = __viaddmin_u32(cin, uint32_t(PPL - i) << DSH, c[i]);   // order bit 0/1 stays
             if (PAD && x0 + i >= W) t = init_key;
             Bq.v[i] = t;
         }
@@ -761,46 +810,45 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
             // flight, neighbouring pixels mostly share a label so they hit the same L1 lines
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
-                uint32_t l = Bq.v[i] & LMASK;
+                uint32_t l = key_label(Bq.v[i], fp.mul_ord, fp.neg_ord);
                 if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) load in range
-                c[i] = __float_as_uint(dl[l - 1u]);
+                c[i] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
             }
             const long rowpx = fpx + (long)y * W;
             // transpose through shared memory so that global stores are row-contiguous: keys, then depths
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < PPL / 2; ++j)
-                *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+            for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
             if (VEC) {
+                const long ro = (long)y * W;
                 if (out_dt || WANT_LBL) {
+                    float* pdt = out_dt + colbase + ro;
+                    int32_t* plb = out_lbl + colbase + ro;
 #pragma unroll
-                    for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
-                        const int lc = (j * 32 + lane) * 4;
-                        const int col = task.clo + lc;
-                        if (lc < 32 * PPL && col >= task.c0 && col < task.c1) {
-                            const uint4 k = *reinterpret_cast<const uint4*>(&stage[lc]);
+                    for (int j = 0; j < NJ; ++j) {
+                        if ((okmask >> j) & 1u) {
+                            const uint4 k = sread[j * 32];
                             if (out_dt)
-                                st_stream_v4(out_dt + rowpx + col, __float_as_uint((float)(k.x >> DSH)),
-                                             __float_as_uint((float)(k.y >> DSH)), __float_as_uint((float)(k.z >> DSH)),
-                                             __float_as_uint((float)(k.w >> DSH)));
+                                st_stream_v4(pdt + j * 128, __float_as_uint(key_dist_f32(k.x, fp.mul_dist)),
+                                             __float_as_uint(key_dist_f32(k.y, fp.mul_dist)),
+                                             __float_as_uint(key_dist_f32(k.z, fp.mul_dist)),
+                                             __float_as_uint(key_dist_f32(k.w, fp.mul_dist)));
                             if (WANT_LBL)
-                                st_stream_v4(out_lbl + rowpx + col, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
+                                st_stream_v4(plb + j * 128, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
                         }
                     }
                 }
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < PPL / 2; ++j)
-                    *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
+                for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(c[2 * j], c[2 * j + 1]);
                 __syncwarp();
+                float* pd = out_depth + colbase + ro;
 #pragma unroll
-                for (int j = 0; j < (32 * PPL + 127) / 128; ++j) {
-                    const int lc = (j * 32 + lane) * 4;
-                    const int col = task.clo + lc;
-                    if (lc < 32 * PPL && col >= task.c0 && col < task.c1) {
-                        const uint4 k = *reinterpret_cast<const uint4*>(&stage[lc]);
-                        st_stream_v4(out_depth + rowpx + col, k.x, k.y, k.z, k.w);
+                for (int j = 0; j < NJ; ++j) {
+                    if ((okmask >> j) & 1u) {
+                        const uint4 k = sread[j * 32];
+                        st_stream_v4(pd + j * 128, k.x, k.y, k.z, k.w);
                     }
                 }
             } else {

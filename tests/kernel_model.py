@@ -1,18 +1,19 @@
 """numpy model of the arithmetic the sm_100a chamfer kernel performs (csrc/dtfill_kernels.cu) -- TEST CODE.
 
 It mirrors, lane for lane, what one warp does for one task (a band of rows of one frame): packed 32-bit
-keys ``dist:11 | order:3 | label:18``, the 7-candidate stencil as unsigned minima, the in-lane sequential
-(min,+) scan, the cross-lane Hillis-Steele carry in a widened ``dist:14 | label:18`` form, and the carry
-application.  tests/test_kernel_model.py checks it against the oracle; it exists so the kernel's packing,
+keys ``dist:11 | order:4 | label:17``, the 7-candidate stencil as unsigned minima, the in-lane sequential
+(min,+) scan, the cross-lane Hillis-Steele carry in a widened ``dist:15 | label:17`` form, and the carry
+application.  Stencil candidates use even order values so that a stored key may keep a residual order bit
+(0/1, left by the carry application, which is not cleared) without changing any comparison.  tests/test_kernel_model.py checks it against the oracle; it exists so the kernel's packing,
 tie-breaking and band/halo logic are verified on the CPU before a GPU is involved.
 """
 from __future__ import annotations
 
 import numpy as np
 
-DSH, OSH = 21, 18
-LMASK = np.uint64((1 << 18) - 1)
-ORDMASK = np.uint64(7 << 18)
+DSH, OSH = 21, 17
+LMASK = np.uint64((1 << 17) - 1)
+ORDMASK = np.uint64(15 << 17)
 KEYMASK = np.uint64(0xFFFFFFFF)
 D1 = np.uint64(1 << DSH)
 
@@ -45,26 +46,26 @@ def _row_scan(c, ppl, order_scan, reverse, init_key, clamp_dist):
         U[:, i] = _clr(np.minimum(v[:, i], U[:, i - 1] + step))
     # cross-lane carry in the widened form dist:14 | label:18
     e = U[:, ppl - 1]
-    E = ((e >> np.uint64(DSH)) << np.uint64(18)) | (e & LMASK)
+    E = ((e >> np.uint64(DSH)) << np.uint64(OSH)) | (e & LMASK)
     d = 1
     while d < lanes:
         other = E.copy()
         other[d:] = E[:-d]                  # shfl_up: lanes < d keep their own value
-        t = other + np.uint64((d * ppl) << 18)
+        t = other + np.uint64((d * ppl) << OSH)
         take = (t | LMASK) < E
         E = np.where(take, t, E)
         d *= 2
     cin = np.empty_like(E)
     cin[1:] = E[:-1]
-    cin[0] = (np.uint64(clamp_dist) << np.uint64(18))
-    cd = np.minimum(cin >> np.uint64(18), np.uint64(clamp_dist))
+    cin[0] = (np.uint64(clamp_dist) << np.uint64(OSH))
+    cd = np.minimum(cin >> np.uint64(OSH), np.uint64(clamp_dist))
     cin_key = (cd << np.uint64(DSH)) | np.uint64(1 << OSH) | (cin & LMASK)
     cin_key[0] = (np.uint64(clamp_dist) << np.uint64(DSH)) | np.uint64(1 << OSH)
     out = np.empty_like(U)
     for i in range(ppl):
         t = cin_key + np.uint64((i + 1) << DSH)
         assert (t >> np.uint64(32)).max() == 0
-        out[:, i] = _clr(np.minimum(U[:, i], t))
+        out[:, i] = np.minimum(U[:, i], t)            # residual order bit 0/1 is kept
     if reverse:
         out = out[::-1, ::-1]
     return out.reshape(-1).copy()
@@ -77,7 +78,7 @@ def chamfer_band(src: np.ndarray, rank: np.ndarray, lo: int, hi: int, ppl: int):
     Wp = 32 * ppl
     assert W <= Wp
     init = H + W + 8
-    assert 2 * H + W + ppl + 12 <= 2047 and int(rank.max()) < (1 << 18)
+    assert 2 * H + W + ppl + 12 <= 2047 and int(rank.max()) < (1 << 17)
     clamp = 2047 - ppl - 1
     INIT = np.uint64(init << DSH)
     n = hi - lo
@@ -94,10 +95,10 @@ def chamfer_band(src: np.ndarray, rank: np.ndarray, lo: int, hi: int, ppl: int):
     for y in range(n):
         c = None
         for o, (dy, dx, cost) in enumerate(FWD):
-            cand = _add(shifted(A if dy == -1 else Bp, dx), cost, o)
+            cand = _add(shifted(A if dy == -1 else Bp, dx), cost, 2 * o)
             c = cand if c is None else np.minimum(c, cand)
         c = np.where(pad[y], rk[y], c)
-        row = _row_scan(c, ppl, 7, False, INIT, clamp)
+        row = _row_scan(c, ppl, 14, False, INIT, clamp)
         row = np.where(colpad, INIT, row)
         F[y] = row
         Bp, A = A, row
@@ -106,7 +107,7 @@ def chamfer_band(src: np.ndarray, rank: np.ndarray, lo: int, hi: int, ppl: int):
     for y in range(n - 1, -1, -1):
         c = F[y].copy()
         for o, (dy, dx, cost) in enumerate(BWD):
-            cand = _add(shifted(A if dy == 1 else Bp, dx), cost, o + 1)
+            cand = _add(shifted(A if dy == 1 else Bp, dx), cost, 2 * (o + 1))
             c = np.minimum(c, cand)
         c = _clr(c)
         row = _row_scan(c, ppl, 1, True, INIT, clamp)
