@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
     __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
     __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
     __shared__ uint8_t occw[MAX_CELLS / 4 + 1024];   // planner: per cell-row and word, occupancy nibble
+    __shared__ uint16_t nextsrc[4096];           // planner: first row >= y that holds a source (H if none)
     const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         const uint32_t s_ = rs[y], v_ = rv[y];
         rs[y] = bs; rv[y] = bv;
         bs += s_; bv += v_;
+        if (y < 4096) nextsrc[y] = s_ ? (uint16_t)y : (uint16_t)0xFFFF;
     }
     __syncthreads();
 
@@ -447,6 +449,14 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b + fp.frame0);
         if (kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
 
+        if (plan && H <= 4096) {                     // suffix minimum: first source row at or below y
+            uint16_t nx = (uint16_t)H;
+            for (int y = H - 1; y >= 0; --y) {
+                const uint16_t v = nextsrc[y];
+                nx = v != 0xFFFF ? v : nx;
+                nextsrc[y] = nx;
+            }
+        }
         Task t[MAXT];
         int cost[MAXT];
         int nt = 0;
@@ -513,22 +523,21 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
             t[nt++] = blank(kind);
         }
         // longest task first: the block scheduler hands out blocks in index order (slot-major task array)
+        int ord[MAXT];
+        for (int i = 0; i < nt; ++i) ord[i] = i;
         for (int i = 1; i < nt; ++i) {
-            const Task q = t[i]; const int c = cost[i];
+            const int oi = ord[i], c = cost[oi];
             int j = i - 1;
-            while (j >= 0 && cost[j] < c) { t[j + 1] = t[j]; cost[j + 1] = cost[j]; --j; }
-            t[j + 1] = q; cost[j + 1] = c;
-        }
-        for (int i = 0; i < nt; ++i) {
-            // rows without any source above them stay unreached in the forward pass: skip them
-            int f = t[i].lo;
-            while (f < t[i].hi - 1 && ((f + 1 < H ? rs[f + 1] : nsrc) == rs[f])) ++f;
-            t[i].fstart = f;
+            while (j >= 0 && cost[ord[j]] < c) { ord[j + 1] = ord[j]; --j; }
+            ord[j + 1] = oi;
         }
         for (int i = 0; i < MAXT; ++i) {
             if (i < nt) {
-                t[i].scratch_off += b * fp.scratch_units_per_frame;
-                ws.tasks[(long)i * B + b] = t[i];
+                Task q = t[ord[i]];
+                // rows without any source above them stay unreached in the forward pass: skip them
+                if (plan && H <= 4096) q.fstart = min((int)nextsrc[q.lo], q.hi - 1);
+                q.scratch_off += b * fp.scratch_units_per_frame;
+                ws.tasks[(long)i * B + b] = q;
             } else {
                 Task q = blank(TASK_SKIP);
                 q.hi = q.r1 = 0;
