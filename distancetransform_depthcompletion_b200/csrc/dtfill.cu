@@ -145,13 +145,16 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     fp.mul_ord = 1u << (32 - OSH);
     fp.neg_ord = 0u - (1u << OSH);
     fp.four = 4u;
-    {   // band planner target: enough independent tasks to give every SM ~8 warps over the whole batch
+    {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {
-            const long want_tasks = (long)h->sm_count * 8;
-            const long per_frame = (want_tasks + Btot - 1) / Btot;
-            cap = per_frame <= 1 ? 0 : (int)((2L * H * 5 / 4) / per_frame);
-            if (cap > 0 && cap < 96) cap = 96;
+            const long per_frame = ((long)h->sm_count * 28 + Btot - 1) / Btot;      // tiles wanted per frame
+            if (per_frame <= 1) cap = 0;                                              // batch alone fills the GPU
+            else {
+                const long band_rows = (5L * H / 2) / per_frame;                       // ~2.5 tiles per band of rows
+                cap = (int)(2 * band_rows + 42);
+                if (cap < 96) cap = 96;
+            }
         }
         fp.band_cap = plan.ppl ? cap : 0;
     }
