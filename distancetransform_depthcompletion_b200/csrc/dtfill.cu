@@ -78,6 +78,17 @@ int ensure(dtfill_t* h, Buf& b, size_t bytes) {
     return 0;
 }
 
+// Host buffers of a dtfill_run call with host pointers: each sub-batch copies its own slices on its own stream, so
+// the host->device copy of one slice, the kernels of another and the device->host copy of a third overlap.
+struct HostIO {
+    const float* in = nullptr;
+    float* depth = nullptr;
+    float* dt = nullptr;
+    int32_t* lbl = nullptr;
+    uint8_t* mask = nullptr;
+    int32_t* counts = nullptr;
+};
+
 struct Plan {
     int ppl = 0;        // pixels per lane of the full-width instance; 0: 64-bit-key path only
     bool pad = false;
@@ -222,7 +233,7 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
 
 // Enqueue the whole path on h->stream; all pointers are device pointers.
 int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
-            float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts) {
+            float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts, const HostIO* hio = nullptr) {
     if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
     if ((long)H + W >= 60000 || (long)H * W >= (1l << 31) || W > 28000)
@@ -266,20 +277,44 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
-    if (nsub <= 0) nsub = 1;      // measured: sub-batches do not pay, the scan is bound by per-task latency
+    // device-resident data: sub-batches do not pay (the scan is bound by per-task latency).  Host buffers: slices
+    // pipeline the PCIe copies in both directions with the kernels.
+    if (nsub <= 0) nsub = hio ? (B >= 32 ? 8 : (B >= 4 ? 4 : 1)) : 1;
     if (nsub > dtfill_ctx::MAX_SUB) nsub = dtfill_ctx::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
+    auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
+        if (!hio) return 0;
+        const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
+        CU(cudaMemcpyAsync(const_cast<float*>(in) + o, hio->in + o, n * 4, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    auto copy_out = [&](cudaStream_t st, int b0, int nb) -> int {
+        if (!hio) return 0;
+        const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
+        CU(cudaMemcpyAsync(hio->depth + o, out_depth + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->dt) CU(cudaMemcpyAsync(hio->dt + o, out_dt + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->lbl) CU(cudaMemcpyAsync(hio->lbl + o, out_lbl + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->mask) CU(cudaMemcpyAsync(hio->mask + o, out_mask + o, n, cudaMemcpyDeviceToHost, st));
+        if (hio->counts)
+            CU(cudaMemcpyAsync(hio->counts + 2 * (size_t)b0, out_counts + 2 * (size_t)b0, (size_t)nb * 8,
+                               cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
     if (nsub == 1) {
+        if ((rc = copy_in(s, 0, B))) return rc;
         if ((rc = enqueue_range(h, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
                                 out_counts, scratch_units_per_frame, 0, &launches))) return rc;
+        if ((rc = copy_out(s, 0, B))) return rc;
     } else {
         CU(cudaEventRecord(h->fork_ev, s));
         for (int i = 0; i < nsub; ++i) {
             const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
             CU(cudaStreamWaitEvent(h->sub[i], h->fork_ev, 0));
+            if ((rc = copy_in(h->sub[i], b0, b1 - b0))) return rc;
             if ((rc = enqueue_range(h, h->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
                                     out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return rc;
+            if ((rc = copy_out(h->sub[i], b0, b1 - b0))) return rc;
             CU(cudaEventRecord(h->join_ev[i], h->sub[i]));
             CU(cudaStreamWaitEvent(s, h->join_ev[i], 0));
         }
@@ -404,9 +439,10 @@ int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
     const size_t npx = (size_t)B * H * W;
     int rc;
     const float* in_d = in;
+    const bool pipelined = !in_is_device && !out_is_device;     // both sides on the host: copies are sliced
     if (!in_is_device) {
         if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
-        CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, h->stream));
+        if (!pipelined) CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, h->stream));
         in_d = (const float*)h->in_dev.p;
     }
     float* od = out_depth; float* odt = out_dt; int32_t* ol = out_lbl; uint8_t* om = out_mask; int32_t* oc = out_counts;
@@ -417,6 +453,12 @@ int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
         if (out_lbl) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ol = (int32_t*)h->lbl_dev.p; }
         if (out_mask) { if ((rc = ensure(h, h->mask_dev, npx))) return rc; om = (uint8_t*)h->mask_dev.p; }
         if (out_counts) { if ((rc = ensure(h, h->counts_out_dev, (size_t)B * 8))) return rc; oc = (int32_t*)h->counts_out_dev.p; }
+    }
+    if (pipelined) {
+        HostIO hio;
+        hio.in = in; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask; hio.counts = out_counts;
+        if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc, &hio))) return rc;
+        return dtfill_status(h, first_bad_frame, nullptr);
     }
     if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc))) return rc;
     if (!out_is_device) {
