@@ -122,10 +122,12 @@ def test_planner_tiles_cover_every_pixel_once(handle):
     lies inside its sub-image, and KITTI-like frames do get split (rows and columns)."""
     for cap in (-1, 60, 150):
         handle.set_band_cap(cap)
+        handle.set_subbatches(1)          # one task list for the whole batch (frame indices are per sub-batch)
         x = np.stack([synth.kitti_frame(800 + i, beam_step=(1, 8)[i % 2]) for i in range(4)])
         handle.run_host(x, 0.1, 0.1)
         t = handle.debug_tasks()
         handle.set_band_cap(-1)
+        handle.set_subbatches(-1)
         for b in range(4):
             cover = np.zeros((352, 1216), np.int32)
             tb = t[t[:, 0] == b]
