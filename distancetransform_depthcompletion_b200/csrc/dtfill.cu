@@ -44,6 +44,8 @@ struct dtfill_ctx {
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
     int* status_host = nullptr;   // pinned [2]
+    int32_t* counts_host = nullptr;   // pinned staging for out_counts (a pageable destination would serialise the
+    size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
     int last_launches = 0;
     int last_B = 0;
     bool profiling = false;
@@ -382,6 +384,7 @@ void dtfill_destroy(dtfill_t* h) {
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->status_host) cudaFreeHost(h->status_host);
+    if (h->counts_host) cudaFreeHost(h->counts_host);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
@@ -456,9 +459,21 @@ int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
     }
     if (pipelined) {
         HostIO hio;
-        hio.in = in; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask; hio.counts = out_counts;
+        hio.in = in; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask;
+        if (out_counts) {
+            if (h->counts_host_cap < (size_t)B * 2) {
+                if (h->counts_host) cudaFreeHost(h->counts_host);
+                h->counts_host = nullptr;
+                h->counts_host_cap = 0;
+                CU(cudaHostAlloc((void**)&h->counts_host, (size_t)B * 8 + 64, cudaHostAllocDefault));
+                h->counts_host_cap = (size_t)B * 2 + 16;
+            }
+            hio.counts = h->counts_host;
+        }
         if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc, &hio))) return rc;
-        return dtfill_status(h, first_bad_frame, nullptr);
+        rc = dtfill_status(h, first_bad_frame, nullptr);
+        if (out_counts && (rc == 0 || rc == DTFILL_E_INDEX)) memcpy(out_counts, h->counts_host, (size_t)B * 8);
+        return rc;
     }
     if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc))) return rc;
     if (!out_is_device) {
