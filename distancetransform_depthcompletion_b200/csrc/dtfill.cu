@@ -199,7 +199,7 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
         ++*launches;
     }
     if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
-    k1b_scan_compact<<<nb, 256, 0, s>>>(fp, ws, oc);
+    k1b_scan_compact<<<nb, K1B_THREADS, 0, s>>>(fp, ws, oc);
     ++*launches;
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 

@@ -227,12 +227,15 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
                     const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
                     if (lane >= d) inc += o;
                 }
+                // few pixels per lane are valid (~5 % density): walk the set bits and re-read the values (L1 hits)
                 float* dst = rowvals + row * W + cv + (inc - c);
-                const float x[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
-                                     q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if ((vb >> j) & 1u) *dst++ = x[j];
+                const float* xs = rp + col;
+                uint32_t m = vb;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    *dst++ = __ldg(xs + j);
+                }
                 cv += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
@@ -319,8 +322,11 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in
 // K1b: per frame -- exclusive scans of the row counts, depth_list compaction, task emission.
 // One 256-thread block per frame.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* smem /*[9]*/, uint32_t& total)
+constexpr int K1B_THREADS = 512;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem /*[K1B_THREADS/32 + 1]*/, uint32_t& total)
 {
+    constexpr int NW = K1B_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -332,82 +338,99 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int i = 0; i < 8; ++i) { const uint32_t t = smem[i]; smem[i] = run; run += t; }
-        smem[8] = run;
+        for (int i = 0; i < NW; ++i) { const uint32_t t = smem[i]; smem[i] = run; run += t; }
+        smem[NW] = run;
     }
     __syncthreads();
     const uint32_t base = smem[wid];
-    total = smem[8];
+    total = smem[NW];
     __syncthreads();
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspace ws,
-                                                         int32_t* __restrict__ out_counts)
+// barrier among the 256 planner threads only (warps 8..15), so that the compaction warps are not held up
+__device__ __forceinline__ void planner_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, Workspace ws,
+                                                                 int32_t* __restrict__ out_counts)
 {
-    __shared__ uint32_t sm[9];
+    __shared__ uint32_t sm[K1B_THREADS / 32 + 1];
     __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
     __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
     __shared__ uint8_t occw[MAX_CELLS / 4 + 1024];   // planner: per cell-row and word, occupancy nibble
-    __shared__ uint16_t nextsrc[4096];           // planner: first row >= y that holds a source (H if none)
+    __shared__ uint32_t srcrows[128];            // planner: bit y = row y holds a source (H <= 4096)
     const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
-    const int per = (H + 255) / 256;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int per = (H + K1B_THREADS - 1) / K1B_THREADS;
     const int y0 = min(H, tid * per), y1 = min(H, y0 + per);
     uint32_t* rs = ws.rowsrc + (long)b * H;
     uint32_t* rv = ws.rowval + (long)b * H;
 
+    if (tid < 128) srcrows[tid] = 0;
     uint32_t ls = 0, lv = 0;
     for (int y = y0; y < y1; ++y) { ls += rs[y]; lv += rv[y]; }
     uint32_t nsrc, nval;
-    uint32_t bs = block_exclusive_scan_256(ls, sm, nsrc);
-    uint32_t bv = block_exclusive_scan_256(lv, sm, nval);
+    uint32_t bs = block_exclusive_scan(ls, sm, nsrc);
+    uint32_t bv = block_exclusive_scan(lv, sm, nval);
     for (int y = y0; y < y1; ++y) {
         const uint32_t s_ = rs[y], v_ = rv[y];
         rs[y] = bs; rv[y] = bv;
         bs += s_; bv += v_;
-        if (y < 4096) nextsrc[y] = s_ ? (uint16_t)y : (uint16_t)0xFFFF;
+        if (s_ && y < 4096) atomicOr(&srcrows[y >> 5], 1u << (y & 31));
     }
     __syncthreads();
 
-    // depth_list = in[valid] in raster order (tools.py:24): K1 left every row's valid depths compacted at the
-    // start of the row's slot in ws.scratch; concatenate the non-empty rows.
-    const int lane = tid & 31, wid = tid >> 5;
-    float* dl = ws.dlist + (long)b * H * W;
-    const float* rowvals = reinterpret_cast<const float*>(ws.scratch) + (long)b * H * W;
-    for (int y = wid; y < H; y += 8) {
-        const uint32_t base = rv[y];
-        const uint32_t next = (y + 1 < H) ? rv[y + 1] : nval;
-        const uint32_t cnt = next - base;
-        const float* src = rowvals + (long)y * W;
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32 * 12) {       // 12 loads in flight per lane
-            float v[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const uint32_t i = i0 + k * 32 + lane;
-                v[k] = i < cnt ? src[i] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const uint32_t i = i0 + k * 32 + lane;
-                if (i < cnt) dl[base + i] = v[k];
-            }
-        }
-    }
-
-    // ---- task emission -------------------------------------------------------------------------------
     const int B = fp.B;
     int kind = (nsrc == 0) ? TASK_NOSRC : ((fp.force_wide || nsrc > MAX_FAST_LABEL) ? TASK_WIDE : TASK_CHAMFER);
     if (nval == 0) kind = TASK_SKIP;
     const int nh = (H + CELL_H - 1) / CELL_H, nw = (W + CELL_W - 1) / CELL_W;
-    const bool plan = kind == TASK_CHAMFER && fp.band_cap > 0 && nh * nw <= MAX_CELLS && nh <= 1024 &&
+    const bool plan = kind == TASK_CHAMFER && fp.band_cap > 0 && nh * nw <= MAX_CELLS && nh <= 1024 && H <= 4096 &&
                       2 * H > fp.band_cap;
+
+    if (wid < 8) {
+        // ---- warps 0..7: depth_list = in[valid] in raster order (tools.py:24).  K1 left every row's valid depths
+        // compacted at the start of the row's slot in ws.scratch; concatenate the non-empty rows.
+        float* dl = ws.dlist + (long)b * H * W;
+        const float* rowvals = reinterpret_cast<const float*>(ws.scratch) + (long)b * H * W;
+        for (int yb = wid * 32; yb < H; yb += 8 * 32) {
+            // one coalesced read of 33 row bases per 32 rows instead of two dependent loads per row
+            const int yy = yb + lane;
+            const uint32_t mybase = yy < H ? rv[yy] : nval;
+            const uint32_t nextbase = __shfl_down_sync(0xffffffffu, mybase, 1);
+            const uint32_t after = (yb + 32 < H) ? rv[yb + 32] : nval;
+            const uint32_t mycnt = (lane == 31 ? after : nextbase) - mybase;
+            for (int r = 0; r < 32 && yb + r < H; ++r) {
+                const uint32_t cnt = __shfl_sync(0xffffffffu, mycnt, r);
+                if (cnt == 0) continue;
+                const uint32_t base = __shfl_sync(0xffffffffu, mybase, r);
+                const float* src = rowvals + (long)(yb + r) * W;
+                for (uint32_t i0 = 0; i0 < cnt; i0 += 32 * 12) {       // 12 loads in flight per lane
+                    float v[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) {
+                        const uint32_t i = i0 + k * 32 + lane;
+                        v[k] = i < cnt ? src[i] : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) {
+                        const uint32_t i = i0 + k * 32 + lane;
+                        if (i < cnt) dl[base + i] = v[k];
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- warps 8..15: tile planner -------------------------------------------------------------------------
+    const int ptid = tid - 256, pw = wid - 8;
     if (plan) {
         // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
         // rowcell nibbles of CELL_H consecutive rows OR-ed per word, then one distance cell per bit
         const uint8_t* rc = ws.rowcell + (long)b * H * WW;
-        for (int i = tid; i < nh * WW; i += 256) {
+        for (int i = ptid; i < nh * WW; i += 256) {
             const int cy = i / WW, w = i - cy * WW;
             uint32_t o = 0;
 #pragma unroll
@@ -417,31 +440,60 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
             }
             occw[i] = (uint8_t)o;
         }
-        __syncthreads();
-        for (int i = tid; i < nh * nw; i += 256) {
+        planner_sync();
+        for (int i = ptid; i < nh * nw; i += 256) {
             const int cy = i / nw, cx = i - cy * nw;
             cellD[i] = ((occw[cy * WW + (cx >> 2)] >> (cx & 3)) & 1u) ? 0 : 60000;
         }
-        __syncthreads();
-        for (int cx = tid; cx < nw; cx += 256) {
+        planner_sync();
+        for (int cx = ptid; cx < nw; cx += 256) {        // vertical sweeps, one thread per cell column
             uint32_t d = 60000;
             for (int cy = 0; cy < nh; ++cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
             d = 60000;
             for (int cy = nh - 1; cy >= 0; --cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
         }
-        __syncthreads();
-        for (int cy = tid; cy < nh; cy += 256) {
+        planner_sync();
+        // horizontal sweeps, one warp per cell row: lanes own contiguous chunks, (min,+) scans via shuffles
+        const int chunk = (nw + 31) / 32;
+        for (int cy = pw; cy < nh; cy += 8) {
+            uint16_t* rowp = cellD + cy * nw;
+            const int xa = min(nw, lane * chunk), xb = min(nw, xa + chunk);
+            // left -> right: value entering the chunk from the lanes before it
             uint32_t d = 60000;
-            for (int cx = 0; cx < nw; ++cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+            for (int x = xa; x < xb; ++x) d = min(d + CELL_W, (uint32_t)rowp[x]);
+            uint32_t e = d;                               // chunk-local distance at its last cell
+#pragma unroll
+            for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, e, s_);
+                if (lane >= s_) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+            }
+            uint32_t cin = __shfl_up_sync(0xffffffffu, e, 1);
+            if (lane == 0) cin = 60000;
+            d = min(cin, 60000u);
+            for (int x = xa; x < xb; ++x) { d = min(d + CELL_W, (uint32_t)rowp[x]); rowp[x] = (uint16_t)min(d, 60000u); }
+            __syncwarp();
+            // right -> left, and the row maximum
             d = 60000;
+            for (int x = xb - 1; x >= xa; --x) d = min(d + CELL_W, (uint32_t)rowp[x]);
+            e = xb > xa ? d : 60000u;
+#pragma unroll
+            for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                const uint32_t o = __shfl_down_sync(0xffffffffu, e, s_);
+                if (lane + s_ < 32) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+            }
+            cin = __shfl_down_sync(0xffffffffu, e, 1);
+            if (lane == 31) cin = 60000;
+            d = min(cin, 60000u);
             uint32_t mx = 0;
-            for (int cx = nw - 1; cx >= 0; --cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); mx = max(mx, d); }
-            cellU[cy] = (int)min(mx, 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
+            for (int x = xb - 1; x >= xa; --x) { d = min(d + CELL_W, (uint32_t)rowp[x]); mx = max(mx, min(d, 60000u)); }
+#pragma unroll
+            for (int s_ = 16; s_ > 0; s_ >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s_));
+            if (lane == 0) cellU[cy] = (int)mx + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
         }
-        __syncthreads();
+        planner_sync();
     }
 
-    if (tid == 0) {
+    if (ptid == 0) {
         ws.counts[2 * b] = (int)nsrc;
         ws.counts[2 * b + 1] = (int)nval;
         if (out_counts) { out_counts[2 * b] = (int)nsrc; out_counts[2 * b + 1] = (int)nval; }
@@ -449,14 +501,14 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
         if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b + fp.frame0);
         if (kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
 
-        if (plan && H <= 4096) {                     // suffix minimum: first source row at or below y
-            uint16_t nx = (uint16_t)H;
-            for (int y = H - 1; y >= 0; --y) {
-                const uint16_t v = nextsrc[y];
-                nx = v != 0xFFFF ? v : nx;
-                nextsrc[y] = nx;
+        auto first_source_row = [&](int y) {        // first row >= y that holds a source, H if none
+            for (int w = y >> 5; w < 128 && (w << 5) < H; ++w) {
+                uint32_t m = srcrows[w];
+                if (w == (y >> 5)) m &= ~0u << (y & 31);
+                if (m) return min(H, (w << 5) + __ffs(m) - 1);
             }
-        }
+            return H;
+        };
         Task t[MAXT];
         int cost[MAXT];
         int nt = 0;
@@ -535,7 +587,7 @@ __global__ void __launch_bounds__(256) k1b_scan_compact(FrameParams fp, Workspac
             if (i < nt) {
                 Task q = t[ord[i]];
                 // rows without any source above them stay unreached in the forward pass: skip them
-                if (plan && H <= 4096) q.fstart = min((int)nextsrc[q.lo], q.hi - 1);
+                if (plan) q.fstart = min(first_source_row(q.lo), q.hi - 1);
                 q.scratch_off += b * fp.scratch_units_per_frame;
                 ws.tasks[(long)i * B + b] = q;
             } else {
