@@ -359,6 +359,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
     __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
     __shared__ uint8_t occw[MAX_CELLS / 4 + 1024];   // planner: per cell-row and word, occupancy nibble
     __shared__ uint32_t srcrows[128];            // planner: bit y = row y holds a source (H <= 4096)
+    __shared__ Task st[MAXT];                    // planner: tasks of this frame before ordering
+    __shared__ int scost[MAXT];
+    __shared__ int snt;
     const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
@@ -430,15 +433,26 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
         // rowcell nibbles of CELL_H consecutive rows OR-ed per word, then one distance cell per bit
         const uint8_t* rc = ws.rowcell + (long)b * H * WW;
-        for (int i = ptid; i < nh * WW; i += 256) {
-            const int cy = i / WW, w = i - cy * WW;
-            uint32_t o = 0;
+        for (int i0 = 0; i0 < nh * WW; i0 += 256 * 8) {           // 32 independent byte loads in flight per thread
+            uint32_t o[8];
 #pragma unroll
-            for (int r = 0; r < CELL_H; ++r) {
-                const int y = cy * CELL_H + r;
-                if (y < H) o |= rc[(long)y * WW + w];
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * 256 + ptid;
+                o[k] = 0;
+                if (i < nh * WW) {
+                    const int cy = i / WW, w = i - cy * WW;
+#pragma unroll
+                    for (int r = 0; r < CELL_H; ++r) {
+                        const int y = cy * CELL_H + r;
+                        if (y < H) o[k] |= rc[(long)y * WW + w];
+                    }
+                }
             }
-            occw[i] = (uint8_t)o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * 256 + ptid;
+                if (i < nh * WW) occw[i] = (uint8_t)o[k];
+            }
         }
         planner_sync();
         for (int i = ptid; i < nh * nw; i += 256) {
@@ -501,17 +515,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         if (nval == 0 || nsrc > nval) atomicMin(&ws.status[0], b + fp.frame0);
         if (kind == TASK_WIDE) atomicAdd(&ws.status[1], 1);
 
-        auto first_source_row = [&](int y) {        // first row >= y that holds a source, H if none
-            for (int w = y >> 5; w < 128 && (w << 5) < H; ++w) {
-                uint32_t m = srcrows[w];
-                if (w == (y >> 5)) m &= ~0u << (y & 31);
-                if (m) return min(H, (w << 5) + __ffs(m) - 1);
-            }
-            return H;
-        };
-        Task t[MAXT];
-        int cost[MAXT];
         int nt = 0;
+        Task* t = st;                 // tasks are built in shared memory and written out by all planner threads
+        int* cost = scost;
         auto blank = [&](int knd) {
             Task q;
             q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = knd; q.scratch_off = 0; q.fstart = 0;
@@ -574,27 +580,37 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
             cost[0] = 4 * H;
             t[nt++] = blank(kind);
         }
-        // longest task first: the block scheduler hands out blocks in index order (slot-major task array)
-        int ord[MAXT];
-        for (int i = 0; i < nt; ++i) ord[i] = i;
-        for (int i = 1; i < nt; ++i) {
-            const int oi = ord[i], c = cost[oi];
-            int j = i - 1;
-            while (j >= 0 && cost[ord[j]] < c) { ord[j + 1] = ord[j]; --j; }
-            ord[j + 1] = oi;
-        }
-        for (int i = 0; i < MAXT; ++i) {
-            if (i < nt) {
-                Task q = t[ord[i]];
-                // rows without any source above them stay unreached in the forward pass: skip them
-                if (plan) q.fstart = min(first_source_row(q.lo), q.hi - 1);
+        snt = nt;
+    }
+    planner_sync();
+    // ---- all planner threads: order the tasks (longest first: the block scheduler hands out blocks in index
+    // order, slot-major task array), fill in the forward start rows, write the 32 slots of this frame
+    {
+        const int nt = snt;
+        if (ptid < MAXT) {
+            Task q;
+            int slot = ptid;
+            if (ptid < nt) {
+                const int c = scost[ptid];
+                int rank = 0;
+                for (int j = 0; j < nt; ++j) rank += (scost[j] > c) || (scost[j] == c && j < ptid);
+                slot = rank;
+                q = st[ptid];
+                if (plan) {       // rows without any source above them stay unreached in the forward pass: skip them
+                    int f = H;
+                    for (int w = q.lo >> 5; w < 128 && (w << 5) < H; ++w) {
+                        uint32_t m = srcrows[w];
+                        if (w == (q.lo >> 5)) m &= ~0u << (q.lo & 31);
+                        if (m) { f = min(H, (w << 5) + __ffs(m) - 1); break; }
+                    }
+                    q.fstart = min(f, q.hi - 1);
+                }
                 q.scratch_off += b * fp.scratch_units_per_frame;
-                ws.tasks[(long)i * B + b] = q;
             } else {
-                Task q = blank(TASK_SKIP);
-                q.hi = q.r1 = 0;
-                ws.tasks[(long)i * B + b] = q;
+                q.frame = b; q.lo = 0; q.hi = 0; q.r0 = 0; q.r1 = 0; q.kind = TASK_SKIP; q.scratch_off = 0; q.fstart = 0;
+                q.clo = 0; q.c0 = 0; q.c1 = W; q.pad_ = 0;
             }
+            ws.tasks[(long)slot * B + b] = q;
         }
     }
 }
