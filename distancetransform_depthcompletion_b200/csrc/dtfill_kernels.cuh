@@ -672,6 +672,16 @@ __device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t cl
     return key;
 }
 
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // dist field of a key as float, on the FMA pipe (the ALU pipe is the one this kernel saturates):
 // (key >> 21) + 2^23 as the high half of a multiply-add, then the float with that bit pattern minus 2^23.
 __device__ __forceinline__ float key_dist_f32(uint32_t key, uint32_t mul_dist) {
@@ -733,7 +743,9 @@ template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
 __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
-    __shared__ __align__(16) uint32_t stage[32 * PPL];
+    __shared__ __align__(16) uint32_t stage[32 * PPL];    // keys of an output row, transposed for coalesced stores
+    __shared__ __align__(16) uint32_t dstage[32 * PPL];   // gathered depths of an output row (filled by cp.async)
+    __shared__ __align__(16) uint2 fwdbuf[16 * PPL];      // forward keys of the next row to scan, [j][lane]
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
     const int lane = threadIdx.x;
@@ -822,6 +834,12 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     }
 
     // ---------------- backward pass: rows hi-1 .. r0 ----------------
+    // Long-latency traffic goes through cp.async so that it costs neither registers nor exposed latency:
+    //  * A(y): the forward keys of row y, copied scratch -> fwdbuf one step before they are needed
+    //  * G(y): the gather depth_list[lbl-1] (tools.py:26) of an output row, copied straight into the transposition
+    //          buffer dstage and flushed to out_depth one step later.
+    // cp.async groups complete in issue order; the order of issue is A(hi-1), G(hi) [empty], then per step y:
+    // A(y-1), G(y).  At the top of step y the pending groups are A(y), G(y+1).
     fill_row(ra, init_key);
     fill_row(rb, init_key);
     const float* dl = ws.dlist + fpx;
@@ -837,17 +855,50 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     }
     const long colbase = fpx + task.clo + lane * 4;
     const uint4* sread = reinterpret_cast<const uint4*>(&stage[lane * 4]);
+    const uint4* dread = reinterpret_cast<const uint4*>(&dstage[lane * 4]);
     uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
+    const uint32_t dstage_lane = (uint32_t)__cvta_generic_to_shared(&dstage[xl]);
+    const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(&fwdbuf[lane]);
+
+    auto issue_fwd_row = [&](int y) {            // group A(y)
+        if (y >= task.fstart && y >= task.lo) {
+            const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+#pragma unroll
+            for (int j = 0; j < PPL / 2; ++j) cp_async8(fwdbuf_lane + j * 256, src + j * 32);
+        }
+        cp_async_commit();
+    };
+    auto flush_depth_row = [&](int y) {           // out_depth row y from dstage (its gathers have landed)
+        const long ro = (long)y * W;
+        if (VEC) {
+            float* pd = out_depth + colbase + ro;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if ((okmask >> j) & 1u) {
+                    const uint4 k = dread[j * 32];
+                    st_stream_v4(pd + j * 128, k.x, k.y, k.z, k.w);
+                }
+            }
+        } else {
+            for (int lc = lane; lc < 32 * PPL; lc += 32) {
+                const int col = task.clo + lc;
+                if (col >= task.c0 && col < task.c1) out_depth[fpx + ro + col] = __uint_as_float(dstage[lc]);
+            }
+        }
+    };
+
+    issue_fwd_row(task.hi - 1);
+    cp_async_commit();                            // G(hi): empty
 
     auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
-        const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
-        if (lane < PPL && y - 2 >= task.fstart)      // forward row two steps ahead -> L2 (one 128 B line per lane)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(scr + (long)(y - 2 - task.lo) * (16 * PPL) + lane * 16));
+        if (lane < PPL && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(scr + (long)(y - 3 - task.lo) * (16 * PPL) + lane * 16));
+        cp_async_wait<1>();                          // A(y) has landed (G(y+1) may still be in flight)
         uint32_t c[PPL];
         if (y >= task.fstart) {
 #pragma unroll
             for (int j = 0; j < PPL / 2; ++j) {
-                const uint2 f = src[j * 32];
+                const uint2 f = fwdbuf[j * 32 + lane];
                 c[2 * j] = f.x; c[2 * j + 1] = f.y;
             }
         } else {
@@ -856,17 +907,17 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         }
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-            // own forward value is OpenCV's first operand (order <= 1); it is folded in last so that its load
-            // from the scratch has the whole stencil to complete
-            uint32_t m = at(Bq, i + 1) + KC(3, 2);                       // (+2,+1)
+            uint32_t m = c[i];                                            // own forward value first (order <= 1)
+            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 2), m);              // (+2,+1)
             m = __viaddmin_u32(at(Bq, i - 1), KC(3, 4), m);              // (+2,-1)
             m = __viaddmin_u32(at(A, i + 2), KC(3, 6), m);               // (+1,+2)
             m = __viaddmin_u32(at(A, i + 1), KC(2, 8), m);               // (+1,+1)
             m = __viaddmin_u32(at(A, i), KC(1, 10), m);                  // (+1, 0)
             m = __viaddmin_u32(at(A, i - 1), KC(2, 12), m);              // (+1,-1)
             m = __viaddmin_u32(at(A, i - 2), KC(3, 14), m);              // (+1,-2)
-            c[i] = min(m, c[i]) & ORDCLR;
+            c[i] = m & ORDCLR;
         }
+        issue_fwd_row(y - 1);                        // A(y-1): fwdbuf has been consumed above
         uint32_t u = c[PPL - 1];
 #pragma unroll
         for (int i = PPL - 2; i >= 0; --i) {
@@ -882,50 +933,44 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         }
         refresh_halo(Bq, lane, init_key);
 
-        if (y >= task.r0 && y < task.r1) {
-            // gather depth_list[lbl-1] (tools.py:26) for this lane's own pixels first: PPL independent loads in
-            // flight, neighbouring pixels mostly share a label so they hit the same L1 lines
+        // ---- output: flush the depth row gathered in the previous step, start this row's gather, write dt / lbl
+        const bool out_prev = y + 1 >= task.r0 && y + 1 < task.r1;
+        const bool out_this = y >= task.r0 && y < task.r1;
+        if (out_prev) {
+            cp_async_wait<1>();                      // G(y+1) has landed (A(y-1) may still be in flight)
+            __syncwarp();
+            flush_depth_row(y + 1);
+            __syncwarp();                            // dstage is free again
+        }
+        if (out_this) {
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
                 uint32_t l = key_label(Bq.v[i], fp.mul_ord, fp.neg_ord);
-                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) load in range
-                c[i] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
+                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) copy in range
+                cp_async4(dstage_lane + 4 * i, dlm1_bytes + (uint64_t)l * fp.four);
             }
-            const long rowpx = fpx + (long)y * W;
-            // transpose through shared memory so that global stores are row-contiguous: keys, then depths
-            __syncwarp();
+        }
+        cp_async_commit();                           // G(y), possibly empty
+        if (out_this && (out_dt || WANT_LBL)) {
+            // transpose the keys through shared memory so that global stores are row-contiguous
 #pragma unroll
             for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
+            const long ro = (long)y * W;
             if (VEC) {
-                const long ro = (long)y * W;
-                if (out_dt || WANT_LBL) {
-                    float* pdt = out_dt + colbase + ro;
-                    int32_t* plb = out_lbl + colbase + ro;
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        if ((okmask >> j) & 1u) {
-                            const uint4 k = sread[j * 32];
-                            if (out_dt)
-                                st_stream_v4(pdt + j * 128, __float_as_uint(key_dist_f32(k.x, fp.mul_dist)),
-                                             __float_as_uint(key_dist_f32(k.y, fp.mul_dist)),
-                                             __float_as_uint(key_dist_f32(k.z, fp.mul_dist)),
-                                             __float_as_uint(key_dist_f32(k.w, fp.mul_dist)));
-                            if (WANT_LBL)
-                                st_stream_v4(plb + j * 128, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
-                        }
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(c[2 * j], c[2 * j + 1]);
-                __syncwarp();
-                float* pd = out_depth + colbase + ro;
+                float* pdt = out_dt + colbase + ro;
+                int32_t* plb = out_lbl + colbase + ro;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     if ((okmask >> j) & 1u) {
                         const uint4 k = sread[j * 32];
-                        st_stream_v4(pd + j * 128, k.x, k.y, k.z, k.w);
+                        if (out_dt)
+                            st_stream_v4(pdt + j * 128, __float_as_uint(key_dist_f32(k.x, fp.mul_dist)),
+                                         __float_as_uint(key_dist_f32(k.y, fp.mul_dist)),
+                                         __float_as_uint(key_dist_f32(k.z, fp.mul_dist)),
+                                         __float_as_uint(key_dist_f32(k.w, fp.mul_dist)));
+                        if (WANT_LBL)
+                            st_stream_v4(plb + j * 128, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
                     }
                 }
             } else {
@@ -933,20 +978,12 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
                     const int col = task.clo + lc;
                     if (col >= task.c0 && col < task.c1) {
                         const uint32_t k = stage[lc];
-                        if (out_dt) out_dt[rowpx + col] = (float)(k >> DSH);
-                        if (WANT_LBL) out_lbl[rowpx + col] = (int32_t)(k & LMASK);
+                        if (out_dt) out_dt[fpx + ro + col] = (float)(k >> DSH);
+                        if (WANT_LBL) out_lbl[fpx + ro + col] = (int32_t)(k & LMASK);
                     }
                 }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < PPL / 2; ++j)
-                    *reinterpret_cast<uint2*>(&stage[xl + 2 * j]) = make_uint2(c[2 * j], c[2 * j + 1]);
-                __syncwarp();
-                for (int lc = lane; lc < 32 * PPL; lc += 32) {
-                    const int col = task.clo + lc;
-                    if (col >= task.c0 && col < task.c1) out_depth[rowpx + col] = __uint_as_float(stage[lc]);
-                }
             }
+            __syncwarp();                            // stage is free for the next row
         }
     };
 
@@ -955,6 +992,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         bwd_step(ra, rb, y);
         const Row<PPL> t = ra; ra = rb; rb = t;
     }
+    cp_async_wait<0>();                              // G(r0)
+    __syncwarp();
+    flush_depth_row(task.r0);
 }
 
 // ------------------------------------------------------------------------------------------------------
