@@ -675,8 +675,15 @@ __device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t cl
 __device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+__device__ __forceinline__ void cp_async16_l2only(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+// forward-state scratch is written once and read once, a whole pass later: keep it out of L1 (L2 only)
+__device__ __forceinline__ void st_scratch_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_scratch_v2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -772,7 +779,8 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     const uint32_t* bits_f = ws.srcbits + (long)b * H * WW;
     const uint16_t* pre_f = ws.wprefix + (long)b * H * WW;
     const uint32_t* rowbase = ws.rowsrc + (long)b * H;
-    uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_off * 16;   // PPL/2 uint2 per lane per row
+    constexpr int VW = (PPL % 4 == 0) ? 4 : 2;   // keys per scratch vector
+    uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_off * 16;   // 32*PPL keys per row
 
     Row<PPL> ra, rb;
     fill_row(ra, init_key);
@@ -820,9 +828,13 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
             Bq.v[i] = t;
         }
         refresh_halo(Bq, lane, init_key);
-        uint2* dst = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+        // forward state -> scratch, [vector j][lane] so that every store instruction is fully coalesced
+        char* dst = reinterpret_cast<char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
-        for (int j = 0; j < PPL / 2; ++j) dst[j * 32] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+        for (int j = 0; j < PPL / VW; ++j) {
+            if (VW == 4) st_scratch_v4(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3]);
+            else st_scratch_v2(dst + j * 256, Bq.v[2 * j], Bq.v[2 * j + 1]);
+        }
     };
 
     // one copy of the step in the instruction stream (the unrolled step is ~13 KB of code); the two live rows
@@ -834,12 +846,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     }
 
     // ---------------- backward pass: rows hi-1 .. r0 ----------------
-    // Long-latency traffic goes through cp.async so that it costs neither registers nor exposed latency:
-    //  * A(y): the forward keys of row y, copied scratch -> fwdbuf one step before they are needed
-    //  * G(y): the gather depth_list[lbl-1] (tools.py:26) of an output row, copied straight into the transposition
-    //          buffer dstage and flushed to out_depth one step later.
-    // cp.async groups complete in issue order; the order of issue is A(hi-1), G(hi) [empty], then per step y:
-    // A(y-1), G(y).  At the top of step y the pending groups are A(y), G(y+1).
+    // The forward keys of row y-1 are copied scratch -> fwdbuf with cp.async (16 B, L2 only) while row y is being
+    // scanned: no registers, no exposed latency, no L1 pollution.  (The depth gather is NOT done with cp.async: 4-byte
+    // LDGSTS cost 8 LSU cycles each and 20-38 of them per row step saturate the LSU -- measured.)
     fill_row(ra, init_key);
     fill_row(rb, init_key);
     const float* dl = ws.dlist + fpx;
@@ -857,14 +866,16 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     const uint4* sread = reinterpret_cast<const uint4*>(&stage[lane * 4]);
     const uint4* dread = reinterpret_cast<const uint4*>(&dstage[lane * 4]);
     uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
-    const uint32_t dstage_lane = (uint32_t)__cvta_generic_to_shared(&dstage[xl]);
-    const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(&fwdbuf[lane]);
+    const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(fwdbuf) + lane * (4 * VW);
 
     auto issue_fwd_row = [&](int y) {            // group A(y)
         if (y >= task.fstart && y >= task.lo) {
-            const uint2* src = scr + (long)(y - task.lo) * (16 * PPL) + lane;
+            const char* src = reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
-            for (int j = 0; j < PPL / 2; ++j) cp_async8(fwdbuf_lane + j * 256, src + j * 32);
+            for (int j = 0; j < PPL / VW; ++j) {
+                if (VW == 4) cp_async16_l2only(fwdbuf_lane + j * 512, src + j * 512);
+                else cp_async8(fwdbuf_lane + j * 256, src + j * 256);
+            }
         }
         cp_async_commit();
     };
@@ -888,18 +899,23 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
     };
 
     issue_fwd_row(task.hi - 1);
-    cp_async_commit();                            // G(hi): empty
 
     auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
         if (lane < PPL && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(scr + (long)(y - 3 - task.lo) * (16 * PPL) + lane * 16));
-        cp_async_wait<1>();                          // A(y) has landed (G(y+1) may still be in flight)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(scr) +
+                                                          (long)(y - 3 - task.lo) * (128 * PPL) + lane * 128));
+        cp_async_wait<0>();                          // A(y), the only group in flight, has landed
         uint32_t c[PPL];
         if (y >= task.fstart) {
 #pragma unroll
-            for (int j = 0; j < PPL / 2; ++j) {
-                const uint2 f = fwdbuf[j * 32 + lane];
-                c[2 * j] = f.x; c[2 * j + 1] = f.y;
+            for (int j = 0; j < PPL / VW; ++j) {
+                if (VW == 4) {
+                    const uint4 f = reinterpret_cast<const uint4*>(fwdbuf)[j * 32 + lane];
+                    c[4 * j] = f.x; c[4 * j + 1] = f.y; c[4 * j + 2] = f.z; c[4 * j + 3] = f.w;
+                } else {
+                    const uint2 f = fwdbuf[j * 32 + lane];
+                    c[2 * j] = f.x; c[2 * j + 1] = f.y;
+                }
             }
         } else {
 #pragma unroll
@@ -937,20 +953,20 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         const bool out_prev = y + 1 >= task.r0 && y + 1 < task.r1;
         const bool out_this = y >= task.r0 && y < task.r1;
         if (out_prev) {
-            cp_async_wait<1>();                      // G(y+1) has landed (A(y-1) may still be in flight)
-            __syncwarp();
+            __syncwarp();                            // row y+1's depths were stored to dstage at the end of its step
             flush_depth_row(y + 1);
             __syncwarp();                            // dstage is free again
         }
         if (out_this) {
+            // gather depth_list[lbl-1] (tools.py:26): PPL independent loads in flight per lane; depth_list stays
+            // L1 resident because the scratch traffic bypasses L1
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
                 uint32_t l = key_label(Bq.v[i], fp.mul_ord, fp.neg_ord);
-                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) copy in range
-                cp_async4(dstage_lane + 4 * i, dlm1_bytes + (uint64_t)l * fp.four);
+                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) load in range
+                c[i] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
             }
         }
-        cp_async_commit();                           // G(y), possibly empty
         if (out_this && (out_dt || WANT_LBL)) {
             // transpose the keys through shared memory so that global stores are row-contiguous
 #pragma unroll
@@ -985,6 +1001,11 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
             }
             __syncwarp();                            // stage is free for the next row
         }
+        if (out_this) {                              // gathered depths -> dstage (flushed during the next step)
+            uint2* dwrite = reinterpret_cast<uint2*>(&dstage[xl]);
+#pragma unroll
+            for (int j = 0; j < PPL / 2; ++j) dwrite[j] = make_uint2(c[2 * j], c[2 * j + 1]);
+        }
     };
 
 #pragma unroll 1
@@ -992,7 +1013,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) 
         bwd_step(ra, rb, y);
         const Row<PPL> t = ra; ra = rb; rb = t;
     }
-    cp_async_wait<0>();                              // G(r0)
+    cp_async_wait<0>();
     __syncwarp();
     flush_depth_row(task.r0);
 }
