@@ -747,7 +747,7 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
 }
 
 template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
-__global__ void __launch_bounds__(32, (PPL >= 38 ? 16 : (PPL >= 20 ? 24 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+__global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
     __shared__ __align__(16) uint32_t stage[32 * PPL];    // keys of an output row, transposed for coalesced stores
