@@ -158,6 +158,7 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     fp.mul_ord = 1u << (32 - OSH);
     fp.neg_ord = 0u - (1u << OSH);
     fp.four = 4u;
+    fp.one = 1u;
     {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {

@@ -76,6 +76,7 @@ struct FrameParams {
     uint32_t mul_ord;          // 1 << (32 - OSH):  umulhi(key, mul_ord)   == key >> OSH
     uint32_t neg_ord;          // -(1 << OSH):      key + (key >> OSH) * neg_ord == key & LMASK
     uint32_t four;             // sizeof(float)
+    uint32_t one;              // 1: x * one + c keeps a plain add on the FMA pipe
 };
 
 struct Workspace {
@@ -792,10 +793,14 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
         typename LaneBits<PPL>::type bits; uint32_t rank;
         decode_row_bits<PPL>(nextbits, x0, bits, rank);
         nextbits = fetch_row_bits<PPL>(bits_f, pre_f, rowbase, WW, x0, min(y + 1, task.hi - 1));   // one row ahead
+        if (lane < 2 && y + 4 < task.hi) {           // bit row and prefixes four rows ahead -> L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(bits_f + (long)(y + 4) * WW + (x0 >> 5) + lane * 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pre_f + (long)(y + 4) * WW + (x0 >> 5) + lane * 32));
+        }
         uint32_t c[PPL];
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-            uint32_t m = at(Bq, i - 1) + KC(3, 0);                       // (-2,-1) cost 3
+            uint32_t m = at(Bq, i - 1) * fp.one + KC(3, 0);              // (-2,-1) cost 3 (IMAD: FMA pipe)
             m = __viaddmin_u32(at(Bq, i + 1), KC(3, 2), m);              // (-2,+1) cost 3
             m = __viaddmin_u32(at(A, i - 2), KC(3, 4), m);               // (-1,-2) cost 3
             m = __viaddmin_u32(at(A, i - 1), KC(2, 6), m);               // (-1,-1) cost 2
