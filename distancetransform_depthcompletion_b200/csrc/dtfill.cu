@@ -223,14 +223,20 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
         default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;  // NOSRC only
     }
     ++*launches;
-    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, h->side_join[sub_index], 0));
-    if (h->profiling) CU(cudaEventRecord(h->ev[3], s));
-    {   // wide fallback: returns immediately for every task the fast kernel handled
-        const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
-        k2_chamfer_wide<<<nb, 32, smem, s>>>(fp, ws, od, odt, ol);
+    // 64-bit-key fallback: returns immediately for every task the fast kernels handle.  It touches other frames
+    // than they do, so it runs next to the narrow tiles; only per-kernel profiling serialises it behind the join.
+    const size_t wide_smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
+    if (!h->profiling) {
+        k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
-    if (h->profiling) CU(cudaEventRecord(h->ev[4], s));
+    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, h->side_join[sub_index], 0));
+    if (h->profiling) {
+        CU(cudaEventRecord(h->ev[3], s));
+        k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
+        ++*launches;
+        CU(cudaEventRecord(h->ev[4], s));
+    }
     return 0;
 }
 
