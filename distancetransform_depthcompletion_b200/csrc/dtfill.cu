@@ -514,9 +514,10 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
         p_d = (const float*)h->in_dev.p;
         g_d = h->gt_dev.p;
     }
-    int chunks = (int)((npx + 16383) / 16384);
+    int chunks = (int)((npx + 16383) / 16384);     // chunk boundaries stay multiples of 4 pixels when npx is
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
+    while (chunks > 1 && (((npx + chunks - 1) / chunks) & 3)) --chunks;
     if ((rc = ensure(h, h->partial, (size_t)B * chunks * ACC * 8))) return rc;
     if ((rc = ensure(h, h->per_frame, (size_t)B * 9 * 8))) return rc;
     if ((rc = ensure(h, h->sums, 10 * 8))) return rc;

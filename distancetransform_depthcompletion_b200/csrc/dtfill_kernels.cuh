@@ -1223,7 +1223,27 @@ __global__ void __launch_bounds__(256) k4_metrics_partial(const float* __restric
     double a[ACC];
 #pragma unroll
     for (int k = 0; k < ACC; ++k) a[k] = 0.0;
-    for (long i = i0 + threadIdx.x; i < i1; i += 256) metric_accumulate<GT, MODE>(p[i], g[i], a);
+    if (((npx | i0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(gt)) & 31) == 0) {
+        // 4 pixels per thread and iteration: one 128-bit load of the prediction, one or two of the ground truth
+        for (long i = i0 + 4 * (long)threadIdx.x; i < i1; i += 4 * 256) {
+            const float4 o = __ldg(reinterpret_cast<const float4*>(p + i));
+            GT t[4];
+            if (sizeof(GT) == 8) {
+                const double2 t0 = __ldg(reinterpret_cast<const double2*>(g + i));
+                const double2 t1 = __ldg(reinterpret_cast<const double2*>(g + i + 2));
+                t[0] = (GT)t0.x; t[1] = (GT)t0.y; t[2] = (GT)t1.x; t[3] = (GT)t1.y;
+            } else {
+                const float4 tf = __ldg(reinterpret_cast<const float4*>(g + i));
+                t[0] = (GT)tf.x; t[1] = (GT)tf.y; t[2] = (GT)tf.z; t[3] = (GT)tf.w;
+            }
+            metric_accumulate<GT, MODE>(o.x, t[0], a);
+            metric_accumulate<GT, MODE>(o.y, t[1], a);
+            metric_accumulate<GT, MODE>(o.z, t[2], a);
+            metric_accumulate<GT, MODE>(o.w, t[3], a);
+        }
+    } else {
+        for (long i = i0 + threadIdx.x; i < i1; i += 256) metric_accumulate<GT, MODE>(p[i], g[i], a);
+    }
 #pragma unroll
     for (int k = 0; k < ACC; ++k) {
         double v = a[k];
