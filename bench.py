@@ -145,10 +145,20 @@ class CpuReference:
         return ("port", "C restatement oracle/dtfill_oracle.c (cv2 not importable here), one process per core")
 
 
-def make_frames(n: int, seed0: int) -> np.ndarray:
+WORKLOADS = {   # name -> (beam_step or None for NYU, H, W, source threshold, default batch)
+    "kitti64": (1, 352, 1216, 0.1, 256), "kitti32": (2, 352, 1216, 0.1, 256), "kitti16": (4, 352, 1216, 0.1, 256),
+    "kitti8": (8, 352, 1216, 0.1, 256), "nyu": (None, 480, 640, 0.001, 1024),
+}
+
+
+def make_frames(n: int, seed0: int, workload: str = "kitti64") -> np.ndarray:
     from distancetransform_depthcompletion_b200 import synth
     distinct = min(n, 64)
-    base = np.stack([synth.kitti_frame(seed0 + i) for i in range(distinct)])
+    step = WORKLOADS[workload][0]
+    if step is None:
+        base = np.stack([synth.nyu_frame(seed0 + i) for i in range(distinct)])
+    else:
+        base = np.stack([synth.kitti_frame(seed0 + i, beam_step=step) for i in range(distinct)])
     if distinct == n:
         return base
     reps = -(-n // distinct)
@@ -162,7 +172,7 @@ def make_frames(n: int, seed0: int) -> np.ndarray:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    batch = args.batch
+    batch = args.batch or 256
     cores = os.cpu_count() or 1
     sample = min(batch, max(cores * 4, 32))
     ref = CpuReference(make_frames(sample, 0))
@@ -200,8 +210,10 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    frames_np = make_frames(B, 1000 * rank)
+    global H, W
+    _, H, W, src_thr, default_batch = WORKLOADS[args.workload]
+    B = args.batch or default_batch
+    frames_np = make_frames(B, 1000 * rank, args.workload)
     pin_in = _lib.pinned_empty((B, H, W), np.float32)
     pin_in[...] = frames_np
     x = torch.from_numpy(frames_np).to(dev)
@@ -222,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     for _ in range(args.warmup):
-        eng.fill(x, out=out)
+        eng.fill(x, src_thr=src_thr, out=out)
     bad, launches_per_step = eng.status()
     assert bad == -1, f"unexpected bad frame {bad}"
 
@@ -233,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.fill(x, out=out)
+        eng.fill(x, src_thr=src_thr, out=out)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -250,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
     kt = {}
     reps = min(args.steps, 5)
     for _ in range(reps):
-        eng.fill(x, out=out)
+        eng.fill(x, src_thr=src_thr, out=out)
         for k, v in eng.handle.kernel_times().items():
             kt[k] = kt.get(k, 0.0) + v / reps
     eng.handle.set_profiling(False)
@@ -262,11 +274,11 @@ def run_ours(args, rank, world, local_rank):
     pin_out = dict(depth=_lib.pinned_empty((B, H, W), np.float32), dt=_lib.pinned_empty((B, H, W), np.float32),
                    mask=_lib.pinned_empty((B, H, W), np.uint8))
     e2e_steps = max(2, min(args.steps, 5))
-    h.run_host(pin_in, 0.1, 0.1, want_dt=True, want_mask=True, out=pin_out)      # warm-up (allocates staging)
+    h.run_host(pin_in, src_thr, 0.1, want_dt=True, want_mask=True, out=pin_out)      # warm-up (allocates staging)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        r = h.run_host(pin_in, 0.1, 0.1, want_dt=True, want_mask=True, out=pin_out)
+        r = h.run_host(pin_in, src_thr, 0.1, want_dt=True, want_mask=True, out=pin_out)
     t_e2e = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
@@ -304,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(frames_np)
+        ref = CpuReference(frames_np)        # (the port uses the KITTI thresholds; NYU frames have depths >= 1 m)
         sample = min(B, max(ref.cores * 4, 32))
         ref.run(min(sample, max(ref.cores, 8)))
         reps_cpu, t_cpu = 0, 0.0
@@ -320,8 +332,9 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 keys (integer chamfer) + f32 copy", "data": "synthetic",
-        "config": {"workload": f"kitti64: batch of {B} synthetic KITTI 64-beam frames 352x1216 (~5% density) per GPU "
-                               "(BASELINE.json configs[1])",
+        "config": {"workload": (f"kitti64: batch of {B} synthetic KITTI 64-beam frames 352x1216 (~5% density) per GPU "
+                                "(BASELINE.json configs[1])") if args.workload == "kitti64" else
+                               f"{args.workload}: batch of {B} synthetic frames {H}x{W} per GPU",
                    "outputs": "filled depth f32 + distance channel f32 + validity mask u8 (13 B/px algorithmic)",
                    "l2": f"inputs+outputs per step {ALG_BYTES_PER_PX * px_step / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                    "frames_per_step_per_gpu": B},
@@ -342,7 +355,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU and step (default: the workload's)")
+    ap.add_argument("--workload", default="kitti64", choices=sorted(WORKLOADS),
+                    help="kitti64 is the BASELINE.json metric; the others are the remaining configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
     ap.add_argument("--subbatches", type=int, default=None, help="override the number of sub-batch streams")
