@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                     umax = max(umax, cellU[c]);
                     const int L = max(0, lo), Hh = min(H, hi);
                     const int cst = (Hh - L) + (Hh - r0);
-                    const bool take = c == cy || nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H;
+                    // extend while the tile stays under the target cost, while extending is (nearly) free, or while
+                    // the band is still short compared with its halo (sparse frames: tall bands, less redundancy)
+                    const bool take = c == cy || nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H ||
+                                      (c - cy) * CELL_H < 2 * umax;
                     if (!take) break;
                     prev = cst; end = c + 1; best_lo = L; best_hi = Hh; best_u = umax;
                 }
@@ -548,9 +551,20 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 // extra columns stay below ~60 % (n * nwid <= 1.6 W)
                 int ntile = 0;
                 if (nwid > 0 && W > nwid && (W & 3) == 0) {
-                    for (int n = 2; n <= 4 && !ntile; ++n)
-                        if ((long)n * nwid - 2L * (n - 1) * (best_u + 4) >= W && 5 * n * nwid <= 8 * W &&
-                            nt + n <= MAXT) ntile = n;
+                    for (int n = 2; n <= 4 && !ntile; ++n) {
+                        if (5 * n * nwid > 8 * W || nt + n > MAXT) break;
+                        bool fits = true;                      // every interior tile edge at least best_u away
+                        int prev_split = 0;
+                        for (int k = 0; k < n && fits; ++k) {
+                            const int s0 = (int)(((long)(W - nwid) * k / (n - 1)) & ~3L);
+                            const int s1 = (int)(((long)(W - nwid) * (k + 1) / (n - 1)) & ~3L);
+                            const int split = k == n - 1 ? W : ((s1 + s0 + nwid) / 2) & ~3;
+                            if ((k > 0 && prev_split - s0 < best_u) || (k < n - 1 && s0 + nwid - split < best_u) ||
+                                split <= prev_split) fits = false;
+                            prev_split = split;
+                        }
+                        if (fits) ntile = n;
+                    }
                 }
                 if (ntile) {
                     q.kind = TASK_NARROW;
