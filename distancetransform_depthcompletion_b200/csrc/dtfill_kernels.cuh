@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                     // extend while the tile stays under the target cost, while extending is (nearly) free, or while
                     // the band is still short compared with its halo (sparse frames: tall bands, less redundancy)
                     const bool take = c == cy || nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H ||
-                                      (c - cy) * CELL_H < 2 * umax;
+                                      (c - cy) * CELL_H < 2 * cellU[c];
                     if (!take) break;
                     prev = cst; end = c + 1; best_lo = L; best_hi = Hh; best_u = umax;
                 }
