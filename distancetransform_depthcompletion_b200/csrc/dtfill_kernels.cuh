@@ -765,9 +765,12 @@ template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
 __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
-    __shared__ __align__(16) uint32_t stage[32 * PPL];    // keys of an output row, transposed for coalesced stores
-    __shared__ __align__(16) uint32_t dstage[32 * PPL];   // gathered depths of an output row (filled by cp.async)
+    // One transposition buffer: within a step it first holds the keys of the output row (-> dt / lbl stores), then
+    // its gathered depths, which are flushed to out_depth at the start of the next step.  Keeping shared memory
+    // small matters: what is left of the 228 KB is the L1 that serves the depth_list gather.
+    __shared__ __align__(16) uint32_t stage[32 * PPL];
     __shared__ __align__(16) uint2 fwdbuf[16 * PPL];      // forward keys of the next row to scan, [j][lane]
+    uint32_t* const dstage = stage;
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
     const int lane = threadIdx.x;
