@@ -762,15 +762,14 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
 }
 
 template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
-__global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+__global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
-    // One transposition buffer: within a step it first holds the keys of the output row (-> dt / lbl stores), then
-    // its gathered depths, which are flushed to out_depth at the start of the next step.  Keeping shared memory
-    // small matters: what is left of the 228 KB is the L1 that serves the depth_list gather.
+    // Transposition buffer for the keys of an output row.  Keeping shared memory small matters: what is left of the
+    // 228 KB is the L1 that serves the depth_list gather.
     __shared__ __align__(16) uint32_t stage[32 * PPL];
     __shared__ __align__(16) uint2 fwdbuf[16 * PPL];      // forward keys of the next row to scan, [j][lane]
-    uint32_t* const dstage = stage;
+
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
     const int lane = threadIdx.x;
@@ -886,7 +885,6 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
     }
     const long colbase = fpx + task.clo + lane * 4;
     const uint4* sread = reinterpret_cast<const uint4*>(&stage[lane * 4]);
-    const uint4* dread = reinterpret_cast<const uint4*>(&dstage[lane * 4]);
     uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
     const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(fwdbuf) + lane * (4 * VW);
 
@@ -901,23 +899,14 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
         }
         cp_async_commit();
     };
-    auto flush_depth_row = [&](int y) {           // out_depth row y from dstage (its gathers have landed)
-        const long ro = (long)y * W;
-        if (VEC) {
-            float* pd = out_depth + colbase + ro;
+    // Depths gathered for an output row stay in registers across the loop back-edge and are stored at the start of
+    // the next step: the gather's latency is covered by the row rotation, and nothing else is live meanwhile.
+    uint32_t g[NJ * 4];
+    auto flush_depth_row = [&](int y) {
+        float* pd = out_depth + colbase + (long)y * W;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                if ((okmask >> j) & 1u) {
-                    const uint4 k = dread[j * 32];
-                    st_stream_v4(pd + j * 128, k.x, k.y, k.z, k.w);
-                }
-            }
-        } else {
-            for (int lc = lane; lc < 32 * PPL; lc += 32) {
-                const int col = task.clo + lc;
-                if (col >= task.c0 && col < task.c1) out_depth[fpx + ro + col] = __uint_as_float(dstage[lc]);
-            }
-        }
+        for (int j = 0; j < NJ; ++j)
+            if ((okmask >> j) & 1u) st_stream_v4(pd + j * 128, g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
     };
 
     issue_fwd_row(task.hi - 1);
@@ -926,6 +915,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
         if (lane < PPL && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(scr) +
                                                           (long)(y - 3 - task.lo) * (128 * PPL) + lane * 128));
+        if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
         cp_async_wait<0>();                          // A(y), the only group in flight, has landed
         uint32_t c[PPL];
         if (y >= task.fstart) {
@@ -971,26 +961,10 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
         }
         refresh_halo(Bq, lane, init_key);
 
-        // ---- output: flush the depth row gathered in the previous step, start this row's gather, write dt / lbl
-        const bool out_prev = y + 1 >= task.r0 && y + 1 < task.r1;
-        const bool out_this = y >= task.r0 && y < task.r1;
-        if (out_prev) {
-            __syncwarp();                            // row y+1's depths were stored to dstage at the end of its step
-            flush_depth_row(y + 1);
-            __syncwarp();                            // dstage is free again
-        }
-        if (out_this) {
-            // gather depth_list[lbl-1] (tools.py:26): PPL independent loads in flight per lane; depth_list stays
-            // L1 resident because the scratch traffic bypasses L1
-#pragma unroll
-            for (int i = 0; i < PPL; ++i) {
-                uint32_t l = key_label(Bq.v[i], fp.mul_ord, fp.neg_ord);
-                if (PAD) l = max(l, 1u);           // columns beyond W carry label 0; keep their (unused) load in range
-                c[i] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
-            }
-        }
-        if (out_this && (out_dt || WANT_LBL)) {
-            // transpose the keys through shared memory so that global stores are row-contiguous
+        // ---- output of row y: keys -> shared memory (transpose), then per lane 4 consecutive pixels per group:
+        // dt / lbl stores and the gather depth_list[lbl-1] (tools.py:26).  In this layout neighbouring lanes ask
+        // for neighbouring labels (consecutive ranks along a beam), so a gather instruction touches few lines.
+        if (y >= task.r0 && y < task.r1) {
 #pragma unroll
             for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
             __syncwarp();
@@ -1009,6 +983,12 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
                                          __float_as_uint(key_dist_f32(k.w, fp.mul_dist)));
                         if (WANT_LBL)
                             st_stream_v4(plb + j * 128, k.x & LMASK, k.y & LMASK, k.z & LMASK, k.w & LMASK);
+                        const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t l = key_label(kk[e], fp.mul_ord, fp.neg_ord);     // >= 1 inside [c0,c1)
+                            g[4 * j + e] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
+                        }
                     }
                 }
             } else {
@@ -1018,15 +998,11 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
                         const uint32_t k = stage[lc];
                         if (out_dt) out_dt[fpx + ro + col] = (float)(k >> DSH);
                         if (WANT_LBL) out_lbl[fpx + ro + col] = (int32_t)(k & LMASK);
+                        out_depth[fpx + ro + col] = dl[(k & LMASK) - 1u];
                     }
                 }
             }
             __syncwarp();                            // stage is free for the next row
-        }
-        if (out_this) {                              // gathered depths -> dstage (flushed during the next step)
-            uint2* dwrite = reinterpret_cast<uint2*>(&dstage[xl]);
-#pragma unroll
-            for (int j = 0; j < PPL / 2; ++j) dwrite[j] = make_uint2(c[2 * j], c[2 * j + 1]);
         }
     };
 
@@ -1036,8 +1012,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 15 : (PPL >= 20 ? 20 : 32))) 
         const Row<PPL> t = ra; ra = rb; rb = t;
     }
     cp_async_wait<0>();
-    __syncwarp();
-    flush_depth_row(task.r0);
+    if (VEC) flush_depth_row(task.r0);
 }
 
 // ------------------------------------------------------------------------------------------------------
