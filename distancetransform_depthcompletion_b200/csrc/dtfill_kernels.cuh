@@ -156,13 +156,22 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
     for (long row = warp; row < nrows; row += nwarps) {
         const float* rp = in + row * W;
         uint32_t cs = 0, cv = 0;
+        // software pipeline over the 512-pixel chunks: the four 128-bit loads of the next chunk are issued (volatile
+        // asm, so they stay ahead) before the current chunk is processed
+        float4 nq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            nq[g] = lane * 16 + 4 * g < W ? ld_stream_v4(rp + lane * 16 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int col = (ch << 9) + lane * 16;
             float4 q[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                q[g] = col + 4 * g < W ? __ldg(reinterpret_cast<const float4*>(rp + col + 4 * g))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int g = 0; g < 4; ++g) q[g] = nq[g];
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    nq[g] = col + 512 + 4 * g < W ? ld_stream_v4(rp + col + 512 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint32_t sb = 0, vb = 0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
