@@ -112,9 +112,11 @@ __device__ __forceinline__ void st_stream_v2(void* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
 }
+// 128-bit read-only load that may allocate in L1: a lane's 16 pixels are four such loads of consecutive 16 B, so
+// the second half of every 32 B sector is an L1 hit instead of a second trip to L2
 __device__ __forceinline__ float4 ld_stream_v4(const float* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
