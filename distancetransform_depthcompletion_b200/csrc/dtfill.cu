@@ -40,7 +40,7 @@ struct dtfill_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     // workspace
-    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, frame_done;
+    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
     int* status_host = nullptr;   // pinned [2]
@@ -184,7 +184,6 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     ws.scratch = (uint32_t*)h->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
     ws.tasks = (Task*)h->tasks.p + (size_t)b0 * MAXT;
     ws.status = (int*)h->status.p;
-    ws.frame_done = (int*)h->frame_done.p + b0;
     const float* in_s = in + npx0;
     float* od = out_depth + npx0;
     float* odt = out_dt ? out_dt + npx0 : nullptr;
@@ -192,15 +191,17 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     uint8_t* om = out_mask ? out_mask + npx0 : nullptr;
     int32_t* oc = out_counts ? out_counts + 2 * (size_t)b0 : nullptr;
 
-    {   // K1: one warp per row, 16 rows per block; the block that completes a frame also finalises it (K1b)
-        CU(cudaMemsetAsync(ws.frame_done, 0, (size_t)nb * sizeof(int), s));
-        if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
-        dim3 grid((H + K1B_THREADS / 32 - 1) / (K1B_THREADS / 32), nb);
-        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, K1B_THREADS, 0, s>>>(in_s, fp, ws, om, oc);
-        else k1_mask_rows<<<grid, K1B_THREADS, 0, s>>>(in_s, fp, ws, om, oc);
+    if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
+    {   // K1: one warp per row
+        long want = ((long)rows + 7) / 8;
+        int grid = (int)(want < 1 ? 1 : want);
+        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
+        else k1_mask_rows<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
         ++*launches;
     }
     if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
+    k1b_scan_compact<<<nb, K1B_THREADS, 0, s>>>(fp, ws, oc);
+    ++*launches;
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
     const bool want_lbl = ol != nullptr;
@@ -267,7 +268,6 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, h->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, h->status, 16))) return rc;
-    if ((rc = ensure(h, h->frame_done, (size_t)B * sizeof(int)))) return rc;
     {
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
         static size_t configured = 0;
@@ -386,7 +386,7 @@ void dtfill_destroy(dtfill_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     Buf* bufs[] = {&h->srcbits, &h->valbits, &h->wprefix, &h->rowcell, &h->rowsrc, &h->rowval, &h->counts, &h->dlist,
-                   &h->scratch, &h->tasks, &h->status, &h->frame_done, &h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev,
+                   &h->scratch, &h->tasks, &h->status, &h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev,
                    &h->mask_dev, &h->counts_out_dev, &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);

@@ -3,8 +3,8 @@
 // Pipeline for a batch of frames [B,H,W] float32 (all device resident):
 //   K1  k1_mask_rows      in -> source/valid bit rows, per-word source prefix, row counts, validity mask (u8)
 //                         (reference: value_mask tools.py:8 / eval_NYU.py:115, with_value tools.py:22, net.py:131)
-//   K1b frame_finalize    (run by the last K1 block of each frame) exclusive row bases (= raster ranks, OpenCV's
-//                         label initialisation), depth_list = in[valid] in raster order (tools.py:24), tile planner
+//   K1b k1b_scan_compact  per frame: exclusive row bases (= raster ranks, OpenCV's label initialisation),
+//                         depth_list = in[valid] in raster order (tools.py:24), task list for K2
 //   K2  k2_chamfer<PPL>   one warp per task: OpenCV's forward/backward 5x5 chamfer scan with label
 //                         propagation (the cv2 call at tools.py:9) restructured as row-sequential,
 //                         lane-parallel (min,+) scans on packed keys kept in registers, fused with the gather
@@ -91,7 +91,6 @@ struct Workspace {
     uint32_t* scratch;   // forward state, lane-major rows of 32*PPL keys
     Task* tasks;         // [B * max_tasks_per_frame]
     int* status;         // [0] first bad frame (INT_MAX if none), [1] number of wide tasks
-    int* frame_done;     // [B] K1 blocks finished per frame (zeroed before every run)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -128,9 +127,212 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1b (frame_finalize): per frame -- exclusive scans of the row counts, depth_list compaction, tile planner.
-// Executed by the LAST K1 block of a frame to finish (512 threads), so it overlaps with the K1 work of the other
-// frames instead of being a separate, latency-bound launch.
+// K1 (W % 4 == 0): predicates -> bit rows, per-word source prefix, coarse cells, row counts, validity mask,
+// and the row-local compaction of the valid depths (into ws.scratch, which K2 only uses later).
+// One warp per row; a lane owns 16 consecutive pixels of every 512-pixel chunk (four 128-bit loads).
+// The predicates are evaluated without branches: a > b  <=>  sign(b - a) for IEEE floats (a NaN operand gives
+// the canonical positive NaN, i.e. "false", like the comparison), and the sign bits of four differences are
+// gathered into a nibble with byte permutes and one multiply.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, float t3)
+{
+    // top bytes of the four floats -> one word -> bits 7,15,23,31 -> nibble (multiply gathers them into 28..31)
+    const uint32_t p01 = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0073);   // [t0.b3, t1.b3, 0, 0]
+    const uint32_t p23 = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0073);
+    const uint32_t w = __byte_perm(p01, p23, 0x5410) & 0x80808080u;
+    return (w * 0x00204081u) >> 28;
+}
+
+__global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                         uint8_t* __restrict__ out_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int W = fp.W, WW = fp.WW;
+    const long nrows = (long)fp.B * fp.H;
+    const int nchunks = (W + 511) >> 9;
+    const float sthr = fp.src_thr, vthr = fp.val_thr;
+    const bool mask16 = (W & 15) == 0;
+    float* rowvals = reinterpret_cast<float*>(ws.scratch);
+    for (long row = warp; row < nrows; row += nwarps) {
+        const float* rp = in + row * W;
+        uint32_t cs = 0, cv = 0;
+        // software pipeline over the 512-pixel chunks: the four 128-bit loads of the next chunk are issued (volatile
+        // asm, so they stay ahead) before the current chunk is processed
+        float4 nq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            nq[g] = lane * 16 + 4 * g < W ? ld_stream_v4(rp + lane * 16 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int col = (ch << 9) + lane * 16;
+            float4 q[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) q[g] = nq[g];
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    nq[g] = col + 512 + 4 * g < W ? ld_stream_v4(rp + col + 512 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t sb = 0, vb = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr
+                const float d0 = __fsub_rn(1.0f, q[g].x), d1 = __fsub_rn(1.0f, q[g].y);
+                const float d2 = __fsub_rn(1.0f, q[g].z), d3 = __fsub_rn(1.0f, q[g].w);
+                const uint32_t ns = sign_nibble(__fsub_rn(sthr, d0), __fsub_rn(sthr, d1), __fsub_rn(sthr, d2),
+                                                __fsub_rn(sthr, d3));                       // bit = d > src_thr
+                const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
+                                                __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
+                const uint32_t inb = col + 4 * g < W ? 0xFu : 0u;
+                sb |= ((ns ^ 0xFu) & inb) << (4 * g);
+                vb |= (nv & inb) << (4 * g);
+            }
+            if (out_mask && col < W) {
+                uint32_t m[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                uint8_t* mp = out_mask + row * W + col;
+                if (mask16) {
+                    st_stream_v4(mp, m[0], m[1], m[2], m[3]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (col + 4 * g < W) st_stream_u32(mp + 4 * g, m[g]);
+                }
+            }
+            // 32-bit words from the halves of 2 neighbouring lanes
+            uint32_t sw = sb << ((lane & 1) * 16), vw = vb << ((lane & 1) * 16);
+            sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
+            vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
+            // coarse cells: bit j of the word's nibble = some source among its pixels 8j..8j+7
+            const uint32_t cell = ((sw & 0xFFu) != 0) | (((sw & 0xFF00u) != 0) << 1) | (((sw & 0xFF0000u) != 0) << 2) |
+                                  (((sw & 0xFF000000u) != 0) << 3);
+            const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);
+            const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
+            uint32_t spre = 0, stot = 0;
+            if (sany) {
+                const uint32_t c = __popc(sb);
+                uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                spre = inc - c;
+                stot = __shfl_sync(0xffffffffu, inc, 31);
+            }
+            const int w = (ch << 4) + (lane >> 1);
+            if ((lane & 1) == 0 && w < WW) {
+                const long wi = row * WW + w;
+                ws.srcbits[wi] = sw;
+                ws.valbits[wi] = vw;
+                ws.wprefix[wi] = (uint16_t)(cs + spre);
+                ws.rowcell[wi] = (uint8_t)cell;
+            }
+            cs += stot;
+            if (vany) {
+                const uint32_t c = __popc(vb);
+                uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                // few pixels per lane are valid (~5 % density): walk the set bits and re-read the values (L1 hits)
+                float* dst = rowvals + row * W + cv + (inc - c);
+                const float* xs = rp + col;
+                uint32_t m = vb;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    *dst++ = __ldg(xs + j);
+                }
+                cv += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        if (lane == 0) {
+            ws.rowsrc[row] = cs;
+            ws.rowval[row] = cv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1 for widths that are not a multiple of 4 (no 128-bit row alignment): same outputs, scalar loads + ballots.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
+                                                     uint8_t* __restrict__ out_mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int W = fp.W, WW = fp.WW;
+    const long nrows = (long)fp.B * fp.H;
+    const bool vec_mask = (W & 3) == 0;
+    const uint32_t ltmask = lanemask_lt();
+    float* rowvals = reinterpret_cast<float*>(ws.scratch);
+    for (long row = warp; row < nrows; row += nwarps) {
+        const float* rp = in + row * W;
+        uint32_t cs = 0, cv = 0;
+        for (int c0 = 0; c0 < WW; c0 += 16) {
+            float x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int col = (c0 + k) * 32 + lane;
+                x[k] = col < W ? ld_stream(rp + col) : 0.0f;
+            }
+            uint32_t mys = 0, myv = 0, mypre = 0;
+            uint32_t vq[4];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int col = (c0 + k) * 32 + lane;
+                const bool inb = col < W;
+                const float d = __fsub_rn(1.0f, x[k]);                 // tools.py:8  1.0 - x  (float32)
+                const bool sp = inb && !(d > fp.src_thr);             // value_mask == 0  <=> source
+                const bool vp = inb && (x[k] > fp.val_thr);           // tools.py:22 with_value
+                const uint32_t sw = __ballot_sync(0xffffffffu, sp);
+                const uint32_t vw = __ballot_sync(0xffffffffu, vp);
+                if (lane == k) { mys = sw; myv = vw; mypre = cs; }
+                if (vp) rowvals[row * W + cv + __popc(vw & ltmask)] = x[k];
+                cs += __popc(sw);
+                cv += __popc(vw);
+                vq[k & 3] = vw;
+                if (out_mask) {
+                    if (vec_mask) {
+                        if ((k & 3) == 3) {
+                            const int col4 = (c0 + k - 3) * 32 + lane * 4;
+                            if (col4 < W) {
+                                const int q = lane >> 3;
+                                const uint32_t word = q == 0 ? vq[0] : q == 1 ? vq[1] : q == 2 ? vq[2] : vq[3];
+                                const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;
+                                st_stream_u32(out_mask + row * W + col4, (nib * 0x00204081u) & 0x01010101u);
+                            }
+                        }
+                    } else if (inb) {
+                        out_mask[row * W + col] = (uint8_t)vp;
+                    }
+                }
+            }
+            if (lane < 16 && c0 + lane < WW) {
+                const long wi = row * WW + c0 + lane;
+                ws.srcbits[wi] = mys;
+                ws.valbits[wi] = myv;
+                ws.wprefix[wi] = (uint16_t)mypre;
+                ws.rowcell[wi] = (uint8_t)(((mys & 0xFFu) != 0) | (((mys & 0xFF00u) != 0) << 1) |
+                                           (((mys & 0xFF0000u) != 0) << 2) | (((mys & 0xFF000000u) != 0) << 3));
+            }
+        }
+        if (lane == 0) {
+            ws.rowsrc[row] = cs;
+            ws.rowval[row] = cv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1b: per frame -- exclusive scans of the row counts, depth_list compaction, task emission.
+// One 256-thread block per frame.
 // ------------------------------------------------------------------------------------------------------
 constexpr int K1B_THREADS = 512;
 
@@ -161,8 +363,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 // barrier among the 256 planner threads only (warps 8..15), so that the compaction warps are not held up
 __device__ __forceinline__ void planner_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __noinline__ void frame_finalize(const FrameParams& fp, const Workspace& ws, int32_t* __restrict__ out_counts,
-                                            const int b)
+__global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, Workspace ws,
+                                                                 int32_t* __restrict__ out_counts)
 {
     __shared__ uint32_t sm[K1B_THREADS / 32 + 1];
     __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
@@ -172,6 +374,7 @@ __device__ __noinline__ void frame_finalize(const FrameParams& fp, const Workspa
     __shared__ Task st[MAXT];                    // planner: tasks of this frame before ordering
     __shared__ int scost[MAXT];
     __shared__ int snt;
+    const int b = blockIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
@@ -436,226 +639,6 @@ __device__ __noinline__ void frame_finalize(const FrameParams& fp, const Workspa
             ws.tasks[(long)slot * B + b] = q;
         }
     }
-}
-
-// Tail of both K1 kernels: the block that completes a frame's last rows finalises the frame.
-__device__ __forceinline__ void k1_finish_frame(const FrameParams& fp, const Workspace& ws, int32_t* out_counts, int b)
-{
-    __shared__ int s_last;
-    __threadfence();                                   // this thread's row data is visible device-wide
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&ws.frame_done[b], 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        frame_finalize(fp, ws, out_counts, b);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// K1 (W % 4 == 0): predicates -> bit rows, per-word source prefix, coarse cells, row counts, validity mask,
-// and the row-local compaction of the valid depths (into ws.scratch, which K2 only uses later).
-// One warp per row; a lane owns 16 consecutive pixels of every 512-pixel chunk (four 128-bit loads).
-// The predicates are evaluated without branches: a > b  <=>  sign(b - a) for IEEE floats (a NaN operand gives
-// the canonical positive NaN, i.e. "false", like the comparison), and the sign bits of four differences are
-// gathered into a nibble with byte permutes and one multiply.
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, float t3)
-{
-    // top bytes of the four floats -> one word -> bits 7,15,23,31 -> nibble (multiply gathers them into 28..31)
-    const uint32_t p01 = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0073);   // [t0.b3, t1.b3, 0, 0]
-    const uint32_t p23 = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0073);
-    const uint32_t w = __byte_perm(p01, p23, 0x5410) & 0x80808080u;
-    return (w * 0x00204081u) >> 28;
-}
-
-__global__ void __launch_bounds__(K1B_THREADS) k1_mask_rows_v16(const float* __restrict__ in, FrameParams fp, Workspace ws,
-                                                                 uint8_t* __restrict__ out_mask,
-                                                                 int32_t* __restrict__ out_counts)
-{
-    const int lane = threadIdx.x & 31;
-    const int yrow = blockIdx.x * (K1B_THREADS / 32) + (threadIdx.x >> 5);      // grid: (row blocks, frames)
-    const int W = fp.W, WW = fp.WW;
-    const int nchunks = (W + 511) >> 9;
-    const float sthr = fp.src_thr, vthr = fp.val_thr;
-    const bool mask16 = (W & 15) == 0;
-    float* rowvals = reinterpret_cast<float*>(ws.scratch);
-    bool once = yrow < fp.H;
-    for (const long row = (long)blockIdx.y * fp.H + yrow; once; once = false) {
-        const float* rp = in + row * W;
-        uint32_t cs = 0, cv = 0;
-        // software pipeline over the 512-pixel chunks: the four 128-bit loads of the next chunk are issued (volatile
-        // asm, so they stay ahead) before the current chunk is processed
-        float4 nq[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-            nq[g] = lane * 16 + 4 * g < W ? ld_stream_v4(rp + lane * 16 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int col = (ch << 9) + lane * 16;
-            float4 q[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) q[g] = nq[g];
-            if (ch + 1 < nchunks) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    nq[g] = col + 512 + 4 * g < W ? ld_stream_v4(rp + col + 512 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            uint32_t sb = 0, vb = 0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr
-                const float d0 = __fsub_rn(1.0f, q[g].x), d1 = __fsub_rn(1.0f, q[g].y);
-                const float d2 = __fsub_rn(1.0f, q[g].z), d3 = __fsub_rn(1.0f, q[g].w);
-                const uint32_t ns = sign_nibble(__fsub_rn(sthr, d0), __fsub_rn(sthr, d1), __fsub_rn(sthr, d2),
-                                                __fsub_rn(sthr, d3));                       // bit = d > src_thr
-                const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
-                                                __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
-                const uint32_t inb = col + 4 * g < W ? 0xFu : 0u;
-                sb |= ((ns ^ 0xFu) & inb) << (4 * g);
-                vb |= (nv & inb) << (4 * g);
-            }
-            if (out_mask && col < W) {
-                uint32_t m[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
-                uint8_t* mp = out_mask + row * W + col;
-                if (mask16) {
-                    st_stream_v4(mp, m[0], m[1], m[2], m[3]);
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        if (col + 4 * g < W) st_stream_u32(mp + 4 * g, m[g]);
-                }
-            }
-            // 32-bit words from the halves of 2 neighbouring lanes
-            uint32_t sw = sb << ((lane & 1) * 16), vw = vb << ((lane & 1) * 16);
-            sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
-            vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
-            // coarse cells: bit j of the word's nibble = some source among its pixels 8j..8j+7
-            const uint32_t cell = ((sw & 0xFFu) != 0) | (((sw & 0xFF00u) != 0) << 1) | (((sw & 0xFF0000u) != 0) << 2) |
-                                  (((sw & 0xFF000000u) != 0) << 3);
-            const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);
-            const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
-            uint32_t spre = 0, stot = 0;
-            if (sany) {
-                const uint32_t c = __popc(sb);
-                uint32_t inc = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                spre = inc - c;
-                stot = __shfl_sync(0xffffffffu, inc, 31);
-            }
-            const int w = (ch << 4) + (lane >> 1);
-            if ((lane & 1) == 0 && w < WW) {
-                const long wi = row * WW + w;
-                ws.srcbits[wi] = sw;
-                ws.valbits[wi] = vw;
-                ws.wprefix[wi] = (uint16_t)(cs + spre);
-                ws.rowcell[wi] = (uint8_t)cell;
-            }
-            cs += stot;
-            if (vany) {
-                const uint32_t c = __popc(vb);
-                uint32_t inc = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                // few pixels per lane are valid (~5 % density): walk the set bits and re-read the values (L1 hits)
-                float* dst = rowvals + row * W + cv + (inc - c);
-                const float* xs = rp + col;
-                uint32_t m = vb;
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    *dst++ = __ldg(xs + j);
-                }
-                cv += __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        if (lane == 0) {
-            ws.rowsrc[row] = cs;
-            ws.rowval[row] = cv;
-        }
-    }
-    k1_finish_frame(fp, ws, out_counts, blockIdx.y);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// K1 for widths that are not a multiple of 4 (no 128-bit row alignment): same outputs, scalar loads + ballots.
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K1B_THREADS) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
-                                                             uint8_t* __restrict__ out_mask,
-                                                             int32_t* __restrict__ out_counts)
-{
-    const int lane = threadIdx.x & 31;
-    const int yrow = blockIdx.x * (K1B_THREADS / 32) + (threadIdx.x >> 5);      // grid: (row blocks, frames)
-    const int W = fp.W, WW = fp.WW;
-    const bool vec_mask = (W & 3) == 0;
-    const uint32_t ltmask = lanemask_lt();
-    float* rowvals = reinterpret_cast<float*>(ws.scratch);
-    bool once = yrow < fp.H;
-    for (const long row = (long)blockIdx.y * fp.H + yrow; once; once = false) {
-        const float* rp = in + row * W;
-        uint32_t cs = 0, cv = 0;
-        for (int c0 = 0; c0 < WW; c0 += 16) {
-            float x[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int col = (c0 + k) * 32 + lane;
-                x[k] = col < W ? ld_stream(rp + col) : 0.0f;
-            }
-            uint32_t mys = 0, myv = 0, mypre = 0;
-            uint32_t vq[4];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int col = (c0 + k) * 32 + lane;
-                const bool inb = col < W;
-                const float d = __fsub_rn(1.0f, x[k]);                 // tools.py:8  1.0 - x  (float32)
-                const bool sp = inb && !(d > fp.src_thr);             // value_mask == 0  <=> source
-                const bool vp = inb && (x[k] > fp.val_thr);           // tools.py:22 with_value
-                const uint32_t sw = __ballot_sync(0xffffffffu, sp);
-                const uint32_t vw = __ballot_sync(0xffffffffu, vp);
-                if (lane == k) { mys = sw; myv = vw; mypre = cs; }
-                if (vp) rowvals[row * W + cv + __popc(vw & ltmask)] = x[k];
-                cs += __popc(sw);
-                cv += __popc(vw);
-                vq[k & 3] = vw;
-                if (out_mask) {
-                    if (vec_mask) {
-                        if ((k & 3) == 3) {
-                            const int col4 = (c0 + k - 3) * 32 + lane * 4;
-                            if (col4 < W) {
-                                const int q = lane >> 3;
-                                const uint32_t word = q == 0 ? vq[0] : q == 1 ? vq[1] : q == 2 ? vq[2] : vq[3];
-                                const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;
-                                st_stream_u32(out_mask + row * W + col4, (nib * 0x00204081u) & 0x01010101u);
-                            }
-                        }
-                    } else if (inb) {
-                        out_mask[row * W + col] = (uint8_t)vp;
-                    }
-                }
-            }
-            if (lane < 16 && c0 + lane < WW) {
-                const long wi = row * WW + c0 + lane;
-                ws.srcbits[wi] = mys;
-                ws.valbits[wi] = myv;
-                ws.wprefix[wi] = (uint16_t)mypre;
-                ws.rowcell[wi] = (uint8_t)(((mys & 0xFFu) != 0) | (((mys & 0xFF00u) != 0) << 1) |
-                                           (((mys & 0xFF0000u) != 0) << 2) | (((mys & 0xFF000000u) != 0) << 3));
-            }
-        }
-        if (lane == 0) {
-            ws.rowsrc[row] = cs;
-            ws.rowval[row] = cv;
-        }
-    }
-    k1_finish_frame(fp, ws, out_counts, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------------
