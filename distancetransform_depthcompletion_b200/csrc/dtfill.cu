@@ -267,7 +267,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     const int scratch_units_per_frame = plan.ppl ? 3 * H * plan.ppl : (int)(((size_t)H * W + 31) / 32);
     if ((rc = ensure(h, h->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
-    if ((rc = ensure(h, h->status, 16))) return rc;
+    if ((rc = ensure(h, h->status, 256))) return rc;
     {
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
         static size_t configured = 0;
@@ -558,6 +558,14 @@ int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks) {
     if (n > max_tasks) n = max_tasks;
     if (n > 0) CU(cudaMemcpy(out, h->tasks.p, (size_t)n * sizeof(Task), cudaMemcpyDeviceToHost));
     return (int)n;
+}
+
+int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n) {
+    if (!h || !out || n < 0 || n > 64) return fail(DTFILL_E_ARG, "dtfill_debug_read_status: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out, h->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int dtfill_set_subbatches(dtfill_t* h, int n) {

@@ -383,6 +383,12 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
     uint32_t* rs = ws.rowsrc + (long)b * H;
     uint32_t* rv = ws.rowval + (long)b * H;
 
+#ifdef DTFILL_PLANNER_CLOCKS     // phase clocks of block 0 (profiles/k1b_clock.py reads them through dtfill_debug_read_status)
+    const long long dbg_t0 = clock64();
+    auto dbg_mark = [&](int k) { if (b == 0 && (tid == 0 || tid == 256)) ws.status[4 + k + (tid ? 8 : 0)] = (int)(clock64() - dbg_t0); };
+#else
+    auto dbg_mark = [](int) {};
+#endif
     if (tid < 128) srcrows[tid] = 0;
     uint32_t ls = 0, lv = 0;
     for (int y = y0; y < y1; ++y) { ls += rs[y]; lv += rv[y]; }
@@ -397,6 +403,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
     }
     __syncthreads();
 
+    dbg_mark(0);
     const int B = fp.B;
     int kind = (nsrc == 0) ? TASK_NOSRC : ((fp.force_wide || nsrc > MAX_FAST_LABEL) ? TASK_WIDE : TASK_CHAMFER);
     if (nval == 0) kind = TASK_SKIP;
@@ -436,6 +443,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 }
             }
         }
+        dbg_mark(1);
         return;
     }
 
@@ -467,57 +475,96 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
             }
         }
         planner_sync();
+        dbg_mark(1);
         for (int i = ptid; i < nh * nw; i += 256) {
             const int cy = i / nw, cx = i - cy * nw;
             cellD[i] = ((occw[cy * WW + (cx >> 2)] >> (cx & 3)) & 1u) ? 0 : 60000;
         }
         planner_sync();
+        dbg_mark(2);
         for (int cx = ptid; cx < nw; cx += 256) {        // vertical sweeps, one thread per cell column
             uint32_t d = 60000;
-            for (int cy = 0; cy < nh; ++cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+            for (int c0 = 0; c0 < nh; c0 += 8) {         // 8 loads ahead of the dependent (min,+) chain
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = c0 + k < nh ? (uint32_t)cellD[(c0 + k) * nw + cx] : 60000u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    d = min(min(d + CELL_H, v[k]), 60000u);
+                    if (c0 + k < nh) cellD[(c0 + k) * nw + cx] = (uint16_t)d;
+                }
+            }
             d = 60000;
-            for (int cy = nh - 1; cy >= 0; --cy) { d = min(d + CELL_H, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+            for (int c0 = nh - 1; c0 >= 0; c0 -= 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = c0 - k >= 0 ? (uint32_t)cellD[(c0 - k) * nw + cx] : 60000u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    d = min(min(d + CELL_H, v[k]), 60000u);
+                    if (c0 - k >= 0) cellD[(c0 - k) * nw + cx] = (uint16_t)d;
+                }
+            }
         }
         planner_sync();
-        // horizontal sweeps, one warp per cell row: lanes own contiguous chunks, (min,+) scans via shuffles
+        dbg_mark(3);
+        // horizontal sweeps, one warp per cell row: a lane keeps its (up to 8) consecutive cells in registers,
+        // (min,+) scans across lanes via shuffles; only the row maximum leaves the warp
         const int chunk = (nw + 31) / 32;
-        for (int cy = pw; cy < nh; cy += 8) {
-            uint16_t* rowp = cellD + cy * nw;
-            const int xa = min(nw, lane * chunk), xb = min(nw, xa + chunk);
-            // left -> right: value entering the chunk from the lanes before it
-            uint32_t d = 60000;
-            for (int x = xa; x < xb; ++x) d = min(d + CELL_W, (uint32_t)rowp[x]);
-            uint32_t e = d;                               // chunk-local distance at its last cell
+        if (chunk <= 8) {
+            for (int cy = pw; cy < nh; cy += 8) {
+                const uint16_t* rowp = cellD + cy * nw;
+                const int xa = lane * chunk;
+                uint32_t v[8];
 #pragma unroll
-            for (int s_ = 1; s_ < 32; s_ <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, e, s_);
-                if (lane >= s_) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+                for (int k = 0; k < 8; ++k) v[k] = (k < chunk && xa + k < nw) ? (uint32_t)rowp[xa + k] : 120000u;
+                // left -> right
+                uint32_t d = 120000u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k < chunk) d = min(d + CELL_W, v[k]);
+                uint32_t e = d;
+#pragma unroll
+                for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, e, s_);
+                    if (lane >= s_) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+                }
+                uint32_t cin = __shfl_up_sync(0xffffffffu, e, 1);
+                d = lane == 0 ? 120000u : cin;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k < chunk) { d = min(d + CELL_W, v[k]); v[k] = d; }
+                // right -> left
+                d = 120000u;
+#pragma unroll
+                for (int k = 7; k >= 0; --k) if (k < chunk) d = min(d + CELL_W, v[k]);
+                e = d;
+#pragma unroll
+                for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                    const uint32_t o = __shfl_down_sync(0xffffffffu, e, s_);
+                    if (lane + s_ < 32) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+                }
+                cin = __shfl_down_sync(0xffffffffu, e, 1);
+                d = lane == 31 ? 120000u : cin;
+                uint32_t mx = 0;
+#pragma unroll
+                for (int k = 7; k >= 0; --k)
+                    if (k < chunk) { d = min(d + CELL_W, v[k]); if (xa + k < nw) mx = max(mx, d); }
+#pragma unroll
+                for (int s_ = 16; s_ > 0; s_ >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s_));
+                if (lane == 0) cellU[cy] = (int)min(mx, 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
             }
-            uint32_t cin = __shfl_up_sync(0xffffffffu, e, 1);
-            if (lane == 0) cin = 60000;
-            d = min(cin, 60000u);
-            for (int x = xa; x < xb; ++x) { d = min(d + CELL_W, (uint32_t)rowp[x]); rowp[x] = (uint16_t)min(d, 60000u); }
-            __syncwarp();
-            // right -> left, and the row maximum
-            d = 60000;
-            for (int x = xb - 1; x >= xa; --x) d = min(d + CELL_W, (uint32_t)rowp[x]);
-            e = xb > xa ? d : 60000u;
-#pragma unroll
-            for (int s_ = 1; s_ < 32; s_ <<= 1) {
-                const uint32_t o = __shfl_down_sync(0xffffffffu, e, s_);
-                if (lane + s_ < 32) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+        } else {
+            for (int cy = pw * 32 + lane; cy < nh; cy += 256) {      // very wide frames: one thread per cell row
+                uint32_t d = 60000;
+                for (int cx = 0; cx < nw; ++cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
+                d = 60000;
+                uint32_t mx = 0;
+                for (int cx = nw - 1; cx >= 0; --cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); mx = max(mx, min(d, 60000u)); }
+                cellU[cy] = (int)mx + (CELL_H - 1) + (CELL_W - 1);
             }
-            cin = __shfl_down_sync(0xffffffffu, e, 1);
-            if (lane == 31) cin = 60000;
-            d = min(cin, 60000u);
-            uint32_t mx = 0;
-            for (int x = xb - 1; x >= xa; --x) { d = min(d + CELL_W, (uint32_t)rowp[x]); mx = max(mx, min(d, 60000u)); }
-#pragma unroll
-            for (int s_ = 16; s_ > 0; s_ >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s_));
-            if (lane == 0) cellU[cy] = (int)mx + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
         }
         planner_sync();
     }
+    dbg_mark(4);
 
     if (ptid == 0) {
         ws.counts[2 * b] = (int)nsrc;
@@ -608,6 +655,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         }
         snt = nt;
     }
+    dbg_mark(5);
     planner_sync();
     // ---- all planner threads: order the tasks (longest first: the block scheduler hands out blocks in index
     // order, slot-major task array), fill in the forward start rows, write the 32 slots of this frame
@@ -639,6 +687,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
             ws.tasks[(long)slot * B + b] = q;
         }
     }
+    dbg_mark(6);
 }
 
 // ------------------------------------------------------------------------------------------------------
