@@ -233,29 +233,45 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        eng.fill(x, src_thr=src_thr, out=out)
-    bad, launches_per_step = eng.status()
-    assert bad == -1, f"unexpected bad frame {bad}"
+    # two output sets: with two batches in flight (pipeline depth 2) consecutive steps must not share outputs
+    outs = [out, {k: torch.empty_like(v) for k, v in out.items()}]
 
-    # ---- device-resident timing: exactly K steps between two events on the launching stream ----
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.fill(x, src_thr=src_thr, out=out)
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def timed_steps(depth):
+        """Exactly K steps between two events on the launching stream; max over ranks."""
+        eng.handle.set_pipeline_depth(depth)
+        for i in range(args.warmup):
+            eng.fill(x, src_thr=src_thr, out=outs[i & 1])
+        bad_, launches_ = eng.status()
+        assert bad_ == -1, f"unexpected bad frame {bad_}"
+        sampler_ = ClockSampler(local_rank)
+        barrier()
+        sampler_.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            eng.fill(x, src_thr=src_thr, out=outs[i & 1])
+        eng.flush()                                   # every step's outputs are complete at e1
+        e1.record()
+        barrier()
+        clocks_ = sampler_.stop()
+        ms_ = e0.elapsed_time(e1)
+        if dist is not None:
+            t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_, launches_, clocks_
+
+    ms_strict, launches_per_step, clocks_strict = timed_steps(1)
+    if args.pipeline > 1:
+        ms, launches_per_step, clocks = timed_steps(args.pipeline)
+    else:
+        ms, clocks = ms_strict, clocks_strict
+    eng.handle.set_pipeline_depth(1)
+    assert torch.equal(outs[0]["depth"], outs[1]["depth"]) and torch.equal(outs[0]["dt"], outs[1]["dt"])
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
+    strict = {"value": world * B * args.steps / (ms_strict * 1e-3), "ms_per_step": ms_strict / args.steps,
+              "what": "same K steps with strict stream order between steps (pipeline depth 1)"}
 
     # ---- per-kernel shares (CUDA events between the launches, same stream), separate untimed steps ----
     eng.handle.set_profiling(True)
@@ -337,7 +353,11 @@ def run_ours(args, rank, world, local_rank):
                                f"{args.workload}: batch of {B} synthetic frames {H}x{W} per GPU",
                    "outputs": "filled depth f32 + distance channel f32 + validity mask u8 (13 B/px algorithmic)",
                    "l2": f"inputs+outputs per step {ALG_BYTES_PER_PX * px_step / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
-                   "frames_per_step_per_gpu": B},
+                   "frames_per_step_per_gpu": B,
+                   "pipeline": (f"{args.pipeline} batches in flight (dtfill_set_pipeline_depth): K1/K1b of step n+1 "
+                                "overlap K2 of step n; two output sets alternate; all outputs complete at the end "
+                                "of the timed region") if args.pipeline > 1 else "strict stream order between steps"},
+        "strict": strict,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W * 4),
                 "d2h_bytes_per_step": int(B * H * W * 9), "steps": e2e_steps,
@@ -359,6 +379,8 @@ def main():
     ap.add_argument("--workload", default="kitti64", choices=sorted(WORKLOADS),
                     help="kitti64 is the BASELINE.json metric; the others are the remaining configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="batches in flight in the device-resident timing (1 = strict stream order)")
     ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
     ap.add_argument("--subbatches", type=int, default=None, help="override the number of sub-batch streams")
     args = ap.parse_args()

@@ -55,6 +55,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
         L.dtfill_set_subbatches.argtypes = [vp, ci]
+        L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
+        L.dtfill_flush.argtypes = [vp]
         L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
         L.dtfill_debug_get_tasks.restype = ci
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
@@ -62,7 +64,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
-                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches",
+                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
+                     "dtfill_flush",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
@@ -165,6 +168,14 @@ class Handle:
     def set_band_cap(self, cap: int):
         """Band planner target (row steps per task): >0 explicit, 0 never split frames, -1 automatic."""
         _check(self._L.dtfill_set_band_cap(self._h, int(cap)), "dtfill_set_band_cap")
+
+    def set_pipeline_depth(self, depth: int):
+        """2: consecutive run_device_async calls may overlap (outputs final after flush()/status()); 1: strict."""
+        _check(self._L.dtfill_set_pipeline_depth(self._h, int(depth)), "dtfill_set_pipeline_depth")
+
+    def flush(self):
+        """Pipelined mode: make the handle's stream wait for every call still in flight."""
+        _check(self._L.dtfill_flush(self._h), "dtfill_flush")
 
     def set_subbatches(self, n: int):
         """Number of sub-batches run on forked streams (<= 0: automatic)."""

@@ -34,26 +34,40 @@ struct Buf {
 
 }  // namespace
 
+// One "lane" = everything a call needs while it is in flight: workspace, streams, events.  A handle has two, so
+// that in pipelined mode (dtfill_set_pipeline_depth 2) the HBM-bound first stage of one call overlaps the ALU-bound
+// scan of the previous call.
+struct Lane {
+    static const int MAX_SUB = 8;
+    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status;
+    int* status_host = nullptr;          // pinned [2]
+    cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
+    cudaStream_t side[MAX_SUB] = {};     // narrow tiles run next to the full-width tasks of the same sub-batch
+    cudaEvent_t side_fork[MAX_SUB] = {}, side_join[MAX_SUB] = {};
+    cudaStream_t pipe = nullptr;         // pipelined mode: the stream this lane's calls run on
+    cudaEvent_t done = nullptr;          // ... and the end of its last call
+    bool pending = false;                // done not yet waited for by the handle's stream
+    bool dirty = false;                  // status_host not yet examined by dtfill_status
+    int last_launches = 0;
+    int last_B = 0;
+};
+
 struct dtfill_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    // workspace
-    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status;
+    Lane lanes[2];
+    int ncalls = 0;                   // calls enqueued so far (pipelined mode alternates lanes)
+    int last_lane = 0;
+    int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
+    cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
-    int* status_host = nullptr;   // pinned [2]
     int32_t* counts_host = nullptr;   // pinned staging for out_counts (a pageable destination would serialise the
     size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
-    int last_launches = 0;
-    int last_B = 0;
     bool profiling = false;
-    static const int MAX_SUB = 8;
-    cudaStream_t sub[MAX_SUB] = {};     // sub-batch streams: K2 (ALU bound) of one sub-batch overlaps K1 (HBM bound) of the next
-    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
-    cudaStream_t side[MAX_SUB] = {};    // half-width tiles run next to the full-width tasks of the same sub-batch
-    cudaEvent_t side_fork[MAX_SUB] = {}, side_join[MAX_SUB] = {};
     bool tiles2d = true;
     int nsub = -1;                // -1: automatic
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
@@ -65,7 +79,8 @@ namespace {
 int ensure(dtfill_t* h, Buf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) {
-        CU(cudaStreamSynchronize(h->stream));
+        (void)h;
+        CU(cudaDeviceSynchronize());
         CU(cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -139,7 +154,7 @@ void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FramePar
 
 // Enqueue the path for frames [b0, b0+nb) of the batch on stream s; all pointers are device pointers to the whole
 // batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
-int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
+int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
                   float src_thr, float val_thr, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
                   int32_t* out_counts, int scratch_units_per_frame, int sub_index, int* launches) {
     const int WW = (W + 31) / 32;
@@ -173,17 +188,17 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
         fp.band_cap = plan.ppl ? cap : 0;
     }
     Workspace ws;
-    ws.srcbits = (uint32_t*)h->srcbits.p + rows0 * WW;
-    ws.valbits = (uint32_t*)h->valbits.p + rows0 * WW;
-    ws.wprefix = (uint16_t*)h->wprefix.p + rows0 * WW;
-    ws.rowcell = (uint8_t*)h->rowcell.p + rows0 * WW;
-    ws.rowsrc = (uint32_t*)h->rowsrc.p + rows0;
-    ws.rowval = (uint32_t*)h->rowval.p + rows0;
-    ws.counts = (int32_t*)h->counts.p + 2 * (size_t)b0;
-    ws.dlist = (float*)h->dlist.p + npx0;
-    ws.scratch = (uint32_t*)h->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
-    ws.tasks = (Task*)h->tasks.p + (size_t)b0 * MAXT;
-    ws.status = (int*)h->status.p;
+    ws.srcbits = (uint32_t*)L->srcbits.p + rows0 * WW;
+    ws.valbits = (uint32_t*)L->valbits.p + rows0 * WW;
+    ws.wprefix = (uint16_t*)L->wprefix.p + rows0 * WW;
+    ws.rowcell = (uint8_t*)L->rowcell.p + rows0 * WW;
+    ws.rowsrc = (uint32_t*)L->rowsrc.p + rows0;
+    ws.rowval = (uint32_t*)L->rowval.p + rows0;
+    ws.counts = (int32_t*)L->counts.p + 2 * (size_t)b0;
+    ws.dlist = (float*)L->dlist.p + npx0;
+    ws.scratch = (uint32_t*)L->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
+    ws.tasks = (Task*)L->tasks.p + (size_t)b0 * MAXT;
+    ws.status = (int*)L->status.p;
     const float* in_s = in + npx0;
     float* od = out_depth + npx0;
     float* odt = out_dt ? out_dt + npx0 : nullptr;
@@ -208,13 +223,13 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
     // half-width tiles run on a side stream next to the full-width tasks (different kernel instances)
     cudaStream_t s2 = s;
     if (fp.narrow_ppl) {
-        s2 = h->side[sub_index];
-        CU(cudaEventRecord(h->side_fork[sub_index], s));
-        CU(cudaStreamWaitEvent(s2, h->side_fork[sub_index], 0));
+        s2 = L->side[sub_index];
+        CU(cudaEventRecord(L->side_fork[sub_index], s));
+        CU(cudaStreamWaitEvent(s2, L->side_fork[sub_index], 0));
         if (fp.narrow_ppl == 20) launch_k2<20>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
         else launch_k2<10>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
         ++*launches;
-        CU(cudaEventRecord(h->side_join[sub_index], s2));
+        CU(cudaEventRecord(L->side_join[sub_index], s2));
     }
     switch (plan.ppl) {
         case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
@@ -230,7 +245,7 @@ int enqueue_range(dtfill_t* h, cudaStream_t s, const Plan& plan, int b0, int nb,
         k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
-    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, h->side_join[sub_index], 0));
+    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
     if (h->profiling) {
         CU(cudaEventRecord(h->ev[3], s));
         k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
@@ -248,26 +263,29 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((long)H + W >= 60000 || (long)H * W >= (1l << 31) || W > 28000)
         return fail(DTFILL_E_ARG, "dtfill_run: frame size not supported (H + W < 60000, W <= 28000)");
     CU(cudaSetDevice(h->device));
+    // lane and stream of this call
+    const bool pipelined = h->pipeline_depth > 1 && !h->profiling && !hio;
+    Lane* L = &h->lanes[pipelined ? (h->ncalls & 1) : 0];
     const Plan plan = make_plan(H, W);
     const int WW = (W + 31) / 32;
     const size_t rows = (size_t)B * H;
     const size_t npx = rows * W;
 
     int rc;
-    if ((rc = ensure(h, h->srcbits, rows * WW * 4))) return rc;
-    if ((rc = ensure(h, h->valbits, rows * WW * 4))) return rc;
-    if ((rc = ensure(h, h->wprefix, rows * WW * 2))) return rc;
-    if ((rc = ensure(h, h->rowcell, rows * WW))) return rc;
-    if ((rc = ensure(h, h->rowsrc, rows * 4))) return rc;
-    if ((rc = ensure(h, h->rowval, rows * 4))) return rc;
-    if ((rc = ensure(h, h->counts, (size_t)B * 8))) return rc;
-    if ((rc = ensure(h, h->dlist, npx * 4))) return rc;
+    if ((rc = ensure(h, L->srcbits, rows * WW * 4))) return rc;
+    if ((rc = ensure(h, L->valbits, rows * WW * 4))) return rc;
+    if ((rc = ensure(h, L->wprefix, rows * WW * 2))) return rc;
+    if ((rc = ensure(h, L->rowcell, rows * WW))) return rc;
+    if ((rc = ensure(h, L->rowsrc, rows * 4))) return rc;
+    if ((rc = ensure(h, L->rowval, rows * 4))) return rc;
+    if ((rc = ensure(h, L->counts, (size_t)B * 8))) return rc;
+    if ((rc = ensure(h, L->dlist, npx * 4))) return rc;
     // forward-state scratch in units of 32 keys: tiles overlap by their halos, so allow 3 H full-width rows per
     // frame (the 64-bit-key path keeps one u32 per pixel there; K1 parks H*W floats there as well)
     const int scratch_units_per_frame = plan.ppl ? 3 * H * plan.ppl : (int)(((size_t)H * W + 31) / 32);
-    if ((rc = ensure(h, h->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
-    if ((rc = ensure(h, h->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
-    if ((rc = ensure(h, h->status, 256))) return rc;
+    if ((rc = ensure(h, L->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
+    if ((rc = ensure(h, L->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
+    if ((rc = ensure(h, L->status, 256))) return rc;
     {
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
         static size_t configured = 0;
@@ -279,17 +297,28 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     }
 
     cudaStream_t s = h->stream;
+    if (pipelined) {
+        // this call runs on the lane's own stream, behind whatever the caller queued so far and behind the lane's
+        // previous call (stream order); the handle's stream only joins at dtfill_flush / dtfill_status
+        CU(cudaEventRecord(h->pipe_fork, h->stream));
+        CU(cudaStreamWaitEvent(L->pipe, h->pipe_fork, 0));
+        s = L->pipe;
+    } else {
+        // strict mode: everything still in flight on the lanes joins the handle's stream first
+        for (Lane& o : h->lanes)
+            if (o.pending) { CU(cudaStreamWaitEvent(h->stream, o.done, 0)); o.pending = false; }
+    }
     int launches = 0;
-    h->status_host[0] = INT_MAX;
-    h->status_host[1] = 0;
-    CU(cudaMemcpyAsync(h->status.p, h->status_host, 8, cudaMemcpyHostToDevice, s));
+    L->status_host[0] = INT_MAX;
+    L->status_host[1] = 0;
+    CU(cudaMemcpyAsync(L->status.p, L->status_host, 8, cudaMemcpyHostToDevice, s));
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
     // device-resident data: sub-batches do not pay (the scan is bound by per-task latency).  Host buffers: slices
     // pipeline the PCIe copies in both directions with the kernels.
     if (nsub <= 0) nsub = hio ? (B >= 32 ? 8 : (B >= 4 ? 4 : 1)) : 1;
-    if (nsub > dtfill_ctx::MAX_SUB) nsub = dtfill_ctx::MAX_SUB;
+    if (nsub > Lane::MAX_SUB) nsub = Lane::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
     auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
@@ -312,26 +341,33 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     };
     if (nsub == 1) {
         if ((rc = copy_in(s, 0, B))) return rc;
-        if ((rc = enqueue_range(h, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
+        if ((rc = enqueue_range(h, L, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
                                 out_counts, scratch_units_per_frame, 0, &launches))) return rc;
         if ((rc = copy_out(s, 0, B))) return rc;
     } else {
-        CU(cudaEventRecord(h->fork_ev, s));
+        CU(cudaEventRecord(L->fork_ev, s));
         for (int i = 0; i < nsub; ++i) {
             const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
-            CU(cudaStreamWaitEvent(h->sub[i], h->fork_ev, 0));
-            if ((rc = copy_in(h->sub[i], b0, b1 - b0))) return rc;
-            if ((rc = enqueue_range(h, h->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
+            CU(cudaStreamWaitEvent(L->sub[i], L->fork_ev, 0));
+            if ((rc = copy_in(L->sub[i], b0, b1 - b0))) return rc;
+            if ((rc = enqueue_range(h, L, L->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
                                     out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return rc;
-            if ((rc = copy_out(h->sub[i], b0, b1 - b0))) return rc;
-            CU(cudaEventRecord(h->join_ev[i], h->sub[i]));
-            CU(cudaStreamWaitEvent(s, h->join_ev[i], 0));
+            if ((rc = copy_out(L->sub[i], b0, b1 - b0))) return rc;
+            CU(cudaEventRecord(L->join_ev[i], L->sub[i]));
+            CU(cudaStreamWaitEvent(s, L->join_ev[i], 0));
         }
     }
-    CU(cudaMemcpyAsync(h->status_host, h->status.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(L->status_host, L->status.p, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
-    h->last_launches = launches;
-    h->last_B = B;
+    if (pipelined) {
+        CU(cudaEventRecord(L->done, s));
+        L->pending = true;
+    }
+    L->dirty = true;
+    L->last_launches = launches;
+    L->last_B = B;
+    h->last_lane = (int)(L - h->lanes);
+    ++h->ncalls;
     return 0;
 }
 
@@ -362,21 +398,27 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     h->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    CU(cudaHostAlloc((void**)&h->status_host, 16, cudaHostAllocDefault));
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
-    CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-    for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
-        CU(cudaStreamCreateWithFlags(&h->sub[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
-        CU(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&h->side_fork[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&h->side_join[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->pipe_fork, cudaEventDisableTiming));
+    for (Lane& L : h->lanes) {
+        CU(cudaHostAlloc((void**)&L.status_host, 16, cudaHostAllocDefault));
+        L.status_host[0] = INT_MAX;
+        L.status_host[1] = 0;
+        CU(cudaStreamCreateWithFlags(&L.pipe, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L.fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < Lane::MAX_SUB; ++i) {
+            CU(cudaStreamCreateWithFlags(&L.sub[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&L.join_ev[i], cudaEventDisableTiming));
+            CU(cudaStreamCreateWithFlags(&L.side[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&L.side_fork[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&L.side_join[i], cudaEventDisableTiming));
+        }
     }
     if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
-    h->status_host[0] = INT_MAX;
-    h->status_host[1] = 0;
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
+    if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) h->pipeline_depth = atoi(e) > 1 ? 2 : 1;
     *out_handle = h;
     return 0;
 }
@@ -384,37 +426,68 @@ int dtfill_create(int device, dtfill_t** out_handle) {
 void dtfill_destroy(dtfill_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    Buf* bufs[] = {&h->srcbits, &h->valbits, &h->wprefix, &h->rowcell, &h->rowsrc, &h->rowval, &h->counts, &h->dlist,
-                   &h->scratch, &h->tasks, &h->status, &h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev,
-                   &h->mask_dev, &h->counts_out_dev, &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
+    cudaDeviceSynchronize();
+    for (Lane& L : h->lanes) {
+        Buf* lb[] = {&L.srcbits, &L.valbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
+                     &L.scratch, &L.tasks, &L.status};
+        for (Buf* b : lb)
+            if (b->p) cudaFree(b->p);
+        if (L.status_host) cudaFreeHost(L.status_host);
+        if (L.fork_ev) cudaEventDestroy(L.fork_ev);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.pipe) cudaStreamDestroy(L.pipe);
+        for (int i = 0; i < Lane::MAX_SUB; ++i) {
+            if (L.join_ev[i]) cudaEventDestroy(L.join_ev[i]);
+            if (L.sub[i]) cudaStreamDestroy(L.sub[i]);
+            if (L.side_fork[i]) cudaEventDestroy(L.side_fork[i]);
+            if (L.side_join[i]) cudaEventDestroy(L.side_join[i]);
+            if (L.side[i]) cudaStreamDestroy(L.side[i]);
+        }
+    }
+    Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->gt_dev,
+                   &h->partial, &h->per_frame, &h->sums};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
-    if (h->status_host) cudaFreeHost(h->status_host);
     if (h->counts_host) cudaFreeHost(h->counts_host);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
-    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
-    for (int i = 0; i < dtfill_ctx::MAX_SUB; ++i) {
-        if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
-        if (h->sub[i]) cudaStreamDestroy(h->sub[i]);
-        if (h->side_fork[i]) cudaEventDestroy(h->side_fork[i]);
-        if (h->side_join[i]) cudaEventDestroy(h->side_join[i]);
-        if (h->side[i]) cudaStreamDestroy(h->side[i]);
-    }
+    if (h->pipe_fork) cudaEventDestroy(h->pipe_fork);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
+// Make the handle's stream wait for every call still in flight on the lanes (pipelined mode).
+int dtfill_flush(dtfill_t* h) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_flush: NULL handle");
+    CU(cudaSetDevice(h->device));
+    for (Lane& L : h->lanes)
+        if (L.pending) { CU(cudaStreamWaitEvent(h->stream, L.done, 0)); L.pending = false; }
+    return 0;
+}
+
+int dtfill_set_pipeline_depth(dtfill_t* h, int depth) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_pipeline_depth: NULL handle");
+    int rc = dtfill_flush(h);
+    if (rc) return rc;
+    h->pipeline_depth = depth > 1 ? 2 : 1;
+    return 0;
+}
+
 int dtfill_set_stream(dtfill_t* h, void* cuda_stream) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_stream: NULL handle");
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    cudaStream_t ns = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (ns != h->stream) {
+        int rc = dtfill_flush(h);          // work in flight joins the stream it was issued against
+        if (rc) return rc;
+        h->stream = ns;
+    }
     return 0;
 }
 
 int dtfill_synchronize(dtfill_t* h) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_synchronize: NULL handle");
-    CU(cudaSetDevice(h->device));
+    int rc = dtfill_flush(h);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -428,10 +501,13 @@ int dtfill_run_async(dtfill_t* h, const float* in_dev, int B, int H, int W, floa
 
 int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_status: NULL handle");
-    CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
-    if (kernel_launches) *kernel_launches = h->last_launches;
-    const int bad = h->status_host[0];
+    int rc = dtfill_synchronize(h);
+    if (rc) return rc;
+    if (kernel_launches) *kernel_launches = h->lanes[h->last_lane].last_launches;
+    // calls examined: every one since the previous dtfill_status (one per lane at most in pipelined mode)
+    int bad = INT_MAX;
+    for (Lane& L : h->lanes)
+        if (L.dirty) { bad = L.status_host[0] < bad ? L.status_host[0] : bad; L.dirty = false; }
     if (first_bad_frame) *first_bad_frame = (bad == INT_MAX) ? -1 : bad;
     if (bad != INT_MAX)
         return fail(DTFILL_E_INDEX, "frame " + std::to_string(bad) +
@@ -499,6 +575,7 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_metrics: B, H, W must be positive");
     if (mode != DTFILL_METRICS_KITTI && mode != DTFILL_METRICS_NYU) return fail(DTFILL_E_ARG, "dtfill_metrics: bad mode");
     CU(cudaSetDevice(h->device));
+    { int frc = dtfill_flush(h); if (frc) return frc; }      // pipelined fills feeding this evaluation
     const long npx = (long)H * W;
     const size_t tot = (size_t)B * npx;
     const size_t gsz = gt_is_f64 ? 8 : 4;
@@ -534,7 +611,6 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
     }
     k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, mode, pf_d, sm_d);
     CU(cudaGetLastError());
-    h->last_launches = 2;
     if (!out_is_device) {
         if (per_frame) CU(cudaMemcpyAsync(per_frame, pf_d, (size_t)B * 9 * 8, cudaMemcpyDeviceToHost, s));
         if (sums) CU(cudaMemcpyAsync(sums, sm_d, 10 * 8, cudaMemcpyDeviceToHost, s));
@@ -553,10 +629,11 @@ int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks) {
     if (!h || !out || max_tasks < 0) return fail(DTFILL_E_ARG, "dtfill_debug_get_tasks: bad argument");
     static_assert(sizeof(Task) == 48, "Task layout is part of the debug ABI");
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
-    long n = (long)h->last_B * MAXT;
+    { int rc = dtfill_synchronize(h); if (rc) return rc; }
+    const Lane& L = h->lanes[h->last_lane];
+    long n = (long)L.last_B * MAXT;
     if (n > max_tasks) n = max_tasks;
-    if (n > 0) CU(cudaMemcpy(out, h->tasks.p, (size_t)n * sizeof(Task), cudaMemcpyDeviceToHost));
+    if (n > 0) CU(cudaMemcpy(out, L.tasks.p, (size_t)n * sizeof(Task), cudaMemcpyDeviceToHost));
     return (int)n;
 }
 
@@ -564,7 +641,7 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n) {
     if (!h || !out || n < 0 || n > 64) return fail(DTFILL_E_ARG, "dtfill_debug_read_status: bad argument");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(out, h->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, h->lanes[h->last_lane].status.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

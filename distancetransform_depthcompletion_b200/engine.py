@@ -10,11 +10,16 @@ from . import _lib
 class DTFillEngine:
     """Runs DT + NN fill (+ metrics) on torch CUDA tensors, on torch's current stream, without host copies."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, pipeline_depth: int = 1):
+        """pipeline_depth 2: consecutive fill() calls may overlap on the GPU (the HBM-bound first stage of one batch
+        with the ALU-bound scan of the previous one); their outputs are final after flush() / status(), and a
+        call's output tensors must not be handed to the next call."""
         import torch
         self.torch = torch
         self.device = _lib.default_device() if device is None else int(device)
         self.handle = _lib.Handle(self.device)
+        if pipeline_depth != 1:
+            self.handle.set_pipeline_depth(pipeline_depth)
 
     def _bind_stream(self):
         # torch reports the legacy default stream as handle 0; CUDA's explicit handle for it is cudaStreamLegacy (0x1)
@@ -38,6 +43,11 @@ class DTFillEngine:
         self.handle.run_device_async(frames.data_ptr(), B, H, W, src_thr, val_thr, depth.data_ptr(), dt.data_ptr(),
                                      lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
         return dict(depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
+
+    def flush(self):
+        """Pipelined mode: torch's current stream waits for every fill still in flight."""
+        self._bind_stream()
+        self.handle.flush()
 
     def status(self):
         """Synchronise; (first_bad_frame or -1, kernel launches of the last fill)."""

@@ -109,6 +109,15 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
 
+/* Pipelined mode.  depth 1 (default): strict stream order -- when a call's work completes, in stream order, its
+ * outputs are final.  depth 2: consecutive dtfill_run_async calls may overlap: a call runs on one of two internal
+ * streams, behind whatever was queued on the handle's stream before it and behind the call two back (which used the
+ * same workspace), so the HBM-bound first stage of one batch overlaps the ALU-bound scan of the previous one.
+ * The handle's stream sees the outputs only after dtfill_flush (or dtfill_status / dtfill_synchronize, which
+ * flush).  Callers must not reuse a call's output buffers for the next call. */
+int dtfill_set_pipeline_depth(dtfill_t* h, int depth);
+int dtfill_flush(dtfill_t* h);
+
 /* Frames are split into bands of rows that one warp each processes independently (exact: every band is
  * extended by a halo derived from a guaranteed upper bound of the distances inside it).  cap > 0: target cost of
  * one band in row steps; 0: never split; -1 (default): chosen from the batch size and the SM count. */
@@ -124,6 +133,9 @@ int dtfill_set_subbatches(dtfill_t* h, int n);
  * dtfill_kernels.cuh struct Task; kind 3 = unused slot).  Returns the number of tasks written (<= max_tasks),
  * or a negative error code. */
 int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks);
+/* Raw status words of the last call (n <= 64): [0] first bad frame, [1] wide tasks, [4..] planner phase clocks when
+ * the library is built with -DDTFILL_PLANNER_CLOCKS. */
+int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n);
 
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the

@@ -304,6 +304,34 @@ def test_metrics_batch_sums(handle):
     assert sums[9] == B
 
 
+def test_pipelined_mode_matches_strict(handle):
+    """Pipeline depth 2: consecutive device-resident calls overlap on two internal streams / workspaces; every call's
+    outputs must equal the strict-mode outputs once flushed, and a bad frame in any in-flight call is reported."""
+    import torch
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    strict = DTFillEngine(0)
+    piped = DTFillEngine(0, pipeline_depth=2)
+    batches = [torch.from_numpy(np.stack([synth.kitti_frame(900 + 10 * k + i, beam_step=(1, 2, 8)[k % 3])
+                                          for i in range(3)])).cuda() for k in range(5)]
+    want = []
+    for xb in batches:
+        o = strict.fill(xb, want_lbl=True)
+        strict.status()
+        want.append({k: v.clone() for k, v in o.items() if v is not None})
+    got = [piped.fill(xb, want_lbl=True) for xb in batches]          # five calls in flight, two at a time
+    bad, _ = piped.status()
+    assert bad == -1
+    for w, g in zip(want, got):
+        for k in ("depth", "dt", "lbl", "mask", "counts"):
+            assert torch.equal(w[k], g[k]), k
+    xbad = batches[0].clone()
+    xbad[1] = 0
+    piped.fill(xbad)
+    piped.fill(batches[1])
+    bad, _ = piped.status()
+    assert bad == 1
+
+
 def test_device_resident_engine_matches_host_path(handle):
     import torch
     from distancetransform_depthcompletion_b200.engine import DTFillEngine
