@@ -234,13 +234,14 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # two output sets: with two batches in flight (pipeline depth 2) consecutive steps must not share outputs
-    outs = [out, {k: torch.empty_like(v) for k, v in out.items()}]
+    outs = [out] + [{k: torch.empty_like(v) for k, v in out.items()} for _ in range(max(1, args.pipeline - 1))]
+    no = len(outs)
 
     def timed_steps(depth):
         """Exactly K steps between two events on the launching stream; max over ranks."""
         eng.handle.set_pipeline_depth(depth)
         for i in range(args.warmup):
-            eng.fill(x, src_thr=src_thr, out=outs[i & 1])
+            eng.fill(x, src_thr=src_thr, out=outs[i % no])
         bad_, launches_ = eng.status()
         assert bad_ == -1, f"unexpected bad frame {bad_}"
         sampler_ = ClockSampler(local_rank)
@@ -249,7 +250,7 @@ def run_ours(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            eng.fill(x, src_thr=src_thr, out=outs[i & 1])
+            eng.fill(x, src_thr=src_thr, out=outs[i % no])
         eng.flush()                                   # every step's outputs are complete at e1
         e1.record()
         barrier()
@@ -379,7 +380,7 @@ def main():
     ap.add_argument("--workload", default="kitti64", choices=sorted(WORKLOADS),
                     help="kitti64 is the BASELINE.json metric; the others are the remaining configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--pipeline", type=int, default=3, choices=[1, 2, 3, 4],
                     help="batches in flight in the device-resident timing (1 = strict stream order)")
     ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
     ap.add_argument("--subbatches", type=int, default=None, help="override the number of sub-batch streams")

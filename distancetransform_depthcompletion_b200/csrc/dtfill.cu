@@ -58,7 +58,8 @@ struct dtfill_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    Lane lanes[2];
+    static const int MAX_LANES = 4;
+    Lane lanes[MAX_LANES];
     int ncalls = 0;                   // calls enqueued so far (pipelined mode alternates lanes)
     int last_lane = 0;
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
@@ -265,7 +266,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     CU(cudaSetDevice(h->device));
     // lane and stream of this call
     const bool pipelined = h->pipeline_depth > 1 && !h->profiling && !hio;
-    Lane* L = &h->lanes[pipelined ? (h->ncalls & 1) : 0];
+    Lane* L = &h->lanes[pipelined ? (h->ncalls % h->pipeline_depth) : 0];
     const Plan plan = make_plan(H, W);
     const int WW = (W + 31) / 32;
     const size_t rows = (size_t)B * H;
@@ -418,7 +419,10 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
-    if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) h->pipeline_depth = atoi(e) > 1 ? 2 : 1;
+    if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
+        const int d = atoi(e);
+        h->pipeline_depth = d < 1 ? 1 : (d > dtfill_ctx::MAX_LANES ? dtfill_ctx::MAX_LANES : d);
+    }
     *out_handle = h;
     return 0;
 }
@@ -469,7 +473,7 @@ int dtfill_set_pipeline_depth(dtfill_t* h, int depth) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_pipeline_depth: NULL handle");
     int rc = dtfill_flush(h);
     if (rc) return rc;
-    h->pipeline_depth = depth > 1 ? 2 : 1;
+    h->pipeline_depth = depth < 1 ? 1 : (depth > dtfill_ctx::MAX_LANES ? dtfill_ctx::MAX_LANES : depth);
     return 0;
 }
 

@@ -110,8 +110,8 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
 
 /* Pipelined mode.  depth 1 (default): strict stream order -- when a call's work completes, in stream order, its
- * outputs are final.  depth 2: consecutive dtfill_run_async calls may overlap: a call runs on one of two internal
- * streams, behind whatever was queued on the handle's stream before it and behind the call two back (which used the
+ * outputs are final.  depth 2..4: consecutive dtfill_run_async calls may overlap: a call runs on one of `depth` internal
+ * streams, behind whatever was queued on the handle's stream before it and behind the call `depth` back (which used the
  * same workspace), so the HBM-bound first stage of one batch overlaps the ALU-bound scan of the previous one.
  * The handle's stream sees the outputs only after dtfill_flush (or dtfill_status / dtfill_synchronize, which
  * flush).  Callers must not reuse a call's output buffers for the next call. */

@@ -310,7 +310,7 @@ def test_pipelined_mode_matches_strict(handle):
     import torch
     from distancetransform_depthcompletion_b200.engine import DTFillEngine
     strict = DTFillEngine(0)
-    piped = DTFillEngine(0, pipeline_depth=2)
+    piped = DTFillEngine(0, pipeline_depth=3)
     batches = [torch.from_numpy(np.stack([synth.kitti_frame(900 + 10 * k + i, beam_step=(1, 2, 8)[k % 3])
                                           for i in range(3)])).cuda() for k in range(5)]
     want = []
