@@ -178,7 +178,10 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {
-            const long per_frame = ((long)h->sm_count * 28 + Btot - 1) / Btot;      // tiles wanted per frame
+            // tiles wanted per frame; with batches overlapping (pipelined mode) fewer, taller tiles do: they carry
+            // less halo redundancy and the other batches in flight fill the SMs
+            const long beff = h->pipeline_depth > 1 ? (3L * Btot + 1) / 2 : Btot;
+            const long per_frame = ((long)h->sm_count * 28 + beff - 1) / beff;
             if (per_frame <= 1) cap = 0;                                              // batch alone fills the GPU
             else {
                 const long band_rows = (5L * H / 2) / per_frame;                       // ~2.5 tiles per band of rows
