@@ -312,21 +312,24 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     px_step = B * H * W
     achieved = ALG_BYTES_PER_PX * px_step / (ms_per_step * 1e-3) / 1e9 * 1.0      # per GPU (rank-0 clock = max)
-    traffic = None
+    traffic = traffic_k2 = None          # DRAM bytes from the committed ncu --set full capture (batch 256 only)
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and B == 256 and args.workload == "kitti64":
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic_k2 = tj.get("dram_bytes_per_step"), tj.get("dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            traffic = traffic_k2 = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
+        "traffic": traffic, "traffic_what": "dram__bytes_read+write of all kernels of one step (profiles/traffic.json); "
+                                              "algorithmic bytes per step = 13 B/px x px",
+        "algorithmic_bytes": ALG_BYTES_PER_PX * px_step, "peak_source": peak_src,
         "what": "whole fused path of one step (k1_mask_rows + k1b_scan_compact + k2_chamfer [+ k2_chamfer_wide no-op]): "
                 f"{ALG_BYTES_PER_PX} B/px x {px_step} px per step / step time; dominant kernel k2_chamfer",
         "kernel_ms": kt, "kernel_share": {k: (v / ktot if ktot else None) for k, v in kt.items()},
         "dominant_kernel": {"name": "k2_chamfer", "ms": kt.get("k2_chamfer"),
-                            "alg_bytes": 8 * px_step,
+                            "alg_bytes": 8 * px_step, "traffic": traffic_k2,
                             "achieved_gbs": (8 * px_step / (kt["k2_chamfer"] * 1e-3) / 1e9) if kt.get("k2_chamfer") else None},
     }
 
