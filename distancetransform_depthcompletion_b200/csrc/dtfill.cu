@@ -175,7 +175,6 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     fp.neg_ord = 0u - (1u << OSH);
     fp.four = 4u;
     fp.one = 1u;
-    fp.two = 2u;
     {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {

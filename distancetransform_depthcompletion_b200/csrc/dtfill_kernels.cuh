@@ -77,7 +77,6 @@ struct FrameParams {
     uint32_t neg_ord;          // -(1 << OSH):      key + (key >> OSH) * neg_ord == key & LMASK
     uint32_t four;             // sizeof(float)
     uint32_t one;              // 1: x * one + c keeps a plain add on the FMA pipe
-    uint32_t two;              // 2: umulhi(bits, two) == sign bit;  acc * two + bit == shift-in (Horner)
 };
 
 struct Workspace {
@@ -135,16 +134,6 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // the canonical positive NaN, i.e. "false", like the comparison), and the sign bits of four differences are
 // gathered into a nibble with byte permutes and one multiply.
 // ------------------------------------------------------------------------------------------------------
-// acc = 2 * acc + sign(t): the sign bit of t shifted into acc, two multiply-adds on the FMA pipe (K1's ALU pipe is
-// the busy one; `two` comes from the kernel arguments so that ptxas keeps them as IMADs)
-__device__ __forceinline__ uint32_t shift_in_sign(uint32_t acc, float t, uint32_t two)
-{
-    uint32_t sgn, r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(sgn) : "r"(__float_as_uint(t)), "r"(two));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(acc), "r"(two), "r"(sgn));
-    return r;
-}
-
 __device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, float t3)
 {
     // top bytes of the four floats -> one word -> bits 7,15,23,31 -> nibble (multiply gathers them into 28..31)
@@ -185,22 +174,20 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
                 for (int g = 0; g < 4; ++g)
                     nq[g] = col + 512 + 4 * g < W ? ld_stream_v4(rp + col + 512 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr.
-            // a > b <=> sign(b - a); the 16 sign bits are shifted in from pixel 15 down to pixel 0
-            const float x[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
-                                 q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-            uint32_t nsb = 0, vb = 0;                   // nsb: bit = (1 - x > src_thr), i.e. NOT a source
+            uint32_t sb = 0, vb = 0;
 #pragma unroll
-            for (int j = 15; j >= 0; --j) {
-                const float d = __fsub_rn(1.0f, x[j]);
-                nsb = shift_in_sign(nsb, __fsub_rn(sthr, d), fp.two);
-                vb = shift_in_sign(vb, __fsub_rn(vthr, x[j]), fp.two);
+            for (int g = 0; g < 4; ++g) {
+                // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr
+                const float d0 = __fsub_rn(1.0f, q[g].x), d1 = __fsub_rn(1.0f, q[g].y);
+                const float d2 = __fsub_rn(1.0f, q[g].z), d3 = __fsub_rn(1.0f, q[g].w);
+                const uint32_t ns = sign_nibble(__fsub_rn(sthr, d0), __fsub_rn(sthr, d1), __fsub_rn(sthr, d2),
+                                                __fsub_rn(sthr, d3));                       // bit = d > src_thr
+                const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
+                                                __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
+                const uint32_t inb = col + 4 * g < W ? 0xFu : 0u;
+                sb |= ((ns ^ 0xFu) & inb) << (4 * g);
+                vb |= (nv & inb) << (4 * g);
             }
-            uint32_t inb16 = 0;                         // whole float4 groups are inside or outside the row
-#pragma unroll
-            for (int g = 0; g < 4; ++g) inb16 |= col + 4 * g < W ? 0xFu << (4 * g) : 0u;
-            const uint32_t sb = ~nsb & inb16;
-            vb &= inb16;
             if (out_mask && col < W) {
                 uint32_t m[4];
 #pragma unroll
