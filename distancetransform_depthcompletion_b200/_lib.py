@@ -60,12 +60,13 @@ def load() -> ctypes.CDLL:
         L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
         L.dtfill_debug_get_tasks.restype = ci
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
+        L.dtfill_dt_pool.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
                      "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
-                     "dtfill_flush",
+                     "dtfill_flush", "dtfill_dt_pool",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
@@ -200,6 +201,20 @@ class Handle:
         ms = (ctypes.c_float * 4)()
         _check(self._L.dtfill_kernel_times(self._h, ms), "dtfill_kernel_times")
         return dict(zip(self.KERNEL_NAMES, (float(v) for v in ms)))
+
+    def dt_pool(self, data, mask, B: int, H: int, W: int, table_size: int, scale_num: int, on_device: bool = False,
+                out_ptr=None):
+        """DT pooling levels 2..scale_num (net.py:83-123).  Host arrays -> numpy [scale_num-1,B,H,W]."""
+        if scale_num <= 1:
+            return np.empty((0, B, H, W), np.float32)
+        if not on_device:
+            out = np.empty((scale_num - 1, B, H, W), np.float32)
+            _check(self._L.dtfill_dt_pool(self._h, _ptr(data), _ptr(mask), 0, B, H, W, table_size, scale_num,
+                                          _ptr(out), 0), "dtfill_dt_pool")
+            return out
+        _check(self._L.dtfill_dt_pool(self._h, _ptr(data), _ptr(mask), 1, B, H, W, table_size, scale_num,
+                                      _ptr(out_ptr), 1), "dtfill_dt_pool")
+        return None
 
     def metrics(self, pred, gt, B: int, H: int, W: int, mode: int, gt_is_f64: bool, on_device: bool = False,
                 per_frame_ptr=None, sums_ptr=None):

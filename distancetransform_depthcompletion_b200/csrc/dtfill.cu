@@ -673,6 +673,46 @@ int dtfill_kernel_times(dtfill_t* h, float* ms) {
     return 0;
 }
 
+int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
+                   int table_size, int scale_num, float* out, int out_is_device) {
+    if (!h || !data || !mask) return fail(DTFILL_E_ARG, "dtfill_dt_pool: NULL handle, data or mask");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_dt_pool: B, H, W must be positive");
+    if (table_size < 1 || (table_size & 1) == 0 || table_size > 2 * K5_MAXR + 1)
+        return fail(DTFILL_E_ARG, "dtfill_dt_pool: table_size must be odd and <= 15");       // net.py:72 assert
+    if (scale_num < 1 || scale_num > 4) return fail(DTFILL_E_ARG, "dtfill_dt_pool: scale_num must be 1..4");
+    if (scale_num == 1) return 0;
+    if (!out) return fail(DTFILL_E_ARG, "dtfill_dt_pool: NULL out");
+    CU(cudaSetDevice(h->device));
+    { int frc = dtfill_flush(h); if (frc) return frc; }
+    const size_t npx = (size_t)B * H * W;
+    const int nl = scale_num - 1;
+    cudaStream_t s = h->stream;
+    int rc;
+    const float* d_d = data; const float* m_d = mask; float* o_d = out;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
+        if ((rc = ensure(h, h->gt_dev, npx * 4))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, data, npx * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->gt_dev.p, mask, npx * 4, cudaMemcpyHostToDevice, s));
+        d_d = (const float*)h->in_dev.p; m_d = (const float*)h->gt_dev.p;
+    }
+    if (!out_is_device) {
+        if ((rc = ensure(h, h->depth_dev, npx * 4 * nl))) return rc;
+        o_d = (float*)h->depth_dev.p;
+    }
+    dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
+    for (int l = 0; l < nl; ++l) {
+        const float* src = l == 0 ? d_d : o_d + (size_t)(l - 1) * npx;
+        k5_dt_pool_level<<<grid, 256, 0, s>>>(src, l == 0 ? m_d : nullptr, H, W, table_size, o_d + (size_t)l * npx);
+    }
+    CU(cudaGetLastError());
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out, o_d, npx * 4 * nl, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
 int dtfill_host_alloc(void** out_ptr, size_t bytes) {
     if (!out_ptr) return fail(DTFILL_E_ARG, "dtfill_host_alloc: NULL out_ptr");
     *out_ptr = nullptr;

@@ -1349,4 +1349,61 @@ __global__ void __launch_bounds__(256) k4_metrics_final(const double* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K5: one level of the CNN input stage's "DT pooling" (net.py:83-123 generate_multi_channel).
+// For every pixel: among the pixels of its T x T window (zero padded) whose mask is set, those with the largest
+// weight T - |dy| - |dx| (net.py:71-81), i.e. the city-block-nearest ones, are averaged:
+// out = sum(data[sel]) / (1e-6 + |sel|)  (net.py:93).  With no masked pixel in the window all T*T positions tie at
+// weight 0 and the result is sum(window) / (1e-6 + T*T).  mask == nullptr means mask = data > 0.001 (net.py:95).
+// One thread per pixel, 32 x 8 tile + halo in shared memory, rings of growing city-block distance.
+// ------------------------------------------------------------------------------------------------------
+constexpr int K5_TW = 32, K5_TH = 8, K5_MAXR = 7;      // table_size <= 15
+
+__global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict__ data, const float* __restrict__ mask,
+                                                         int H, int W, int T, float* __restrict__ out)
+{
+    __shared__ float sd[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
+    __shared__ uint8_t smk[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
+    const int R = T / 2;
+    const long fpx = (long)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * K5_TW, y0 = blockIdx.y * K5_TH;
+    const int tw = K5_TW + 2 * R, th = K5_TH + 2 * R;
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int ly = i / tw, lx = i - ly * tw;
+        const int gy = y0 + ly - R, gx = x0 + lx - R;
+        float v = 0.f, m = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            v = data[fpx + (long)gy * W + gx];
+            m = mask ? mask[fpx + (long)gy * W + gx] : (v > 0.001f ? 1.f : 0.f);
+        }
+        sd[ly][lx] = v;
+        smk[ly][lx] = m != 0.f;          // mask * weight > 0  <=>  mask != 0 (weights are >= 1)
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+    const int cx = tx + R, cy = ty + R;
+    float sum = 0.f, cnt = 0.f;
+    if (smk[cy][cx]) {                   // the centre alone carries the largest weight T
+        sum = sd[cy][cx]; cnt = 1.f;
+    } else {
+        for (int d = 1; d <= 2 * R && cnt == 0.f; ++d) {          // ring of city-block distance d inside the window
+            const int dyl = min(d, R);
+            for (int dy = -dyl; dy <= dyl; ++dy) {
+                const int dx = d - abs(dy);
+                if (dx > R) continue;
+                if (smk[cy + dy][cx + dx]) { sum += sd[cy + dy][cx + dx]; cnt += 1.f; }
+                if (dx != 0 && smk[cy + dy][cx - dx]) { sum += sd[cy + dy][cx - dx]; cnt += 1.f; }
+            }
+        }
+        if (cnt == 0.f) {                // nothing masked: every window position ties at weight 0
+            for (int dy = -R; dy <= R; ++dy)
+                for (int dx = -R; dx <= R; ++dx) sum += sd[cy + dy][cx + dx];
+            cnt = (float)(T * T);
+        }
+    }
+    out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
+}
+
 }  // namespace dtfill

@@ -1,0 +1,46 @@
+"""Drop-in for the "DT pooling" helpers every model class of the reference's solution_DeepNet/net.py carries:
+
+    create_weight_matrix(table_size)                           net.py:71-81
+    generate_multi_channel(lidar_data, lidar_mask, ...)        net.py:83-123
+
+numpy in, numpy out (the reference runs these lines as TF ops inside the model).  The window
+search and averaging run on the GPU (kernel k5_dt_pool_level behind dtfill_dt_pool).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def create_weight_matrix(table_size: int = 7) -> np.ndarray:
+    """net.py:71-81: weight table_size - |i - mid| - |j - mid| per window position, flattened, float32."""
+    assert (table_size + 1) % 2 == 0                                         # net.py:72
+    mid = (table_size - 1) // 2
+    i = np.abs(np.arange(table_size) - mid)
+    return (table_size - i[:, None] - i[None, :]).reshape(-1).astype(np.float32)
+
+
+def generate_multi_channel(lidar_data, lidar_mask, table_size: int = 7, scale_num: int = 4, device: int | None = None):
+    """net.py:83-123.  lidar_data, lidar_mask: float32 [B,H,W,1] (or [B,H,W]); returns (lidar_1, lidar_2, lidar_3,
+    lidar_4) with None for the levels beyond scale_num, like the reference; lidar_k has shape [B,H,W] for k >= 2
+    (net.py:93 reduces the patch axis) and lidar_1 is the input itself."""
+    d = np.asarray(lidar_data)
+    m = np.asarray(lidar_mask)
+    if d.dtype != np.float32 or m.dtype != np.float32:
+        raise TypeError("generate_multi_channel: float32 arrays expected")
+    if d.shape != m.shape:
+        raise ValueError(f"generate_multi_channel: data {d.shape} and mask {m.shape} differ")
+    d3 = d[..., 0] if d.ndim == 4 else d
+    m3 = m[..., 0] if m.ndim == 4 else m
+    if d3.ndim != 3:
+        raise ValueError("generate_multi_channel: expected [B,H,W,1] or [B,H,W]")
+    assert (table_size + 1) % 2 == 0                                         # net.py:72
+    if not 1 <= scale_num <= 4:
+        raise ValueError("scale_num must be 1..4")
+    B, H, W = d3.shape
+    levels = _lib.get_handle(device).dt_pool(np.ascontiguousarray(d3), np.ascontiguousarray(m3), B, H, W, table_size,
+                                             scale_num)
+    outs = [d] + [levels[k] for k in range(scale_num - 1)]
+    outs += [None] * (4 - len(outs))
+    return tuple(outs)

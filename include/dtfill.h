@@ -109,6 +109,17 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
 
+/*
+ * DT pooling of the CNN input stage: generate_multi_channel (solution_DeepNet/net.py:83-123, identical in all
+ * model classes) with the weights of create_weight_matrix (net.py:71-81).  data, mask: float32 [B,H,W] (the
+ * reference's [B,H,W,1]); data is the sparse depth already divided by scale_range and multiplied by the mask
+ * (net.py:467-486), mask the validity mask (net.py:464-465).  Writes levels 2..scale_num (1 <= scale_num <= 4)
+ * into out [scale_num-1][B,H,W]: level k is pooled from level k-1 with mask = level k-1 > 0.001 (net.py:95-96).
+ * table_size odd, <= 15.  Waits for completion when out is a host pointer.
+ */
+int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
+                   int table_size, int scale_num, float* out, int out_is_device);
+
 /* Pipelined mode.  depth 1 (default): strict stream order -- when a call's work completes, in stream order, its
  * outputs are final.  depth 2..4: consecutive dtfill_run_async calls may overlap: a call runs on one of `depth` internal
  * streams, behind whatever was queued on the handle's stream before it and behind the call `depth` back (which used the

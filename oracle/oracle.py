@@ -202,3 +202,58 @@ def result_nyu(output: np.ndarray, target: np.ndarray) -> dict:
         imae = np.mean(abs_inv_diff)                                   # :236
     return dict(mse=float(mse), rmse=float(rmse), mae=float(mae), irmse=float(irmse), imae=float(imae),
                 delta1=float(d1), delta2=float(d2), delta3=float(d3), count=int(valid_mask.sum()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DT pooling of the CNN input stage: numpy RESTATEMENT of net.py:71-123.
+# TensorFlow is not installed in the build container, so this cannot be pinned against the reference run
+# live ("parity unpinned" for this row); it follows the reference lines one by one.
+# ---------------------------------------------------------------------------------------------------------
+def create_weight_matrix(table_size: int = 7) -> np.ndarray:
+    """net.py:71-81: weight T - |i-mid| - |j-mid| of every window position, flattened, float32."""
+    assert (table_size + 1) % 2 == 0
+    middle = (table_size - 1) / 2
+    w = np.zeros((table_size, table_size))
+    for i in range(table_size):
+        for j in range(table_size):
+            w[i, j] = table_size - abs(i - middle) - abs(j - middle)
+    return np.reshape(w, (table_size * table_size,)).astype(np.float32)
+
+
+def _extract_patches_same(x: np.ndarray, t: int) -> np.ndarray:
+    """tf.image.extract_patches(sizes=(1,t,t,1), strides 1, rates 1, padding='SAME') for x [B,H,W]:
+    -> [B,H,W,t*t], window rows first, zero padded."""
+    B, H, W = x.shape
+    r = t // 2
+    p = np.zeros((B, H + 2 * r, W + 2 * r), x.dtype)
+    p[:, r:r + H, r:r + W] = x
+    out = np.empty((B, H, W, t * t), x.dtype)
+    k = 0
+    for i in range(t):
+        for j in range(t):
+            out[..., k] = p[:, i:i + H, j:j + W]
+            k += 1
+    return out
+
+
+def pool_level(lidar_data: np.ndarray, lidar_mask: np.ndarray, table_size: int = 7):
+    """One level of generate_multi_channel (net.py:89-96): data, mask float32 [B,H,W] -> (pooled, new mask)."""
+    w = create_weight_matrix(table_size)
+    ein = _extract_patches_same(lidar_data.astype(np.float32), table_size)                       # :89
+    emask = _extract_patches_same(lidar_mask.astype(np.float32), table_size)                     # :90
+    mw = emask * w
+    max_index = (mw == mw.max(axis=-1, keepdims=True)).astype(np.float32)                        # :91-92
+    pooled = (ein * max_index).sum(axis=-1, dtype=np.float32) / (np.float32(0.000001) + max_index.sum(axis=-1, dtype=np.float32))   # :93
+    return pooled.astype(np.float32), (pooled > 0.001).astype(np.float32)                        # :95-96
+
+
+def generate_multi_channel(lidar_data: np.ndarray, lidar_mask: np.ndarray, table_size: int = 7, scale_num: int = 4):
+    """net.py:83-123 for arrays [B,H,W] (the reference carries a trailing channel axis of 1)."""
+    outs = [lidar_data.astype(np.float32)]
+    d, m = lidar_data, lidar_mask
+    for _ in range(scale_num - 1):
+        d, m = pool_level(d, m, table_size)
+        outs.append(d)
+    while len(outs) < 4:
+        outs.append(None)
+    return tuple(outs[:4])

@@ -1,0 +1,68 @@
+"""DT pooling of the CNN input stage (net.py:71-123).  TensorFlow is absent, so the oracle is
+a numpy RESTATEMENT of the reference lines (oracle.generate_multi_channel) -- parity unpinned for this row."""
+import numpy as np
+import pytest
+
+from distancetransform_depthcompletion_b200 import net_pool, synth
+from oracle import oracle as O
+
+
+def test_weight_matrix_matches_restatement():
+    for t in (1, 3, 5, 7, 9):
+        assert np.array_equal(net_pool.create_weight_matrix(t), O.create_weight_matrix(t))
+    w = net_pool.create_weight_matrix(7).reshape(7, 7)
+    assert w[3, 3] == 7 and w[0, 0] == 1 and w[3, 0] == 4 and w.dtype == np.float32
+    with pytest.raises(AssertionError):
+        net_pool.create_weight_matrix(4)
+
+
+def test_restatement_properties():
+    """Level masks are Chebyshev dilations of the validity mask by 3 px per level."""
+    from scipy.ndimage import binary_dilation
+    x = synth.kitti_frame(1)[None, 100:200, :300]
+    mask = (x > 0.1).astype(np.float32)
+    l1, l2, l3, l4 = O.generate_multi_channel(x / 90.0 * mask, mask)
+    sq = np.ones((1, 7, 7), bool)
+    m = mask > 0
+    for lv in (l2, l3, l4):
+        m = binary_dilation(m, sq)
+        assert np.array_equal(lv > 0.001, m)
+    assert np.array_equal(l1, (x / 90.0 * mask).astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale_num,table_size", [(4, 7), (2, 7), (3, 5), (4, 3), (1, 7), (3, 9)])
+def test_gpu_matches_restatement(scale_num, table_size):
+    rng = np.random.default_rng(scale_num * 10 + table_size)
+    frames = [synth.kitti_frame(5)[90:190, 200:520], synth.kitti_frame(6, beam_step=4)[90:190, 200:520],
+              ((rng.random((100, 320)) < 0.02) * rng.uniform(1, 80, (100, 320))).astype(np.float32),
+              np.zeros((100, 320), np.float32)]
+    x = np.stack(frames)[..., None]
+    mask = (x > 0.1).astype(np.float32)                           # net.py:464-465
+    data = (x / np.float32(90.0) * mask).astype(np.float32)       # net.py:467, :486
+    got = net_pool.generate_multi_channel(data, mask, table_size=table_size, scale_num=scale_num)
+    want = O.generate_multi_channel(data[..., 0], mask[..., 0], table_size, scale_num)
+    assert got[0] is data or np.array_equal(got[0], data)
+    for k in range(1, 4):
+        if k >= scale_num:
+            assert got[k] is None and want[k] is None
+            continue
+        assert got[k].shape == (4, 100, 320) and got[k].dtype == np.float32
+        # only the order of the (<= T*T term) float32 sums may differ
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=1e-9)
+        assert np.array_equal(got[k] > 0.001, want[k] > 0.001)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_and_errors():
+    x = synth.kitti_batch([11, 12])
+    mask = (x > 0.1).astype(np.float32)
+    data = (x / np.float32(90.0) * mask).astype(np.float32)
+    got = net_pool.generate_multi_channel(data, mask)
+    want = O.generate_multi_channel(data[..., 0], mask[..., 0])
+    for k in (1, 2, 3):
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=1e-9)
+    with pytest.raises(TypeError):
+        net_pool.generate_multi_channel(data.astype(np.float64), mask)
+    with pytest.raises(ValueError):
+        net_pool.generate_multi_channel(data, mask[:, :10])
