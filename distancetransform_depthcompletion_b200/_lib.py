@@ -61,12 +61,13 @@ def load() -> ctypes.CDLL:
         L.dtfill_debug_get_tasks.restype = ci
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
         L.dtfill_dt_pool.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
+        L.dtfill_outlier_removal.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
                      "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
-                     "dtfill_flush", "dtfill_dt_pool",
+                     "dtfill_flush", "dtfill_dt_pool", "dtfill_outlier_removal",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
@@ -215,6 +216,13 @@ class Handle:
         _check(self._L.dtfill_dt_pool(self._h, _ptr(data), _ptr(mask), 1, B, H, W, table_size, scale_num,
                                       _ptr(out_ptr), 1), "dtfill_dt_pool")
         return None
+
+    def outlier_removal(self, frames: np.ndarray) -> np.ndarray:
+        """frames float32 [B,H,W] -> filtered float32 [B,H,W] (data_read.py:103-128)."""
+        B, H, W = frames.shape
+        out = np.empty((B, H, W), np.float32)
+        _check(self._L.dtfill_outlier_removal(self._h, _ptr(frames), 0, B, H, W, _ptr(out), 0), "dtfill_outlier_removal")
+        return out
 
     def metrics(self, pred, gt, B: int, H: int, W: int, mode: int, gt_is_f64: bool, on_device: bool = False,
                 per_frame_ptr=None, sums_ptr=None):

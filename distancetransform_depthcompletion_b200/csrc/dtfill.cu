@@ -713,6 +713,35 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
     return 0;
 }
 
+int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float* out,
+                           int out_is_device) {
+    if (!h || !in || !out) return fail(DTFILL_E_ARG, "dtfill_outlier_removal: NULL argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_outlier_removal: B, H, W must be positive");
+    CU(cudaSetDevice(h->device));
+    { int frc = dtfill_flush(h); if (frc) return frc; }
+    const size_t npx = (size_t)B * H * W;
+    cudaStream_t s = h->stream;
+    int rc;
+    const float* i_d = in; float* o_d = out;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, s));
+        i_d = (const float*)h->in_dev.p;
+    }
+    if (!out_is_device) {
+        if ((rc = ensure(h, h->depth_dev, npx * 4))) return rc;
+        o_d = (float*)h->depth_dev.p;
+    }
+    dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
+    k6_outlier_removal<<<grid, 256, 0, s>>>(i_d, H, W, o_d);
+    CU(cudaGetLastError());
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out, o_d, npx * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
 int dtfill_host_alloc(void** out_ptr, size_t bytes) {
     if (!out_ptr) return fail(DTFILL_E_ARG, "dtfill_host_alloc: NULL out_ptr");
     *out_ptr = nullptr;

@@ -120,6 +120,11 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
 int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
                    int table_size, int scale_num, float* out, int out_is_device);
 
+/* KITTI outlier filter outlier_removal (data_read.py:103-128), the step just before the path: in, out float32
+ * [B,H,W]; a depth more than 1.0 m farther than the average of the valid depths in its 7 x 7 diamond is zeroed. */
+int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float* out,
+                           int out_is_device);
+
 /* Pipelined mode.  depth 1 (default): strict stream order -- when a call's work completes, in stream order, its
  * outputs are final.  depth 2..4: consecutive dtfill_run_async calls may overlap: a call runs on one of `depth` internal
  * streams, behind whatever was queued on the handle's stream before it and behind the call `depth` back (which used the

@@ -257,3 +257,21 @@ def generate_multi_channel(lidar_data: np.ndarray, lidar_mask: np.ndarray, table
     while len(outs) < 4:
         outs.append(None)
     return tuple(outs[:4])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# KITTI outlier filter: data_read.py:103-128 with the real cv2.filter2D.
+# ---------------------------------------------------------------------------------------------------------
+def cv2_port_outlier_removal(lidar):
+    """data_read.py:103-128 line by line (np.float, removed from numpy, is spelled float64 = what it aliased)."""
+    import cv2
+    DIAMOND_KERNEL_7 = np.asarray([[0, 0, 0, 1, 0, 0, 0], [0, 0, 1, 1, 1, 0, 0], [0, 1, 1, 1, 1, 1, 0],
+                                   [1, 1, 1, 1, 1, 1, 1], [0, 1, 1, 1, 1, 1, 0], [0, 0, 1, 1, 1, 0, 0],
+                                   [0, 0, 0, 1, 0, 0, 0]], dtype=np.uint8)                      # :104-113
+    sparse_lidar = np.squeeze(lidar)                                                            # :115
+    valid_pixels = (sparse_lidar > 0.1).astype(np.float64)                                      # :116
+    lidar_sum = cv2.filter2D(sparse_lidar, -1, DIAMOND_KERNEL_7)                                # :119
+    lidar_count = cv2.filter2D(valid_pixels, -1, DIAMOND_KERNEL_7)                              # :121
+    lidar_aveg = lidar_sum / (lidar_count + 0.00001)                                            # :123
+    potential_outliers = ((sparse_lidar - lidar_aveg) > 1.0).astype(np.float64)                 # :125
+    return (sparse_lidar * (1 - potential_outliers)).astype(np.float32)                         # :128
