@@ -18,7 +18,7 @@ def _frames():
     ys, xs = np.nonzero(x > 0)
     pick = rng.choice(len(ys), 200, replace=False)
     x[ys[pick], xs[pick]] += np.float32(30.0)
-    return [x, synth.kitti_frame(3, beam_step=4), x[:9, :13].copy(), x[200:201, :].copy(), x[:, 600:601].copy()]
+    return [x, synth.kitti_frame(3, beam_step=4), x[:9, :13].copy(), x[200:203, :].copy(), x[:, 600:602].copy()]
 
 
 @pytest.mark.skipif(not (os.path.isdir(REF) and O.have_cv2()), reason="reference checkout or cv2 absent")
@@ -50,11 +50,10 @@ def test_port_matches_the_reference_function():
 @pytest.mark.skipif(not O.have_cv2(), reason="cv2 absent")
 def test_gpu_matches_cv2_port():
     for f in _frames():
-        want = O.cv2_port_outlier_removal(f) if min(f.shape) > 1 else None
-        got = data_read.outlier_removal(f[None, :, :, None] if min(f.shape) > 1 else f)
+        want = O.cv2_port_outlier_removal(f)
+        got = data_read.outlier_removal(f[None, :, :, None])
         assert got.dtype == np.float32 and got.shape == f.shape
-        if want is not None:
-            assert np.array_equal(got, want)          # KITTI-grid depths: sums are exact in float32
+        assert np.array_equal(got, want)              # KITTI-grid depths: sums are exact in float32
     x = _frames()[0]
     assert (data_read.outlier_removal(x) != x).sum() > 100          # the planted outliers are removed
     with pytest.raises(TypeError):
