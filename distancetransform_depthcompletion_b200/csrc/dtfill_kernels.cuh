@@ -1363,45 +1363,63 @@ __global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict_
                                                          int H, int W, int T, float* __restrict__ out)
 {
     __shared__ float sd[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
-    __shared__ uint8_t smk[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
+    __shared__ unsigned long long smk[K5_TH + 2 * K5_MAXR];      // one mask bit per tile column (<= 46 columns)
     const int R = T / 2;
     const long fpx = (long)blockIdx.z * H * W;
     const int x0 = blockIdx.x * K5_TW, y0 = blockIdx.y * K5_TH;
     const int tw = K5_TW + 2 * R, th = K5_TH + 2 * R;
-    for (int i = threadIdx.x; i < tw * th; i += 256) {
-        const int ly = i / tw, lx = i - ly * tw;
-        const int gy = y0 + ly - R, gx = x0 + lx - R;
-        float v = 0.f, m = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            v = data[fpx + (long)gy * W + gx];
-            m = mask ? mask[fpx + (long)gy * W + gx] : (v > 0.001f ? 1.f : 0.f);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // tile + halo: one warp per tile row, two ballots build the row's mask word
+    for (int ly = wid; ly < th; ly += 8) {
+        const int gy = y0 + ly - R;
+        unsigned long long word = 0;
+        for (int l0 = 0; l0 < tw; l0 += 32) {
+            const int lx = l0 + lane;
+            const int gx = x0 + lx - R;
+            float v = 0.f;
+            bool m = false;
+            if (lx < tw && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = data[fpx + (long)gy * W + gx];
+                m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);   // mask * weight > 0 <=> mask != 0
+            }
+            if (lx < tw) sd[ly][lx] = v;
+            word |= (unsigned long long)__ballot_sync(0xffffffffu, m) << l0;
         }
-        sd[ly][lx] = v;
-        smk[ly][lx] = m != 0.f;          // mask * weight > 0  <=>  mask != 0 (weights are >= 1)
+        if (lane == 0) smk[ly] = word;
     }
     __syncthreads();
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = lane, ty = wid;
     const int gx = x0 + tx, gy = y0 + ty;
     if (gx >= W || gy >= H) return;
     const int cx = tx + R, cy = ty + R;
+    const uint32_t fieldmask = (1u << T) - 1u, lowmask = (1u << R) - 1u;
+    int best = 1 << 20;                  // smallest city-block distance to a masked pixel of the window
     float sum = 0.f, cnt = 0.f;
-    if (smk[cy][cx]) {                   // the centre alone carries the largest weight T
-        sum = sd[cy][cx]; cnt = 1.f;
-    } else {
-        for (int d = 1; d <= 2 * R && cnt == 0.f; ++d) {          // ring of city-block distance d inside the window
-            const int dyl = min(d, R);
-            for (int dy = -dyl; dy <= dyl; ++dy) {
-                const int dx = d - abs(dy);
-                if (dx > R) continue;
-                if (smk[cy + dy][cx + dx]) { sum += sd[cy + dy][cx + dx]; cnt += 1.f; }
-                if (dx != 0 && smk[cy + dy][cx - dx]) { sum += sd[cy + dy][cx - dx]; cnt += 1.f; }
-            }
+    for (int dy = -R; dy <= R; ++dy) {
+        // the T mask bits of this window row, centre at bit R
+        const uint32_t f = (uint32_t)(smk[cy + dy] >> tx) & fieldmask;
+        if (!f) continue;
+        const int ady = dy < 0 ? -dy : dy;
+        int dxr = 1 << 20, dxl = 1 << 20;
+        if ((f >> R) & 1u) dxr = dxl = 0;
+        else {
+            const uint32_t right = f >> (R + 1), left = f & lowmask;
+            if (right) dxr = __ffs(right);
+            if (left) dxl = R - (31 - __clz(left));
         }
-        if (cnt == 0.f) {                // nothing masked: every window position ties at weight 0
-            for (int dy = -R; dy <= R; ++dy)
-                for (int dx = -R; dx <= R; ++dx) sum += sd[cy + dy][cx + dx];
-            cnt = (float)(T * T);
+        const int dx = min(dxr, dxl), d = ady + dx;
+        if (d > best) continue;
+        if (d < best) { best = d; sum = 0.f; cnt = 0.f; }
+        if (dx == 0) { sum += sd[cy + dy][cx]; cnt += 1.f; }
+        else {
+            if (dxl == dx) { sum += sd[cy + dy][cx - dx]; cnt += 1.f; }
+            if (dxr == dx) { sum += sd[cy + dy][cx + dx]; cnt += 1.f; }
         }
+    }
+    if (cnt == 0.f) {                    // nothing masked: every window position ties at weight 0
+        for (int dy = -R; dy <= R; ++dy)
+            for (int dx = -R; dx <= R; ++dx) sum += sd[cy + dy][cx + dx];
+        cnt = (float)(T * T);
     }
     out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
 }
@@ -1435,7 +1453,7 @@ __global__ void __launch_bounds__(256) k6_outlier_removal(const float* __restric
     const int gx = x0 + tx, gy = y0 + ty;
     if (gx >= W || gy >= H) return;
     float sum = 0.f;                       // float32 like cv2.filter2D(sparse_lidar, -1, ...)
-    double cnt = 0.0;                      // float64 like the filter of valid_pixels (np.float)
+    int cnt = 0;                           // the float64 filter of valid_pixels (np.float) counts exactly
 #pragma unroll
     for (int dy = -R; dy <= R; ++dy) {
         const int w = R - (dy < 0 ? -dy : dy);
@@ -1444,11 +1462,11 @@ __global__ void __launch_bounds__(256) k6_outlier_removal(const float* __restric
             if (dx < -w || dx > w) continue;
             const float v = sd[ty + R + dy][tx + R + dx];
             sum += v;
-            cnt += v > 0.1f ? 1.0 : 0.0;   // data_read.py:116
+            cnt += v > 0.1f ? 1 : 0;       // data_read.py:116
         }
     }
     const float x = sd[ty + R][tx + R];
-    const double aveg = (double)sum / (cnt + 0.00001);                 // data_read.py:123
+    const double aveg = (double)sum / ((double)cnt + 0.00001);         // data_read.py:123
     const bool outlier = ((double)x - aveg) > 1.0;                     // :125
     out[fpx + (long)gy * W + gx] = outlier ? 0.0f : x;                 // :128  x * (1 - outlier)
 }

@@ -1,0 +1,39 @@
+"""Device-resident timings of the widened rows and of the metrics kernel, batch of 256 KITTI
+frames, CUDA events, 10 repetitions after 3 warm-ups."""
+import os, sys, ctypes
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from distancetransform_depthcompletion_b200 import _lib, synth
+from distancetransform_depthcompletion_b200.engine import DTFillEngine
+
+B, H, W = 256, 352, 1216
+x = torch.from_numpy(bench.make_frames(B, 0)).cuda()
+eng = DTFillEngine(0)
+h = eng.handle
+L = _lib.load()
+
+def timed(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+npx = B * H * W
+mask = (x > 0.1).float()
+data = (x / 90.0 * mask).contiguous()
+pool_out = torch.empty((3, B, H, W), dtype=torch.float32, device="cuda")
+eng._bind_stream()
+t = timed(lambda: h.dt_pool(data.data_ptr(), mask.data_ptr(), B, H, W, 7, 4, on_device=True, out_ptr=pool_out.data_ptr()))
+print("dt_pool 3 levels: %.3f ms / 256 frames  (%.0f frames/s, %.0f GB/s of 8 B/px/level)" % (t, B / t * 1e3, 3 * 8 * npx / t / 1e6))
+out = torch.empty_like(x)
+t = timed(lambda: _lib._check(L.dtfill_outlier_removal(h._h, ctypes.c_void_p(x.data_ptr()), 1, B, H, W, ctypes.c_void_p(out.data_ptr()), 1), "outlier"))
+print("outlier_removal: %.3f ms / 256 frames  (%.0f frames/s, %.0f GB/s of 8 B/px)" % (t, B / t * 1e3, 8 * npx / t / 1e6))
+fill = eng.fill(x)
+gt = torch.from_numpy(np.stack([synth.kitti_gt(i % 16) for i in range(B)])).cuda()
+t = timed(lambda: eng.metrics(fill["depth"], gt))
+print("metrics (Result.evaluate, f64 gt): %.3f ms / 256 frames (%.0f GB/s of 12 B/px)" % (t, 12 * npx / t / 1e6))
