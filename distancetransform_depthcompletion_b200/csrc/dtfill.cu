@@ -70,6 +70,7 @@ struct dtfill_ctx {
     size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
     bool profiling = false;
     bool tiles2d = true;
+    int max_col_tiles = 4;
     int nsub = -1;                // -1: automatic
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
@@ -170,6 +171,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     fp.wide_ppl = plan.ppl ? plan.ppl : 1;
     fp.narrow_ppl = (h->tiles2d && plan.ppl) ? plan.narrow : 0;
     fp.frame0 = b0;
+    fp.max_col_tiles = h->max_col_tiles;
     fp.mul_dist = 1u << (32 - DSH);
     fp.mul_ord = 1u << (32 - OSH);
     fp.neg_ord = 0u - (1u << OSH);
@@ -421,6 +423,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     }
     if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
+    if (const char* e = getenv("DTFILL_MAX_COL_TILES")) h->max_col_tiles = atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
         const int d = atoi(e);

@@ -69,6 +69,7 @@ struct FrameParams {
     int scratch_units_per_frame; // capacity of the forward-state scratch per frame, in units of 32 keys
     int wide_ppl;              // pixels per lane of the full-width kernel instance (scratch units per row)
     int narrow_ppl;            // pixels per lane of the half-width instance, 0 if frames are never split in columns
+    int max_col_tiles;         // planner: at most this many narrow tiles side by side (2..4)
     int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
     // Multipliers handed over at run time so that ptxas keeps the multiply-adds below on the FMA pipe instead of
     // strength-reducing them to shifts/LEAs on the ALU pipe, which is the pipe the scan kernel saturates.
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 // extra columns stay below ~60 % (n * nwid <= 1.6 W)
                 int ntile = 0;
                 if (nwid > 0 && W > nwid && (W & 3) == 0) {
-                    for (int n = 2; n <= 4 && !ntile; ++n) {
+                    for (int n = 2; n <= fp.max_col_tiles && !ntile; ++n) {
                         if (5 * n * nwid > 8 * W || nt + n > MAXT) break;
                         bool fits = true;                      // every interior tile edge at least best_u away
                         int prev_split = 0;
