@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
                         const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint32_t l = key_label(kk[e], fp.mul_ord, fp.neg_ord);     // >= 1 inside [c0,c1)
+                            const uint32_t l = kk[e] & LMASK;                                // >= 1 inside [c0,c1)
                             g[4 * j + e] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
                         }
                     }
