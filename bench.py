@@ -42,7 +42,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms
+    (the timed region lasts ~10 ms), nvidia-smi -lms as fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -50,8 +51,50 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.p = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+
+    def _nvml_loop(self, pynvml, handle):
+        bits = {}
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            v = getattr(pynvml, attr, None) or getattr(pynvml, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if v is not None:
+                bits[name] = v
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(handle))
+                    for n, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -60,6 +103,11 @@ class ClockSampler:
             self.p = None
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "NVML polled every ~2 ms"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -83,7 +131,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------------------
