@@ -334,8 +334,7 @@ def run_ours(args, rank, world, local_rank):
     ktot = sum(kt.values())
 
     # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
-    h = eng.handle
-    h.set_stream(None)
+    h = _lib.Handle(local_rank)           # the numpy-facing API on its own handle and stream, like a user's call
     pin_out = dict(depth=_lib.pinned_empty((B, H, W), np.float32), dt=_lib.pinned_empty((B, H, W), np.float32),
                    mask=_lib.pinned_empty((B, H, W), np.uint8))
     e2e_steps = max(2, min(args.steps, 5))
