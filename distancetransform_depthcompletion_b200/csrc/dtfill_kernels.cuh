@@ -734,11 +734,20 @@ template <int PPL, int DIR>
 __device__ __forceinline__ uint32_t lane_carry(uint32_t e, int lane, uint32_t clamp_dist)
 {
     uint32_t E = ((e >> DSH) << OSH) | (e & LMASK);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, d) : __shfl_down_sync(0xffffffffu, E, d);
-        const uint32_t t = o + (uint32_t(d * PPL) << OSH);
+    {   // distance 1: the neighbouring lane
+        const uint32_t o = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, 1) : __shfl_down_sync(0xffffffffu, E, 1);
+        const uint32_t t = o + (uint32_t(PPL) << OSH);
         E = ((t | LMASK) < E) ? t : E;
+    }
+    // a value carried over d >= 2 lanes is at least 2*PPL; it can only win where a lane's own value is larger than
+    // that, which never happens in densely sampled tiles: one warp-wide maximum decides whether to go on
+    if (__reduce_max_sync(0xffffffffu, E >> OSH) >= 2u * PPL) {
+#pragma unroll
+        for (int d = 2; d < 32; d <<= 1) {
+            const uint32_t o = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, d) : __shfl_down_sync(0xffffffffu, E, d);
+            const uint32_t t = o + (uint32_t(d * PPL) << OSH);
+            E = ((t | LMASK) < E) ? t : E;
+        }
     }
     const uint32_t cin = DIR > 0 ? __shfl_up_sync(0xffffffffu, E, 1) : __shfl_down_sync(0xffffffffu, E, 1);
     const uint32_t cd = min(cin >> OSH, clamp_dist);
