@@ -154,6 +154,24 @@ void launch_k2(bool pad, bool want_lbl, int grid, cudaStream_t s, const FramePar
     }
 }
 
+// tools.py:8 marks a pixel as source when !(float32(1 - x) > src_thr).  The predicate is monotone in x (false below,
+// true above; NaN inputs are sources), so it equals !(x < cut) for the smallest float `cut` that satisfies it.
+// Bisection over the floats in their total order (-inf .. -0 < +0 .. +inf); K1 then needs one subtraction per pixel.
+static inline float ordered_to_float(uint32_t k) {
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    float f; memcpy(&f, &b, 4); return f;
+}
+static float source_cut(float thr) {
+    auto is_src = [thr](float x) { volatile float d = 1.0f - x; return !(d > thr); };
+    uint32_t lo = 0x007FFFFFu, hi = 0xFF800000u;      // ordered keys of -inf and +inf; is_src(+inf) always holds
+    if (is_src(ordered_to_float(lo))) return ordered_to_float(lo);
+    while (hi - lo > 1) {                             // invariant: !is_src(lo), is_src(hi)
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (is_src(ordered_to_float(mid))) hi = mid; else lo = mid;
+    }
+    return ordered_to_float(hi);
+}
+
 // Enqueue the path for frames [b0, b0+nb) of the batch on stream s; all pointers are device pointers to the whole
 // batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
 int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
@@ -165,6 +183,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     FrameParams fp;
     fp.B = nb; fp.H = H; fp.W = W; fp.WW = WW;
     fp.src_thr = src_thr; fp.val_thr = val_thr;
+    fp.src_cut = source_cut(src_thr);
     fp.init_dist = H + W + 8;
     fp.force_wide = plan.ppl == 0;
     fp.scratch_units_per_frame = scratch_units_per_frame;

@@ -63,6 +63,7 @@ constexpr int MAX_CELLS = 15360;   // planner grid limit (30 KB of shared memory
 struct FrameParams {
     int B, H, W, WW;           // WW = 32-bit words per bit row
     float src_thr, val_thr;
+    float src_cut;             // smallest float x (in the total order) with !(float32(1 - x) > src_thr)
     int init_dist;             // "unreached" distance of the fast path: H + W + 8
     int force_wide;            // size not representable in the 32-bit key
     int band_cap;              // planner: target cost (row steps) of one task; <= 0 disables banding
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
     const int W = fp.W, WW = fp.WW;
     const long nrows = (long)fp.B * fp.H;
     const int nchunks = (W + 511) >> 9;
-    const float sthr = fp.src_thr, vthr = fp.val_thr;
+    const float scut = fp.src_cut, vthr = fp.val_thr;
     const bool mask16 = (W & 15) == 0;
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
@@ -178,17 +179,19 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
             uint32_t sb = 0, vb = 0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                // tools.py:8: source <=> !(float32(1 - x) > src_thr);  tools.py:22: valid <=> x > val_thr
-                const float d0 = __fsub_rn(1.0f, q[g].x), d1 = __fsub_rn(1.0f, q[g].y);
-                const float d2 = __fsub_rn(1.0f, q[g].z), d3 = __fsub_rn(1.0f, q[g].w);
-                const uint32_t ns = sign_nibble(__fsub_rn(sthr, d0), __fsub_rn(sthr, d1), __fsub_rn(sthr, d2),
-                                                __fsub_rn(sthr, d3));                       // bit = d > src_thr
+                // tools.py:8: source <=> !(float32(1 - x) > src_thr) <=> !(x < src_cut), src_cut being the smallest
+                // float that satisfies the predicate (found on the host, the predicate is monotone in x);
+                // tools.py:22: valid <=> x > val_thr
+                const uint32_t ns = sign_nibble(__fsub_rn(q[g].x, scut), __fsub_rn(q[g].y, scut), __fsub_rn(q[g].z, scut),
+                                                __fsub_rn(q[g].w, scut));                   // bit = x < src_cut
                 const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
                                                 __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
-                const uint32_t inb = col + 4 * g < W ? 0xFu : 0u;
-                sb |= ((ns ^ 0xFu) & inb) << (4 * g);
-                vb |= (nv & inb) << (4 * g);
+                sb |= ns << (4 * g);
+                vb |= nv << (4 * g);
             }
+            const uint32_t inb = (1u << min(max(W - col, 0), 16)) - 1u;      // pixels of this lane inside the row
+            sb = ~sb & inb;
+            vb &= inb;
             if (out_mask && col < W) {
                 uint32_t m[4];
 #pragma unroll

@@ -64,6 +64,33 @@ def test_random_small_frames_all_paths(handle):
         _check_frames(handle, x, 0.1, 0.1)
 
 
+@pytest.mark.parametrize("thr", [0.1, 0.001, 0.0, 1.0, 0.5, -0.5, 2.0, 1e-30, 0.9999999, 3e38, -3e38])
+def test_source_threshold_boundary(handle, thr):
+    """K1 evaluates tools.py:8's !(float32(1 - x) > thr) as !(x < cut) with a host-computed cut: every float within
+    a few ulps of the boundary, signed zeros, denormals and infinities must classify as the reference does."""
+    thr32 = np.float32(thr)
+    centre = np.float32(1.0) - thr32
+    vals = [centre]
+    for _ in range(6):
+        vals.append(np.nextafter(vals[-1], np.float32(np.inf)))
+    lo = centre
+    for _ in range(6):
+        lo = np.nextafter(lo, np.float32(-np.inf)); vals.append(lo)
+    vals += [0.0, -0.0, 1e-45, -1e-45, 1.0, -1.0, np.inf, 3e38, -3e38, 0.9, 0.999, 1.0000001, 2.0, 1e-38, -1e-38]
+    vals = np.array(vals, np.float32)
+    rng = np.random.default_rng(11)
+    for W in (64, 61):                                      # 128-bit K1 and the scalar K1
+        x = rng.choice(vals, size=(3, 16, W)).astype(np.float32)
+        with np.errstate(over="ignore", invalid="ignore"):
+            src = ~((np.float32(1.0) - x).astype(np.float32) > thr32)
+        r = handle.run_host(x, float(thr32), -3.3e38, want_dt=True, want_lbl=True)
+        assert "index_error" not in r
+        assert np.array_equal(r["counts"][:, 0], src.reshape(3, -1).sum(1))
+        o = O.dt_fill(x, float(thr32), -3.3e38)
+        assert np.array_equal(r["lbl"], o["lbl"]) and np.array_equal(r["dt"], o["dt"])
+        assert np.array_equal(r["depth"].view(np.uint32), o["depth"].view(np.uint32))
+
+
 @pytest.mark.parametrize("W", [320, 640, 1216, 319, 321, 641, 1215, 100, 37])
 def test_lane_layouts(handle, W):
     """Exact multiples of 32*PPL (no padding) and ragged widths for each lane layout (PPL 10/20/38)."""
