@@ -55,6 +55,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
         L.dtfill_set_subbatches.argtypes = [vp, ci]
+        L.dtfill_set_sky_min.argtypes = [vp, ci]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
         L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
@@ -66,7 +67,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
-                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
+                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_outlier_removal",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
@@ -165,11 +166,16 @@ class Handle:
             _check(rc, "dtfill_status")
         return bad.value, launches.value
 
-    KERNEL_NAMES = ("k1_mask_rows", "k1b_scan_compact", "k2_chamfer", "k2_chamfer_wide")
+    KERNEL_NAMES = ("k1_mask_rows", "k1b_scan_compact", "k2_chamfer", "k2_chamfer_wide", "k3_sky")
 
     def set_band_cap(self, cap: int):
         """Band planner target (row steps per task): >0 explicit, 0 never split frames, -1 automatic."""
         _check(self._L.dtfill_set_band_cap(self._h, int(cap)), "dtfill_set_band_cap")
+
+    def set_sky_min(self, rows: int):
+        """Least number of source-free top rows handed to the closed-form kernel k3_sky; 0: never; -1 (default):
+        8 in pipelined mode, never in strict order."""
+        _check(self._L.dtfill_set_sky_min(self._h, int(rows)), "dtfill_set_sky_min")
 
     def set_pipeline_depth(self, depth: int):
         """2: consecutive run_device_async calls may overlap (outputs final after flush()/status()); 1: strict."""
@@ -183,7 +189,7 @@ class Handle:
         """Number of sub-batches run on forked streams (<= 0: automatic)."""
         _check(self._L.dtfill_set_subbatches(self._h, int(n)), "dtfill_set_subbatches")
 
-    TASK_FIELDS = ("frame", "lo", "hi", "r0", "r1", "kind", "scratch_off", "fstart", "clo", "c0", "c1", "reserved")
+    TASK_FIELDS = ("frame", "lo", "hi", "r0", "r1", "kind", "scratch_off", "fstart", "clo", "c0", "c1", "sky")
 
     def debug_tasks(self, max_tasks: int = 1 << 16) -> np.ndarray:
         """Tiles the planner produced for the last run: int32 [n, 12] (TASK_FIELDS), unused slots removed."""
@@ -199,7 +205,7 @@ class Handle:
 
     def kernel_times(self) -> dict:
         """Milliseconds of each kernel of the last run (CUDA events on the handle's stream); profiling must be on."""
-        ms = (ctypes.c_float * 4)()
+        ms = (ctypes.c_float * len(self.KERNEL_NAMES))()
         _check(self._L.dtfill_kernel_times(self._h, ms), "dtfill_kernel_times")
         return dict(zip(self.KERNEL_NAMES, (float(v) for v in ms)))
 

@@ -39,7 +39,7 @@ struct Buf {
 // scan of the previous call.
 struct Lane {
     static const int MAX_SUB = 8;
-    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status;
+    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
     int* status_host = nullptr;          // pinned [2]
     cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
@@ -62,6 +62,7 @@ struct dtfill_ctx {
     Lane lanes[MAX_LANES];
     int ncalls = 0;                   // calls enqueued so far (pipelined mode alternates lanes)
     int last_lane = 0;
+    bool cur_pipelined = false;       // the call being enqueued runs on a lane's own stream
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
     cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
@@ -71,6 +72,9 @@ struct dtfill_ctx {
     bool profiling = false;
     bool tiles2d = true;
     int max_col_tiles = 4;
+    int sky_min = -1;             // source-free top rows go to k3_sky when there are at least this many; 0: never;
+                                  // -1: automatic (8 in pipelined mode, where k3_sky runs beside another batch's
+                                  // scan; never in strict order, where it would only lengthen the call)
     int nsub = -1;                // -1: automatic
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
@@ -190,6 +194,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     fp.wide_ppl = plan.ppl ? plan.ppl : 1;
     fp.narrow_ppl = (h->tiles2d && plan.ppl) ? plan.narrow : 0;
     fp.frame0 = b0;
+    fp.sky_min = h->sky_min >= 0 ? h->sky_min : (h->cur_pipelined ? 8 : 0);
     fp.max_col_tiles = h->max_col_tiles;
     fp.mul_dist = 1u << (32 - DSH);
     fp.mul_ord = 1u << (32 - OSH);
@@ -224,6 +229,8 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     ws.scratch = (uint32_t*)L->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
     ws.tasks = (Task*)L->tasks.p + (size_t)b0 * MAXT;
     ws.status = (int*)L->status.p;
+    ws.sky = (int*)L->sky.p + b0;
+    ws.skykeys = (uint32_t*)L->skykeys.p + (size_t)b0 * 2 * W;
     const float* in_s = in + npx0;
     float* od = out_depth + npx0;
     float* odt = out_dt ? out_dt + npx0 : nullptr;
@@ -277,6 +284,13 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
         ++*launches;
         CU(cudaEventRecord(h->ev[4], s));
     }
+    // rows above the first source row, from the two base rows the scan left in ws.skykeys (blocks of frames without
+    // such rows return at once)
+    if (fp.band_cap > 0 && fp.sky_min > 0 && W <= SKY_MAX_W) {
+        k3_sky<<<dim3(nb, (H + SKY_ROWS - 1) / SKY_ROWS), 256, 0, s>>>(fp, ws, od, odt, ol);
+        ++*launches;
+    }
+    if (h->profiling) CU(cudaEventRecord(h->ev[5], s));
     return 0;
 }
 
@@ -291,6 +305,7 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     // lane and stream of this call
     const bool pipelined = h->pipeline_depth > 1 && !h->profiling && !hio;
     Lane* L = &h->lanes[pipelined ? (h->ncalls % h->pipeline_depth) : 0];
+    h->cur_pipelined = pipelined;
     const Plan plan = make_plan(H, W);
     const int WW = (W + 31) / 32;
     const size_t rows = (size_t)B * H;
@@ -311,6 +326,8 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if ((rc = ensure(h, L->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, L->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
     if ((rc = ensure(h, L->status, 256))) return rc;
+    if ((rc = ensure(h, L->sky, (size_t)B * 4))) return rc;
+    if ((rc = ensure(h, L->skykeys, (size_t)B * 2 * W * 4))) return rc;
     {
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
         static size_t configured = 0;
@@ -443,6 +460,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
     if (const char* e = getenv("DTFILL_MAX_COL_TILES")) h->max_col_tiles = atoi(e);
+    if (const char* e = getenv("DTFILL_SKY_MIN")) h->sky_min = atoi(e) < -1 ? -1 : atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
         const int d = atoi(e);
@@ -651,6 +669,12 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
 int dtfill_set_band_cap(dtfill_t* h, int cap) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_band_cap: NULL handle");
     h->band_cap = cap;
+    return 0;
+}
+
+int dtfill_set_sky_min(dtfill_t* h, int rows) {
+    if (!h || rows < -1) return fail(DTFILL_E_ARG, "dtfill_set_sky_min: NULL handle or row count below -1");
+    h->sky_min = rows;
     return 0;
 }
 

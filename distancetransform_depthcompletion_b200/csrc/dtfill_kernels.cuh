@@ -52,12 +52,14 @@ struct __align__(16) Task {
     int fstart;        // first row >= lo holding a source: the forward pass starts here (rows above stay "unreached")
     int clo;           // first column of the sub-image
     int c0, c1;        // columns whose results are written
-    int pad_;
+    int sky;           // S > 0: r0 == S and rows [0,S) of the frame are filled by k3_sky from the final keys of rows
+                       // S, S+1, which this task stores into ws.skykeys; -2 otherwise
 };
 
 constexpr int MAXT = 32;      // task slots per frame; slot-major layout tasks[slot * B + frame]
 constexpr int CELL_H = 4;     // coarse occupancy cells used by the band planner
 constexpr int CELL_W = 8;
+constexpr int SKY_MAX_W = 1216; // widest frame of the 32-bit-key path (32 lanes x 38 pixels): size of k3_sky's tables
 constexpr int MAX_CELLS = 15360;   // planner grid limit (30 KB of shared memory); larger frames are not banded
 
 struct FrameParams {
@@ -71,6 +73,7 @@ struct FrameParams {
     int wide_ppl;              // pixels per lane of the full-width kernel instance (scratch units per row)
     int narrow_ppl;            // pixels per lane of the half-width instance, 0 if frames are never split in columns
     int max_col_tiles;         // planner: at most this many narrow tiles side by side (2..4)
+    int sky_min;               // planner: least number of source-free top rows worth handing to k3_sky; 0 disables
     int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
     // Multipliers handed over at run time so that ptxas keeps the multiply-adds below on the FMA pipe instead of
     // strength-reducing them to shifts/LEAs on the ALU pipe, which is the pipe the scan kernel saturates.
@@ -92,6 +95,8 @@ struct Workspace {
     float* dlist;        // [B*H*W] depth_list per frame (first n_valid entries used)
     uint32_t* scratch;   // forward state, lane-major rows of 32*PPL keys
     Task* tasks;         // [B * max_tasks_per_frame]
+    int* sky;            // [B] S: rows [0,S) lie above every source and are filled by k3_sky (0: none)
+    uint32_t* skykeys;   // [B*2*W] final keys of rows S and S+1
     int* status;         // [0] first bad frame (INT_MAX if none), [1] number of wide tasks
 };
 
@@ -584,12 +589,23 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         auto blank = [&](int knd) {
             Task q;
             q.frame = b; q.lo = 0; q.hi = H; q.r0 = 0; q.r1 = H; q.kind = knd; q.scratch_off = 0; q.fstart = 0;
-            q.clo = 0; q.c0 = 0; q.c1 = W; q.pad_ = 0;
+            q.clo = 0; q.c0 = 0; q.c1 = W; q.sky = -2;
             return q;
         };
+        // Rows above the first source row f need no scan: their distance is that of row f plus the row offset and
+        // their label follows a fixed route down to two base rows (see k3_sky).  S = rows handed to k3_sky, a
+        // multiple of the cell height with S + 1 <= f; the tiles below cover rows [S, H).
+        int S = 0;
+        if (plan && fp.sky_min > 0 && W <= SKY_MAX_W) {
+            int f = 0;
+            for (int w = 0; w < 128 && (w << 5) < H; ++w)
+                if (srcrows[w]) { f = (w << 5) + __ffs(srcrows[w]) - 1; break; }
+            const int s4 = f >= 1 ? ((f - 1) / CELL_H) * CELL_H : 0;
+            if (s4 >= fp.sky_min) S = s4;
+        }
         if (plan) {
             const int nwid = fp.narrow_ppl * 32;                 // width of a half-width tile (0: never split)
-            int cy = 0, scr = 0;
+            int cy = S / CELL_H, scr = 0;
             bool ok = true;
             while (cy < nh && ok) {
                 const int r0 = cy * CELL_H;
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                     lo = min(lo, c * CELL_H - cellU[c]);
                     hi = max(hi, min(H, (c + 1) * CELL_H) + cellU[c]);
                     umax = max(umax, cellU[c]);
-                    const int L = max(0, lo), Hh = min(H, hi);
+                    const int L = max(S, lo), Hh = min(H, hi);      // nothing above S feeds the forward pass
                     const int cst = (Hh - L) + (Hh - r0);
                     // extend while the tile stays under the target cost, while extending is (nearly) free, or while
                     // the band is still short compared with its halo (sparse frames: tall bands, less redundancy)
@@ -609,6 +625,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 }
                 Task q = blank(TASK_CHAMFER);
                 q.lo = best_lo; q.hi = best_hi; q.r0 = r0; q.r1 = min(H, end * CELL_H);
+                q.sky = (S > 0 && r0 == S) ? S : -2;
                 // n overlapping narrow tiles when the bound leaves every written pixel's ball inside its tile and the
                 // extra columns stay below ~60 % (n * nwid <= 1.6 W)
                 int ntile = 0;
@@ -651,8 +668,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 if (scr > fp.scratch_units_per_frame) ok = false;
                 cy = end;
             }
-            if (!ok) nt = 0;
+            if (!ok) { nt = 0; S = 0; }
         }
+        ws.sky[b] = S;
         if (nt == 0) {
             cost[0] = 4 * H;
             t[nt++] = blank(kind);
@@ -686,7 +704,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 q.scratch_off += b * fp.scratch_units_per_frame;
             } else {
                 q.frame = b; q.lo = 0; q.hi = 0; q.r0 = 0; q.r1 = 0; q.kind = TASK_SKIP; q.scratch_off = 0; q.fstart = 0;
-                q.clo = 0; q.c0 = 0; q.c1 = W; q.pad_ = 0;
+                q.clo = 0; q.c0 = 0; q.c1 = W; q.sky = -2;
             }
             ws.tasks[(long)slot * B + b] = q;
         }
@@ -922,12 +940,15 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
             Bq.v[i] = t;
         }
         refresh_halo(Bq, lane, init_key);
-        // forward state -> scratch, [vector j][lane] so that every store instruction is fully coalesced
-        char* dst = reinterpret_cast<char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
+        // forward state -> scratch, [vector j][lane] so that every store instruction is fully coalesced; the rows of
+        // the upper halo are never read back (the backward pass ends at r0)
+        if (y >= task.r0) {
+            char* dst = reinterpret_cast<char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
-        for (int j = 0; j < PPL / VW; ++j) {
-            if (VW == 4) st_scratch_v4(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3]);
-            else st_scratch_v2(dst + j * 256, Bq.v[2 * j], Bq.v[2 * j + 1]);
+            for (int j = 0; j < PPL / VW; ++j) {
+                if (VW == 4) st_scratch_v4(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3]);
+                else st_scratch_v2(dst + j * 256, Bq.v[2 * j], Bq.v[2 * j + 1]);
+            }
         }
     };
 
@@ -1075,6 +1096,16 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
                     }
                 }
             }
+            if (y <= task.sky + 1) {                 // base rows S, S+1 of the source-free top rows: keys for k3_sky
+                uint32_t* sk = ws.skykeys + ((long)b * 2 + (y - task.sky)) * W;
+                for (int lc = lane * 4; lc < 32 * PPL; lc += 128) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = task.clo + lc + e;
+                        if (col >= task.c0 && col < task.c1) sk[col] = stage[lc + e];
+                    }
+                }
+            }
             __syncwarp();                            // stage is free for the next row
         }
     };
@@ -1086,6 +1117,73 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
     }
     cp_async_wait<0>();
     if (VEC) flush_depth_row(task.r0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: the rows above the first source row f ("sky": the upper third of a KITTI frame).  Nothing lies above or
+// beside them, so OpenCV's forward scan leaves them unreached, and in the backward scan every candidate of a pixel
+// (y,x) with y + 2 <= f has a distance of the form (f - y') + g(x'), g = dt of row f, which is 1-Lipschitz.  Hence
+//     dt(y,x)  = g(x) + (f - y)
+//     lbl(y,x) = lbl(y+2, x+1)  if g(x+1) == g(x) - 1      the first candidate in OpenCV's order that attains
+//              = lbl(y+2, x-1)  elif g(x-1) == g(x) - 1     the minimum (strict '>' update); the candidates
+//              = lbl(y+1, x)    otherwise                   (+1,+2), (+1,+1) tie only if (+2,+1) already did
+// The route is monotone: t(x) diagonal steps down g towards a valley column v(x), then straight down.  With the
+// two base rows S, S+1 (S + 1 <= f, final keys stored by K2) and j = ceil((S - y) / 2) diagonal steps above them:
+//     t(x) <  j :  lbl(y,x) = lbl(S, v(x))
+//     t(x) >= j :  lbl(y,x) = lbl(y + 2j, x + s(x) j),   y + 2j in {S, S+1},  s(x) = +-1 the direction of descent
+// i.e. one table lookup per pixel, no scan.  tests/test_kernel_model.py checks the rule against the oracle.
+// One block per 32 rows of a frame; the per-column tables are rebuilt by every block (W entries).
+// ------------------------------------------------------------------------------------------------------
+constexpr int SKY_ROWS = 32;
+
+__global__ void __launch_bounds__(256) k3_sky(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+                                               float* __restrict__ out_dt, int32_t* __restrict__ out_lbl)
+{
+    __shared__ uint16_t d0[SKY_MAX_W + 2];       // dt of row S, one guard entry on each side
+    __shared__ uint16_t steps[SKY_MAX_W];        // t(x)
+    __shared__ int8_t dir[SKY_MAX_W];            // s(x)
+    __shared__ float dep[2][SKY_MAX_W];          // depth_list[lbl - 1] of the two base rows
+    const int b = blockIdx.x, S = ws.sky[b];
+    const int y0 = blockIdx.y * SKY_ROWS;
+    if (y0 >= S) return;
+    const int H = fp.H, W = fp.W, tid = threadIdx.x;
+    const long fpx = (long)b * H * W;
+    const uint32_t* sk = ws.skykeys + (long)b * 2 * W;
+    const float* dl = ws.dlist + fpx;
+    for (int x = tid; x < W; x += 256) {
+        const uint32_t k0 = sk[x], k1 = sk[W + x];
+        d0[x + 1] = (uint16_t)(k0 >> DSH);
+        dep[0][x] = dl[(k0 & LMASK) - 1u];
+        dep[1][x] = dl[(k1 & LMASK) - 1u];
+    }
+    if (tid == 0) { d0[0] = 0xFFFFu; d0[W + 1] = 0xFFFFu; }
+    __syncthreads();
+    for (int x = tid; x < W; x += 256) {
+        const int g = d0[x + 1];
+        dir[x] = (int)d0[x + 2] == g - 1 ? 1 : ((int)d0[x] == g - 1 ? -1 : 0);
+    }
+    __syncthreads();
+    for (int x = tid; x < W; x += 256) {
+        const int sd = dir[x];
+        int k = 0;
+        for (int xx = x; dir[xx] != 0; xx += sd) ++k;
+        steps[x] = (uint16_t)k;
+    }
+    __syncthreads();
+    const int yend = min(y0 + SKY_ROWS, S);
+    for (int y = y0; y < yend; ++y) {
+        const int j = (S - y + 1) >> 1, odd = (S - y) & 1;
+        const long ro = fpx + (long)y * W;
+        for (int x = tid; x < W; x += 256) {
+            const int t = steps[x], sd = dir[x];
+            const bool valley = t < j;
+            const int col = x + sd * (valley ? t : j);
+            const int r = valley ? 0 : odd;
+            st_stream_u32(out_depth + ro + x, __float_as_uint(dep[r][col]));
+            if (out_dt) st_stream_u32(out_dt + ro + x, __float_as_uint((float)((int)d0[x + 1] + S - y)));
+            if (out_lbl) st_stream_u32(out_lbl + ro + x, sk[r * W + col] & LMASK);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -139,6 +139,12 @@ int dtfill_flush(dtfill_t* h);
  * one band in row steps; 0: never split; -1 (default): chosen from the batch size and the SM count. */
 int dtfill_set_band_cap(dtfill_t* h, int cap);
 
+/* Rows above a frame's first source row are not scanned: their distances and labels follow in closed form from two
+ * rows of the scan (kernel k3_sky; exact, see the kernel's header).  rows = least number of such rows for which
+ * this is done; 0: never, every row goes through the scan; -1 (default): 8 in pipelined mode, where k3_sky runs
+ * beside another batch's scan, and never in strict order, where it would only lengthen the call. */
+int dtfill_set_sky_min(dtfill_t* h, int rows);
+
 /* A batch is processed as n sub-batches on forked streams so that the ALU-bound scan of one overlaps the
  * HBM-bound predicate pass of the next (joined back into the handle's stream before the call returns / the
  * async call's work is complete).  n <= 0: automatic (4 for batches of 64 frames or more). */
@@ -155,8 +161,8 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n);
 
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
- * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide into ms[0..3]. */
-#define DTFILL_NUM_KERNELS 4
+ * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide, k3_sky into ms[0..4]. */
+#define DTFILL_NUM_KERNELS 5
 int dtfill_set_profiling(dtfill_t* h, int enabled);
 int dtfill_kernel_times(dtfill_t* h, float* ms);
 

@@ -142,3 +142,32 @@ def coarse_row_bound(src: np.ndarray, ch: int, cw: int) -> np.ndarray:
             if cx < nw - 1: D[cy, cx] = min(D[cy, cx], D[cy, cx + 1] + cw)
     cellmax = D.max(axis=1) + (ch - 1) + (cw - 1)
     return np.repeat(cellmax, ch)[:H]
+
+
+# ---- rows above the first source row (kernel k3_sky) -----------------------------------------------------------
+def sky_rows_closed_form(dt: np.ndarray, lbl: np.ndarray, S: int):
+    """Rows [0,S) of (dt, lbl) from rows S and S+1 alone, for a frame whose first source row f satisfies S+1 <= f:
+    dt(y,x) = dt(S,x) + (S-y); the label follows t(x) diagonal steps down the distance profile of row S towards
+    its valley column, then straight down (see the header of k3_sky in csrc/dtfill_kernels.cuh)."""
+    H, W = dt.shape
+    g = dt[S].astype(np.int64)
+    INF = np.int64(1) << 40
+    right = np.concatenate([g[1:], [INF]])
+    left = np.concatenate([[INF], g[:-1]])
+    s = np.where(right == g - 1, 1, np.where(left == g - 1, -1, 0))
+    t = np.zeros(W, np.int64)
+    for x in range(W):
+        xx = x
+        while s[xx] != 0:
+            xx += s[x]
+            t[x] += 1
+    odt, ol = dt.copy(), lbl.copy()
+    xs = np.arange(W)
+    for y in range(S):
+        j = (S - y + 1) >> 1
+        valley = t < j
+        row = np.where(valley, S, y + 2 * j)
+        col = np.where(valley, xs + s * t, xs + s * j)
+        ol[y] = lbl[row, col]
+        odt[y] = g + (S - y)
+    return odt, ol

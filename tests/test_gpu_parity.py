@@ -144,28 +144,79 @@ def test_band_splitting_is_exact(handle, cap):
         handle.set_band_cap(-1)
 
 
-def test_planner_tiles_cover_every_pixel_once(handle):
-    """The tiles of a frame partition its pixels (written regions disjoint and complete), each written region
-    lies inside its sub-image, and KITTI-like frames do get split (rows and columns)."""
+@pytest.mark.parametrize("sky", [0, 8])
+def test_planner_tiles_cover_every_pixel_once(handle, sky):
+    """The tiles of a frame (plus, with sky > 0, the rows handed to k3_sky) partition its pixels (written regions
+    disjoint and complete), each written region lies inside its sub-image, and KITTI-like frames do get split
+    (rows and columns)."""
     for cap in (-1, 60, 150):
         handle.set_band_cap(cap)
+        handle.set_sky_min(sky)
         handle.set_subbatches(1)          # one task list for the whole batch (frame indices are per sub-batch)
         x = np.stack([synth.kitti_frame(800 + i, beam_step=(1, 8)[i % 2]) for i in range(4)])
         handle.run_host(x, 0.1, 0.1)
         t = handle.debug_tasks()
         handle.set_band_cap(-1)
+        handle.set_sky_min(-1)
         handle.set_subbatches(-1)
         for b in range(4):
             cover = np.zeros((352, 1216), np.int32)
             tb = t[t[:, 0] == b]
-            for (_, lo, hi, r0, r1, kind, _, fstart, clo, c0, c1, _) in tb:
-                assert kind in (0, 4) and 0 <= lo <= r0 < r1 <= hi <= 352 and lo <= fstart < hi
+            S = max(0, int(tb[:, 11].max()))          # rows [0,S) are k3_sky's (closed form above the first source row)
+            first_src = int(np.argmax((x[b] > 0.9).any(axis=1)))
+            if sky:
+                assert S % 4 == 0 and S + 1 <= first_src and S >= first_src - 4
+            else:
+                assert S == 0
+            cover[:S] += 1
+            for (_, lo, hi, r0, r1, kind, _, fstart, clo, c0, c1, sk) in tb:
+                assert kind in (0, 4) and S <= lo <= r0 < r1 <= hi <= 352 and lo <= fstart < hi
+                assert sk == (S if (S > 0 and r0 == S) else -2) and (sk < 0 or r1 >= S + 2)
                 width = 1216 if kind == 0 else 640
                 assert clo % 4 == 0 and clo <= c0 < c1 <= min(1216, clo + width)
                 cover[r0:r1, c0:c1] += 1
             assert np.all(cover == 1)
         if cap != 0:
             assert len(t) > 4 and np.any(t[:, 5] == 4), "KITTI frames should be tiled in rows and columns"
+
+
+@pytest.mark.parametrize("W", [1216, 1215, 640, 333, 36])
+def test_rows_above_first_source_closed_form(handle, W):
+    """k3_sky: rows above the first source row come from two rows of the scan, not from the scan itself.  Any
+    height of the source-free top (aligned or not with the planner's cells), plateaus and single sources in the
+    first source row, label and distance outputs on or off -- all bit-exact against the oracle."""
+    rng = np.random.default_rng(W)
+    H = 96
+    handle.set_band_cap(40)
+    handle.set_sky_min(8)
+    try:
+        frames = []
+        for top in (1, 2, 7, 8, 9, 12, 13, 31, 32, 33, 60, 90, 94):
+            dens = rng.choice([0.01, 0.1, 0.6])
+            f = ((rng.random((H, W)) < dens) * rng.uniform(1, 50, (H, W))).astype(np.float32)
+            f[:top] = 0
+            f[top] = 0
+            kind = top % 3
+            if kind == 0:
+                f[top, rng.integers(0, W)] = 2.0                       # one source: slopes as long as the row
+            elif kind == 1:
+                f[top, ::max(1, W // 7)] = 3.0                         # sparse comb
+            else:
+                f[top, W // 3: W // 2 + 1] = 4.0                       # a plateau of sources
+            frames.append(f)
+        x = np.stack(frames)
+        r = _check_frames(handle, x, 0.1, 0.1)
+        t = handle.debug_tasks()
+        if W % 4 == 0 or W > 640:
+            assert (t[:, 11] >= 8).any(), "some of these frames must have used the closed form"
+        handle.set_sky_min(0)
+        r0 = handle.run_host(x, 0.1, 0.1, want_dt=True, want_lbl=True)
+        assert not (handle.debug_tasks()[:, 11] > 0).any()
+        for k in ("depth", "dt", "lbl"):
+            assert np.array_equal(r[k], r0[k])
+    finally:
+        handle.set_band_cap(-1)
+        handle.set_sky_min(-1)
 
 
 @pytest.mark.parametrize("W", [660, 800, 1000, 1212, 1216, 400, 500, 592])

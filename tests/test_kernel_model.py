@@ -57,3 +57,26 @@ def test_model_bands_small():
 def test_model_kitti_and_nyu_shapes():
     _run(synth.kitti_frame(0)[100:180], 0.1, 38)       # 80 rows at full width: exercises PPL=38 packing
     _run(synth.nyu_frame(0)[:64], 0.001, 20)
+
+
+def test_sky_rows_closed_form_matches_oracle():
+    """The rule k3_sky implements for the rows above the first source row, against the oracle's scan."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    checked = 0
+    for trial in range(120):
+        H, W = int(rng.integers(6, 50)), int(rng.integers(1, 80))
+        f = int(rng.integers(1, H))
+        dens = rng.choice([0.01, 0.05, 0.3, 0.9])
+        x = ((rng.random((H, W)) < dens) * rng.uniform(1, 50, (H, W))).astype(np.float32)
+        x[:f] = 0
+        x[f, rng.integers(0, W)] = 5.0
+        o = O.dt_fill(x[None], 0.1, 0.1)
+        dt, lbl = o["dt"][0], o["lbl"][0]
+        for S in {f - 1, (f - 1) // 4 * 4, max(f - 3, 0)}:
+            if S < 1:
+                continue
+            odt, ol = M.sky_rows_closed_form(dt.astype(np.int64), lbl, S)
+            assert np.array_equal(odt, dt.astype(np.int64)) and np.array_equal(ol, lbl), (H, W, f, S)
+            checked += 1
+    assert checked > 100
