@@ -55,6 +55,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
         L.dtfill_set_subbatches.argtypes = [vp, ci]
+        L.dtfill_run_u16.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, ci, ctypes.POINTER(ci)]
+        L.dtfill_run_u16_async.argtypes = [vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp]
         L.dtfill_set_sky_min.argtypes = [vp, ci]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
@@ -67,7 +69,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
-                     "dtfill_status", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
+                     "dtfill_status", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_outlier_removal",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
@@ -150,7 +152,38 @@ class Handle:
         _check(rc, "dtfill_run")
         return res
 
+    def run_host_u16(self, png: np.ndarray, crop_top: int, src_thr: float, val_thr: float, want_lidar=False,
+                     want_dt=False, want_lbl=False, want_mask=False, want_counts=True):
+        """png uint16 [B,H_in,W] (KITTI depth PNG samples, depth = sample / 256; data_read.py:215); rows
+        [crop_top, H_in) are processed (train.py:211).  Outputs as run_host, plus the decoded frames on request."""
+        assert png.dtype == np.uint16 and png.ndim == 3 and png.flags.c_contiguous
+        B, Hin, W = png.shape
+        H = Hin - int(crop_top)
+        lidar = np.empty((B, H, W), np.float32) if want_lidar else None
+        depth = np.empty((B, H, W), np.float32)
+        dt = np.empty((B, H, W), np.float32) if want_dt else None
+        lbl = np.empty((B, H, W), np.int32) if want_lbl else None
+        mask = np.empty((B, H, W), np.uint8) if want_mask else None
+        counts = np.empty((B, 2), np.int32) if want_counts else None
+        bad = ctypes.c_int(-1)
+        rc = self._L.dtfill_run_u16(self._h, _ptr(png), 0, B, Hin, W, int(crop_top), float(src_thr), float(val_thr),
+                                    _ptr(lidar), _ptr(depth), _ptr(dt), _ptr(lbl), _ptr(mask), _ptr(counts), 0,
+                                    ctypes.byref(bad))
+        res = dict(lidar=lidar, depth=depth, dt=dt, lbl=lbl, mask=mask, counts=counts, first_bad=bad.value)
+        if rc == E_INDEX:
+            res["index_error"] = last_error()
+            return res
+        _check(rc, "dtfill_run_u16")
+        return res
+
     # ---- device path (raw pointers, e.g. torch tensors' data_ptr()) ------------------------------------
+    def run_device_u16_async(self, in_ptr: int, B: int, H_in: int, W: int, crop_top: int, src_thr: float,
+                             val_thr: float, depth_ptr: int, lidar_ptr: int | None = None, dt_ptr: int | None = None,
+                             lbl_ptr: int | None = None, mask_ptr: int | None = None, counts_ptr: int | None = None):
+        _check(self._L.dtfill_run_u16_async(self._h, _ptr(in_ptr), B, H_in, W, int(crop_top), float(src_thr),
+                                            float(val_thr), _ptr(lidar_ptr), _ptr(depth_ptr), _ptr(dt_ptr),
+                                            _ptr(lbl_ptr), _ptr(mask_ptr), _ptr(counts_ptr)), "dtfill_run_u16_async")
+
     def run_device_async(self, in_ptr: int, B: int, H: int, W: int, src_thr: float, val_thr: float, depth_ptr: int,
                          dt_ptr: int | None = None, lbl_ptr: int | None = None, mask_ptr: int | None = None,
                          counts_ptr: int | None = None):

@@ -63,9 +63,14 @@ struct dtfill_ctx {
     int ncalls = 0;                   // calls enqueued so far (pipelined mode alternates lanes)
     int last_lane = 0;
     bool cur_pipelined = false;       // the call being enqueued runs on a lane's own stream
+    // input of the call being enqueued: float32 frames [B,H,W], or uint16 PNG samples [B,in_H,W] of which rows
+    // [in_crop, in_crop + H) are the frame (dtfill_run_u16); lidar_dev: decoded float32 frames, optional
+    bool in_u16 = false;
+    int in_H = 0, in_crop = 0;
+    float* lidar_dev = nullptr;
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
     cudaEvent_t pipe_fork = nullptr;
-    Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev;      // staging for host-pointer calls
+    Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
     int32_t* counts_host = nullptr;   // pinned staging for out_counts (a pageable destination would serialise the
     size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
@@ -104,7 +109,8 @@ int ensure(dtfill_t* h, Buf& b, size_t bytes) {
 // Host buffers of a dtfill_run call with host pointers: each sub-batch copies its own slices on its own stream, so
 // the host->device copy of one slice, the kernels of another and the device->host copy of a third overlap.
 struct HostIO {
-    const float* in = nullptr;
+    const void* in = nullptr;
+    float* lidar = nullptr;
     float* depth = nullptr;
     float* dt = nullptr;
     int32_t* lbl = nullptr;
@@ -178,7 +184,7 @@ static float source_cut(float thr) {
 
 // Enqueue the path for frames [b0, b0+nb) of the batch on stream s; all pointers are device pointers to the whole
 // batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
-int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const float* in, int H, int W,
+int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const void* in, int H, int W,
                   float src_thr, float val_thr, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
                   int32_t* out_counts, int scratch_units_per_frame, int sub_index, int* launches) {
     const int WW = (W + 31) / 32;
@@ -186,6 +192,8 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     const size_t rows = (size_t)nb * H;
     FrameParams fp;
     fp.B = nb; fp.H = H; fp.W = W; fp.WW = WW;
+    fp.in_H = h->in_u16 ? h->in_H : H;
+    fp.in_crop = h->in_u16 ? h->in_crop : 0;
     fp.src_thr = src_thr; fp.val_thr = val_thr;
     fp.src_cut = source_cut(src_thr);
     fp.init_dist = H + W + 8;
@@ -231,7 +239,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     ws.status = (int*)L->status.p;
     ws.sky = (int*)L->sky.p + b0;
     ws.skykeys = (uint32_t*)L->skykeys.p + (size_t)b0 * 2 * W;
-    const float* in_s = in + npx0;
+    float* olid = h->lidar_dev ? h->lidar_dev + npx0 : nullptr;
     float* od = out_depth + npx0;
     float* odt = out_dt ? out_dt + npx0 : nullptr;
     int32_t* ol = out_lbl ? out_lbl + npx0 : nullptr;
@@ -242,8 +250,15 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     {   // K1: one warp per row
         long want = ((long)rows + 7) / 8;
         int grid = (int)(want < 1 ? 1 : want);
-        if ((W & 3) == 0) k1_mask_rows_v16<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
-        else k1_mask_rows<<<grid, 256, 0, s>>>(in_s, fp, ws, om);
+        if (!h->in_u16) {
+            const float* in_s = (const float*)in + npx0;
+            if ((W & 3) == 0) k1_mask_rows_v16<float><<<grid, 256, 0, s>>>(in_s, fp, ws, om, nullptr);
+            else k1_mask_rows<float><<<grid, 256, 0, s>>>(in_s, fp, ws, om, nullptr);
+        } else {
+            const uint16_t* in_s = (const uint16_t*)in + (size_t)b0 * h->in_H * W;
+            if ((W & 7) == 0) k1_mask_rows_v16<uint16_t><<<grid, 256, 0, s>>>(in_s, fp, ws, om, olid);
+            else k1_mask_rows<uint16_t><<<grid, 256, 0, s>>>(in_s, fp, ws, om, olid);
+        }
         ++*launches;
     }
     if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
@@ -295,7 +310,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
 }
 
 // Enqueue the whole path on h->stream; all pointers are device pointers.
-int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
+int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
             float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts, const HostIO* hio = nullptr) {
     if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
@@ -365,14 +380,16 @@ int enqueue(dtfill_t* h, const float* in, int B, int H, int W, float src_thr, fl
     if (h->profiling || nsub < 1) nsub = 1;
     auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
-        const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
-        CU(cudaMemcpyAsync(const_cast<float*>(in) + o, hio->in + o, n * 4, cudaMemcpyHostToDevice, st));
+        const size_t frame_bytes = h->in_u16 ? (size_t)h->in_H * W * 2 : (size_t)H * W * 4;
+        CU(cudaMemcpyAsync((char*)const_cast<void*>(in) + b0 * frame_bytes, (const char*)hio->in + b0 * frame_bytes,
+                           nb * frame_bytes, cudaMemcpyHostToDevice, st));
         return 0;
     };
     auto copy_out = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
         const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
         CU(cudaMemcpyAsync(hio->depth + o, out_depth + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->lidar) CU(cudaMemcpyAsync(hio->lidar + o, h->lidar_dev + o, n * 4, cudaMemcpyDeviceToHost, st));
         if (hio->dt) CU(cudaMemcpyAsync(hio->dt + o, out_dt + o, n * 4, cudaMemcpyDeviceToHost, st));
         if (hio->lbl) CU(cudaMemcpyAsync(hio->lbl + o, out_lbl + o, n * 4, cudaMemcpyDeviceToHost, st));
         if (hio->mask) CU(cudaMemcpyAsync(hio->mask + o, out_mask + o, n, cudaMemcpyDeviceToHost, st));
@@ -562,34 +579,47 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
     return 0;
 }
 
-int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float src_thr, float val_thr,
-               float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts,
-               int out_is_device, int* first_bad_frame) {
-    if (first_bad_frame) *first_bad_frame = -1;
-    if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
-    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
+namespace {
+
+// Input description of one call, installed on the handle while the call is enqueued.
+struct InputScope {
+    dtfill_t* h;
+    InputScope(dtfill_t* h_, bool u16, int in_H, int in_crop, float* lidar_dev) : h(h_) {
+        h->in_u16 = u16; h->in_H = in_H; h->in_crop = in_crop; h->lidar_dev = lidar_dev;
+    }
+    ~InputScope() { h->in_u16 = false; h->in_H = 0; h->in_crop = 0; h->lidar_dev = nullptr; }
+};
+
+// dtfill_run / dtfill_run_u16: buffers on either side, synchronous.  u16: `in` holds uint16 samples [B,in_H,W].
+int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, int in_crop, int B, int H, int W,
+             float src_thr, float val_thr, float* out_lidar, float* out_depth, float* out_dt, int32_t* out_lbl,
+             uint8_t* out_mask, int32_t* out_counts, int out_is_device, int* first_bad_frame) {
     CU(cudaSetDevice(h->device));
     const size_t npx = (size_t)B * H * W;
+    const size_t in_bytes = u16 ? (size_t)B * in_H * W * 2 : npx * 4;
     int rc;
-    const float* in_d = in;
+    const void* in_d = in;
     const bool pipelined = !in_is_device && !out_is_device;     // both sides on the host: copies are sliced
     if (!in_is_device) {
-        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
-        if (!pipelined) CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, h->stream));
-        in_d = (const float*)h->in_dev.p;
+        if ((rc = ensure(h, h->in_dev, in_bytes))) return rc;
+        if (!pipelined) CU(cudaMemcpyAsync(h->in_dev.p, in, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        in_d = h->in_dev.p;
     }
-    float* od = out_depth; float* odt = out_dt; int32_t* ol = out_lbl; uint8_t* om = out_mask; int32_t* oc = out_counts;
+    float* olid = out_lidar; float* od = out_depth; float* odt = out_dt; int32_t* ol = out_lbl; uint8_t* om = out_mask;
+    int32_t* oc = out_counts;
     if (!out_is_device) {
         if ((rc = ensure(h, h->depth_dev, npx * 4))) return rc;
         od = (float*)h->depth_dev.p;
+        if (out_lidar) { if ((rc = ensure(h, h->lidar_out_dev, npx * 4))) return rc; olid = (float*)h->lidar_out_dev.p; }
         if (out_dt) { if ((rc = ensure(h, h->dt_dev, npx * 4))) return rc; odt = (float*)h->dt_dev.p; }
         if (out_lbl) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ol = (int32_t*)h->lbl_dev.p; }
         if (out_mask) { if ((rc = ensure(h, h->mask_dev, npx))) return rc; om = (uint8_t*)h->mask_dev.p; }
         if (out_counts) { if ((rc = ensure(h, h->counts_out_dev, (size_t)B * 8))) return rc; oc = (int32_t*)h->counts_out_dev.p; }
     }
+    InputScope scope(h, u16, in_H, in_crop, olid);
     if (pipelined) {
         HostIO hio;
-        hio.in = in; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask;
+        hio.in = in; hio.lidar = out_lidar; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask;
         if (out_counts) {
             if (h->counts_host_cap < (size_t)B * 2) {
                 if (h->counts_host) cudaFreeHost(h->counts_host);
@@ -608,12 +638,52 @@ int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
     if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc))) return rc;
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out_depth, od, npx * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_lidar) CU(cudaMemcpyAsync(out_lidar, olid, npx * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out_dt) CU(cudaMemcpyAsync(out_dt, odt, npx * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out_lbl) CU(cudaMemcpyAsync(out_lbl, ol, npx * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out_mask) CU(cudaMemcpyAsync(out_mask, om, npx, cudaMemcpyDeviceToHost, h->stream));
         if (out_counts) CU(cudaMemcpyAsync(out_counts, oc, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     return dtfill_status(h, first_bad_frame, nullptr);
+}
+
+int check_u16_args(const char* who, dtfill_t* h, const void* in, const void* out_depth, int B, int in_H, int W, int crop_top) {
+    if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, std::string(who) + ": NULL handle, input or out_depth");
+    if (B <= 0 || in_H <= 0 || W <= 0) return fail(DTFILL_E_ARG, std::string(who) + ": B, H_in, W must be positive");
+    if (crop_top < 0 || crop_top >= in_H) return fail(DTFILL_E_ARG, std::string(who) + ": crop_top must lie in [0, H_in)");
+    return 0;
+}
+
+}  // namespace
+
+int dtfill_run(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float src_thr, float val_thr,
+               float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts,
+               int out_is_device, int* first_bad_frame) {
+    if (first_bad_frame) *first_bad_frame = -1;
+    if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
+    return run_sync(h, in, in_is_device, false, H, 0, B, H, W, src_thr, val_thr, nullptr, out_depth, out_dt, out_lbl,
+                    out_mask, out_counts, out_is_device, first_bad_frame);
+}
+
+int dtfill_run_u16(dtfill_t* h, const uint16_t* in, int in_is_device, int B, int H_in, int W, int crop_top, float src_thr,
+                   float val_thr, float* out_lidar, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
+                   int32_t* out_counts, int out_is_device, int* first_bad_frame) {
+    if (first_bad_frame) *first_bad_frame = -1;
+    int rc = check_u16_args("dtfill_run_u16", h, in, out_depth, B, H_in, W, crop_top);
+    if (rc) return rc;
+    return run_sync(h, in, in_is_device, true, H_in, crop_top, B, H_in - crop_top, W, src_thr, val_thr, out_lidar, out_depth,
+                    out_dt, out_lbl, out_mask, out_counts, out_is_device, first_bad_frame);
+}
+
+int dtfill_run_u16_async(dtfill_t* h, const uint16_t* in_dev, int B, int H_in, int W, int crop_top, float src_thr,
+                         float val_thr, float* out_lidar_dev, float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev,
+                         uint8_t* out_mask_dev, int32_t* out_counts_dev) {
+    int rc = check_u16_args("dtfill_run_u16_async", h, in_dev, out_depth_dev, B, H_in, W, crop_top);
+    if (rc) return rc;
+    InputScope scope(h, true, H_in, crop_top, out_lidar_dev);
+    return enqueue(h, in_dev, B, H_in - crop_top, W, src_thr, val_thr, out_depth_dev, out_dt_dev, out_lbl_dev, out_mask_dev,
+                   out_counts_dev);
 }
 
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device, int B, int H, int W,

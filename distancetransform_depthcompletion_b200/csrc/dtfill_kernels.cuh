@@ -64,6 +64,7 @@ constexpr int MAX_CELLS = 15360;   // planner grid limit (30 KB of shared memory
 
 struct FrameParams {
     int B, H, W, WW;           // WW = 32-bit words per bit row
+    int in_H, in_crop;         // input frames hold in_H rows; rows [in_crop, in_crop + H) are the frame (uint16 input)
     float src_thr, val_thr;
     float src_cut;             // smallest float x (in the total order) with !(float32(1 - x) > src_thr)
     int init_dist;             // "unreached" distance of the fast path: H + W + 8
@@ -127,6 +128,41 @@ __device__ __forceinline__ float4 ld_stream_v4(const float* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ld_stream_v4u(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// KITTI depth PNG sample -> metres, data_read.py:215 `depth_png.astype(np.float32) / 256.` (exact in float32):
+// 0x47000000 is 32768.0f, whose mantissa step is 2^-8, so OR-ing the sample into the mantissa gives 32768 + v/256.
+__device__ __forceinline__ float u16_depth(uint32_t v16) { return __uint_as_float(0x47000000u | v16) - 32768.0f; }
+__device__ __forceinline__ float load_px(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_px(const uint16_t* p) { return u16_depth(__ldg(p)); }
+__device__ __forceinline__ float load_px_stream(const float* p) { return ld_stream(p); }
+__device__ __forceinline__ float load_px_stream(const uint16_t* p) { return u16_depth(__ldg(p)); }
+
+// 16 consecutive pixels of a row as they arrive from memory (128-bit loads), decoded on use
+template <typename T> struct In16;
+template <> struct In16<float> {
+    float4 q[4];
+    __device__ __forceinline__ void load(const float* p, int col, int W) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) q[g] = col + 4 * g < W ? ld_stream_v4(p + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ float4 get(int g) const { return q[g]; }
+};
+template <> struct In16<uint16_t> {
+    uint4 r[2];
+    __device__ __forceinline__ void load(const uint16_t* p, int col, int W) {     // W % 8 == 0
+#pragma unroll
+        for (int k = 0; k < 2; ++k) r[k] = col + 8 * k < W ? ld_stream_v4u(p + 8 * k) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ __forceinline__ float4 get(int g) const {
+        const uint32_t a = (g & 1) ? r[g >> 1].z : r[g >> 1].x, b = (g & 1) ? r[g >> 1].w : r[g >> 1].y;
+        return make_float4(u16_depth(a & 0xFFFFu), u16_depth(a >> 16), u16_depth(b & 0xFFFFu), u16_depth(b >> 16));
+    }
+};
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -150,8 +186,9 @@ __device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, fl
     return (w * 0x00204081u) >> 28;
 }
 
-__global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict__ in, FrameParams fp, Workspace ws,
-                                                         uint8_t* __restrict__ out_mask)
+template <typename T>
+__global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in, FrameParams fp, Workspace ws,
+                                                         uint8_t* __restrict__ out_mask, float* __restrict__ out_lidar)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -163,23 +200,25 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
     const bool mask16 = (W & 15) == 0;
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
-        const float* rp = in + row * W;
+        const long frame = row / fp.H;
+        const T* rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
         uint32_t cs = 0, cv = 0;
-        // software pipeline over the 512-pixel chunks: the four 128-bit loads of the next chunk are issued (volatile
+        // software pipeline over the 512-pixel chunks: the 128-bit loads of the next chunk are issued (volatile
         // asm, so they stay ahead) before the current chunk is processed
-        float4 nq[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-            nq[g] = lane * 16 + 4 * g < W ? ld_stream_v4(rp + lane * 16 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        In16<T> nq;
+        nq.load(rp + lane * 16, lane * 16, W);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int col = (ch << 9) + lane * 16;
             float4 q[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) q[g] = nq[g];
-            if (ch + 1 < nchunks) {
+            for (int g = 0; g < 4; ++g) q[g] = nq.get(g);
+            if (ch + 1 < nchunks) nq.load(rp + col + 512, col + 512, W);
+            if (out_lidar && col < W) {                  // decoded frame (uint16 input): what the CNN reads as lidar
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                    nq[g] = col + 512 + 4 * g < W ? ld_stream_v4(rp + col + 512 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col + 4 * g < W)
+                        st_stream_v4(out_lidar + row * W + col + 4 * g, __float_as_uint(q[g].x), __float_as_uint(q[g].y),
+                                     __float_as_uint(q[g].z), __float_as_uint(q[g].w));
             }
             uint32_t sb = 0, vb = 0;
 #pragma unroll
@@ -250,12 +289,12 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
                 }
                 // few pixels per lane are valid (~5 % density): walk the set bits and re-read the values (L1 hits)
                 float* dst = rowvals + row * W + cv + (inc - c);
-                const float* xs = rp + col;
+                const T* xs = rp + col;
                 uint32_t m = vb;
                 while (m) {
                     const int j = __ffs(m) - 1;
                     m &= m - 1;
-                    *dst++ = __ldg(xs + j);
+                    *dst++ = load_px(xs + j);
                 }
                 cv += __shfl_sync(0xffffffffu, inc, 31);
             }
@@ -270,8 +309,9 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const float* __restrict_
 // ------------------------------------------------------------------------------------------------------
 // K1 for widths that are not a multiple of 4 (no 128-bit row alignment): same outputs, scalar loads + ballots.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in, FrameParams fp, Workspace ws,
-                                                     uint8_t* __restrict__ out_mask)
+template <typename T>
+__global__ void __launch_bounds__(256) k1_mask_rows(const T* __restrict__ in, FrameParams fp, Workspace ws,
+                                                     uint8_t* __restrict__ out_mask, float* __restrict__ out_lidar)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -282,14 +322,16 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const float* __restrict__ in
     const uint32_t ltmask = lanemask_lt();
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
-        const float* rp = in + row * W;
+        const long frame = row / fp.H;
+        const T* rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
         uint32_t cs = 0, cv = 0;
         for (int c0 = 0; c0 < WW; c0 += 16) {
             float x[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int col = (c0 + k) * 32 + lane;
-                x[k] = col < W ? ld_stream(rp + col) : 0.0f;
+                x[k] = col < W ? load_px_stream(rp + col) : 0.0f;
+                if (out_lidar && col < W) out_lidar[row * W + col] = x[k];
             }
             uint32_t mys = 0, myv = 0, mypre = 0;
             uint32_t vq[4];

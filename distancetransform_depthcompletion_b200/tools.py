@@ -66,3 +66,34 @@ def dt_fill_batch(frames, src_thr: float = KITTI_SRC_THR, val_thr: float = VALID
     if "index_error" in r:
         raise IndexError(r["index_error"])
     return r
+
+
+def DT_complete_batch_png(depth_png_batch, crop_top: int = 96, device: int | None = None):
+    """The reference's loader + crop + fill in one call on the raw PNG samples:
+
+        depth = depth_png.astype(np.float32) / 256.        data_read.py:215
+        lidar = depth[:, crop_top:, :, None]                train.py:211, eval.py:156  (crop_top = 96)
+        refined = DT_complete_batch(lidar)                  tools.py:13-35
+
+    depth_png_batch: uint16 [B, H_in, W] with H_in - crop_top == 352 and W == 1216 (the size tools.py hard-codes).
+    Returns (lidar float32 [B,352,1216,1], refined float32 [B,352,1216,1]); the uint16 -> float32 decode and the
+    crop run inside the first CUDA kernel, so the device reads 2 bytes per pixel."""
+    png = np.asarray(depth_png_batch)
+    if png.dtype != np.uint16:
+        raise TypeError(f"DT_complete_batch_png: expected uint16 PNG samples, got {png.dtype}")
+    if png.ndim != 3:
+        raise IndexError(f"DT_complete_batch_png: expected [B,H_in,W], got shape {png.shape}")
+    B, Hin, W = png.shape
+    H = Hin - int(crop_top)
+    if B == 0:
+        e = np.expand_dims(np.asarray([]), axis=-1).astype(np.float32)
+        return e, e
+    if crop_top < 0 or H <= 0:
+        raise ValueError(f"DT_complete_batch_png: crop_top {crop_top} leaves no rows of {Hin}")
+    if H * W != _H * _W:
+        raise ValueError(f"cannot reshape array of size {H * W} into shape ({_H},{_W})")            # tools.py:25-27
+    r = _lib.get_handle(device).run_host_u16(np.ascontiguousarray(png), crop_top, KITTI_SRC_THR, VALID_THR,
+                                             want_lidar=True)
+    if "index_error" in r:
+        raise IndexError(r["index_error"])                                                          # tools.py:26
+    return r["lidar"].reshape(B, H, W, 1), r["depth"].reshape(B, _H, _W, 1)

@@ -91,6 +91,23 @@ int dtfill_run_async(dtfill_t* h, const float* in_dev, int B, int H, int W, floa
                      float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev, uint8_t* out_mask_dev,
                      int32_t* out_counts_dev);
 
+/* The same path fed with the frames as the KITTI depth PNGs hold them: uint16 samples,
+ * depth = sample / 256 (data_read.py:215 `depth_png.astype(np.float32) / 256.`, exact in float32), laid out
+ * [B, H_in, W]; rows [crop_top, H_in) of every frame are the frame that is processed (train.py:211, eval.py:156
+ * `lidar[:, 96:, :, :]`), so H = H_in - crop_top in every output.  The decode and the crop happen inside the first
+ * kernel: the input costs 2 bytes per pixel of HBM traffic instead of 4, and no float32 copy of the input exists
+ * unless out_lidar (nullable, float32 [B,H,W]: the decoded, cropped frames the reference hands to its CNN next to
+ * the filled depth) asks for it.  All other arguments, outputs and errors as dtfill_run / dtfill_run_async. */
+int dtfill_run_u16(dtfill_t* h, const uint16_t* in, int in_is_device, int B, int H_in, int W, int crop_top,
+                   float src_thr, float val_thr,
+                   float* out_lidar, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
+                   int32_t* out_counts, int out_is_device, int* first_bad_frame);
+
+int dtfill_run_u16_async(dtfill_t* h, const uint16_t* in_dev, int B, int H_in, int W, int crop_top,
+                         float src_thr, float val_thr,
+                         float* out_lidar_dev, float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev,
+                         uint8_t* out_mask_dev, int32_t* out_counts_dev);
+
 /* Synchronise and report the outcome of the last dtfill_run_async: DTFILL_OK or DTFILL_E_INDEX
  * (with *first_bad_frame set).  *kernel_launches receives the number of kernels launched by that call. */
 int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);

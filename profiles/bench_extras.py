@@ -37,3 +37,32 @@ fill = eng.fill(x)
 gt = torch.from_numpy(np.stack([synth.kitti_gt(i % 16) for i in range(B)])).cuda()
 t = timed(lambda: eng.metrics(fill["depth"], gt))
 print("metrics (Result.evaluate, f64 gt): %.3f ms / 256 frames (%.0f GB/s of 12 B/px)" % (t, 12 * npx / t / 1e6))
+
+# ---- f-3: uint16 PNG samples in (decode + 96-row crop inside K1), pipelined like bench.py's headline -----------
+Hin = H + 96
+png = torch.zeros((B, Hin, W), dtype=torch.int32)
+png[:, 96:] = torch.round(x.cpu() * 256).to(torch.int32)
+png = png.to(torch.uint16).cuda() if hasattr(torch, "uint16") else None
+sets = [dict(lidar=torch.empty((B, H, W), device="cuda"), depth=torch.empty((B, H, W), device="cuda"),
+             dt=torch.empty((B, H, W), device="cuda"), mask=torch.empty((B, H, W), dtype=torch.uint8, device="cuda"))
+        for _ in range(3)]
+if png is not None:
+    h.set_pipeline_depth(3)
+    for want_lidar in (0, 1):
+        it = [0]
+        def step():
+            o = sets[it[0] % 3]; it[0] += 1
+            h.run_device_u16_async(png.data_ptr(), B, Hin, W, 96, 0.1, 0.1, o["depth"].data_ptr(),
+                                   o["lidar"].data_ptr() if want_lidar else None, o["dt"].data_ptr(), None,
+                                   o["mask"].data_ptr(), None)
+        for _ in range(6): step()
+        h.flush(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(24): step()
+        h.flush(); e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 24
+        bpp = 2 + 4 + 4 + 1 + 4 * want_lidar
+        print("uint16 input%s, pipelined: %.4f ms / 256 frames (%.0f frames/s, %.0f GB/s of %d B/px)"
+              % (" + decoded lidar out" if want_lidar else "", t, B / t * 1e3, bpp * npx / t / 1e6, bpp))
+    h.set_pipeline_depth(1)

@@ -428,3 +428,47 @@ def test_device_resident_engine_matches_host_path(handle):
     per_frame, sums = eng.metrics(out["depth"], gt)
     want = [O.result_kitti(o["depth"][i], gt[i].cpu().numpy())["rmse"] for i in range(4)]
     np.testing.assert_allclose(per_frame[:, 1].cpu().numpy(), want, rtol=METRIC_RTOL_F64)
+
+
+@pytest.mark.parametrize("W,crop", [(1216, 96), (640, 0), (648, 5), (100, 3), (37, 1)])
+def test_uint16_png_input_decode_and_crop(handle, W, crop):
+    """uint16 PNG samples in, decode (/256, data_read.py:215) + top crop (train.py:211) inside K1.
+    Must equal the float path fed with the reference's own decode, bit for bit, in every output."""
+    rng = np.random.default_rng(W + crop)
+    Hin = 70 + crop
+    B = 5
+    png = ((rng.random((B, Hin, W)) < 0.06) * rng.integers(1, 65536, (B, Hin, W))).astype(np.uint16)
+    png[:, crop + 10, W // 2] = 65535                    # largest sample
+    png[0, crop + 11, 0] = 25                            # 0.0977: neither valid nor source
+    png[0, crop + 12, 1] = 26                            # 0.1016: valid (> 0.1) but not a source
+    png[1, crop + 13, 2] = 230                           # 0.8984: valid, not a source
+    png[1, crop + 13, 3] = 231                           # 0.9023: source
+    png[:, :crop] = 40000                                # the cropped rows must not leak into the result
+    lidar = (png.astype(np.float32) / np.float32(256.0))[:, crop:]          # the reference's decode + crop
+    lidar = np.ascontiguousarray(lidar)
+    ref = handle.run_host(lidar, 0.1, 0.1, want_dt=True, want_lbl=True, want_mask=True)
+    o = O.dt_fill(lidar, 0.1, 0.1)
+    r = handle.run_host_u16(png, crop, 0.1, 0.1, want_lidar=True, want_dt=True, want_lbl=True, want_mask=True)
+    assert "index_error" not in r and "index_error" not in ref
+    assert np.array_equal(r["lidar"].view(np.uint32), lidar.view(np.uint32))
+    for k in ("depth", "dt", "lbl", "mask", "counts"):
+        assert np.array_equal(r[k], ref[k]), k
+    assert np.array_equal(r["lbl"], o["lbl"]) and np.array_equal(r["depth"].view(np.uint32), o["depth"].view(np.uint32))
+    r2 = handle.run_host_u16(png, crop, 0.1, 0.1)        # without the optional outputs
+    assert np.array_equal(r2["depth"], r["depth"]) and r2["lidar"] is None
+
+
+def test_uint16_png_drop_in_and_errors(handle):
+    png = np.zeros((2, 448, 1216), np.uint16)
+    x = synth.kitti_batch([40, 41])[..., 0]
+    png[:, 96:] = np.round(x * 256).astype(np.uint16)
+    lidar, refined = tools.DT_complete_batch_png(png)
+    assert lidar.shape == refined.shape == (2, 352, 1216, 1) and refined.dtype == np.float32
+    want = O.cv2_port_complete_batch(lidar)
+    assert np.array_equal(refined.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(ValueError):
+        tools.DT_complete_batch_png(png, crop_top=95)
+    with pytest.raises(TypeError):
+        tools.DT_complete_batch_png(png.astype(np.int32))
+    with pytest.raises(IndexError):
+        tools.DT_complete_batch_png(np.zeros((1, 448, 1216), np.uint16))     # no valid pixel (tools.py:26)
