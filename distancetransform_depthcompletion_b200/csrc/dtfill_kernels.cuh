@@ -1213,6 +1213,48 @@ __global__ void __launch_bounds__(256) k3_sky(FrameParams fp, Workspace ws, floa
     }
     __syncthreads();
     const int yend = min(y0 + SKY_ROWS, S);
+    if ((W & 3) == 0) {
+        // a thread keeps the tables of 4 consecutive columns in registers and walks 8 rows: per pixel a compare, two
+        // selects, one shared-memory load and one subtraction; 128-bit streaming stores
+        const int ngroups = W >> 2;
+        const float* depflat = &dep[0][0];
+        for (int u = tid; u < ngroups * (SKY_ROWS / 8); u += 256) {
+            const int part = u / ngroups, x = (u - part * ngroups) * 4;
+            int tt[4], sd[4], ts[4];
+            float gf[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                tt[e] = steps[x + e];
+                sd[e] = dir[x + e];
+                ts[e] = x + e + tt[e] * sd[e];                    // valley column, in base row S
+                gf[e] = (float)((int)d0[x + e + 1] + S);
+            }
+            const int ya = y0 + part * 8, yb = min(ya + 8, yend);
+            for (int y = ya; y < yb; ++y) {
+                const int j = (S - y + 1) >> 1, oddoff = ((S - y) & 1) * SKY_MAX_W;
+                const float fy = (float)y;
+                const long ro = fpx + (long)y * W + x;
+                int idx[4];
+                uint32_t od[4], ot[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    idx[e] = tt[e] < j ? ts[e] : x + e + sd[e] * j + oddoff;
+                    od[e] = __float_as_uint(depflat[idx[e]]);
+                    ot[e] = __float_as_uint(gf[e] - fy);          // integers below 2^24: exact
+                }
+                st_stream_v4(out_depth + ro, od[0], od[1], od[2], od[3]);
+                if (out_dt) st_stream_v4(out_dt + ro, ot[0], ot[1], ot[2], ot[3]);
+                if (out_lbl) {
+                    uint32_t ol[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        ol[e] = sk[idx[e] >= SKY_MAX_W ? W + idx[e] - SKY_MAX_W : idx[e]] & LMASK;
+                    st_stream_v4(out_lbl + ro, ol[0], ol[1], ol[2], ol[3]);
+                }
+            }
+        }
+        return;
+    }
     for (int y = y0; y < yend; ++y) {
         const int j = (S - y + 1) >> 1, odd = (S - y) & 1;
         const long ro = fpx + (long)y * W;

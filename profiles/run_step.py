@@ -1,6 +1,6 @@
 """Minimal driver used for the ncu captures: W warm-up steps + K steps of the device-resident hot path
 (batch of 256 synthetic KITTI frames), nothing else.  Same kernels, arguments and batch as bench.py's timed
-region.   python profiles/run_step.py [--steps K] [--warmup W] [--batch B] [--band-cap C]"""
+region.   python profiles/run_step.py [--steps K] [--warmup W] [--batch B] [--band-cap C] [--pipeline D]"""
 import argparse
 import os
 import sys
@@ -17,14 +17,16 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--band-cap", type=int, default=None)
+ap.add_argument("--pipeline", type=int, default=1, help="batches in flight (3 = bench.py's headline mode, k3_sky on)")
 a = ap.parse_args()
 x = torch.from_numpy(bench.make_frames(a.batch, 0)).cuda()
-eng = DTFillEngine(0)
+eng = DTFillEngine(0, pipeline_depth=a.pipeline)
 if a.band_cap is not None:
     eng.handle.set_band_cap(a.band_cap)
-out = None
-for _ in range(a.warmup + a.steps):
-    out = eng.fill(x, out=out)
+outs = [None] * max(1, a.pipeline)
+for i in range(a.warmup + a.steps):
+    out = outs[i % len(outs)] = eng.fill(x, out=outs[i % len(outs)])
+eng.flush()
 bad, launches = eng.status()
 torch.cuda.synchronize()
 print("ok", bad, launches, float(out["depth"].sum()))
