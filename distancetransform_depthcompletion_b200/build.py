@@ -10,7 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libdtfill.so")
 SOURCES = ["dtfill.cu"]
-HEADERS = ["dtfill_kernels.cuh", os.path.join(INCLUDE, "dtfill.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join(INCLUDE, "dtfill.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,177 @@
+// dtfill_k5_pool.cuh -- K5: DT pooling of the CNN input stage (net.py:71-123)
+#pragma once
+#include "dtfill_common.cuh"
+
+namespace dtfill {
+
+// ------------------------------------------------------------------------------------------------------
+// K5: one level of the CNN input stage's "DT pooling" (net.py:83-123 generate_multi_channel).
+// For every pixel: among the pixels of its T x T window (zero padded) whose mask is set, those with the largest
+// weight T - |dy| - |dx| (net.py:71-81), i.e. the city-block-nearest ones, are averaged:
+// out = sum(data[sel]) / (1e-6 + |sel|)  (net.py:93).  With no masked pixel in the window all T*T positions tie at
+// weight 0 and the result is sum(window) / (1e-6 + T*T).  mask == nullptr means mask = data > 0.001 (net.py:95).
+// One thread per pixel, 32 x 8 tile + halo in shared memory, rings of growing city-block distance.
+// ------------------------------------------------------------------------------------------------------
+constexpr int K5_TW = 32, K5_TH = 8, K5_MAXR = 7;      // table_size <= 15
+
+__global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict__ data, const float* __restrict__ mask,
+                                                         int H, int W, int T, float* __restrict__ out)
+{
+    __shared__ float sd[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
+    __shared__ unsigned long long smk[K5_TH + 2 * K5_MAXR];      // one mask bit per tile column (<= 46 columns)
+    const int R = T / 2;
+    const long fpx = (long)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * K5_TW, y0 = blockIdx.y * K5_TH;
+    const int tw = K5_TW + 2 * R, th = K5_TH + 2 * R;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // tile + halo: one warp per tile row, two ballots build the row's mask word
+    for (int ly = wid; ly < th; ly += 8) {
+        const int gy = y0 + ly - R;
+        unsigned long long word = 0;
+        for (int l0 = 0; l0 < tw; l0 += 32) {
+            const int lx = l0 + lane;
+            const int gx = x0 + lx - R;
+            float v = 0.f;
+            bool m = false;
+            if (lx < tw && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = data[fpx + (long)gy * W + gx];
+                m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);   // mask * weight > 0 <=> mask != 0
+            }
+            if (lx < tw) sd[ly][lx] = v;
+            word |= (unsigned long long)__ballot_sync(0xffffffffu, m) << l0;
+        }
+        if (lane == 0) smk[ly] = word;
+    }
+    __syncthreads();
+    const int tx = lane, ty = wid;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+    const int cx = tx + R, cy = ty + R;
+    const uint32_t fieldmask = (1u << T) - 1u, lowmask = (1u << R) - 1u;
+    int best = 1 << 20;                  // smallest city-block distance to a masked pixel of the window
+    float sum = 0.f, cnt = 0.f;
+    for (int dy = -R; dy <= R; ++dy) {
+        // the T mask bits of this window row, centre at bit R
+        const uint32_t f = (uint32_t)(smk[cy + dy] >> tx) & fieldmask;
+        if (!f) continue;
+        const int ady = dy < 0 ? -dy : dy;
+        int dxr = 1 << 20, dxl = 1 << 20;
+        if ((f >> R) & 1u) dxr = dxl = 0;
+        else {
+            const uint32_t right = f >> (R + 1), left = f & lowmask;
+            if (right) dxr = __ffs(right);
+            if (left) dxl = R - (31 - __clz(left));
+        }
+        const int dx = min(dxr, dxl), d = ady + dx;
+        if (d > best) continue;
+        if (d < best) { best = d; sum = 0.f; cnt = 0.f; }
+        if (dx == 0) { sum += sd[cy + dy][cx]; cnt += 1.f; }
+        else {
+            if (dxl == dx) { sum += sd[cy + dy][cx - dx]; cnt += 1.f; }
+            if (dxr == dx) { sum += sd[cy + dy][cx + dx]; cnt += 1.f; }
+        }
+    }
+    if (cnt == 0.f) {                    // nothing masked: every window position ties at weight 0
+        for (int dy = -R; dy <= R; ++dy)
+            for (int dx = -R; dx <= R; ++dx) sum += sd[cy + dy][cx + dx];
+        cnt = (float)(T * T);
+    }
+    out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5t: the same level for window sizes 3, 5, 7, 9 (R = 1..4), restructured so that the work per pixel is a few
+// dozen instructions: a 64 x 32 tile (+ halo) in shared memory; phase 1 computes, once per tile row and output
+// column, the row's nearest masked offset, the sum of the data there (left and right when they tie) and its
+// count; phase 2 lets a thread walk 8 output rows of one column with those row records in registers: the window
+// minimum of |dy| + dx, then the records at that distance.  Windows without any masked pixel sum all T*T values
+// (net.py:91-93: every weight ties at 0); a bit per row record says whether that sum can be anything but +0.
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) k5_dt_pool_tile(const float* __restrict__ data, const float* __restrict__ mask,
+                                                        int H, int W, float* __restrict__ out)
+{
+    constexpr int T = 2 * R + 1, TW = 64, TH = 32, SW = TW + 2 * R, SH = TH + 2 * R, NONE = 15, SR = 8;
+    constexpr uint32_t FM = (1u << T) - 1u, LOW = (1u << R) - 1u;
+    __shared__ float sd[SH][SW + 1];             // data, zero outside the frame
+    __shared__ uint32_t smk[SH][4];              // mask bits of a tile row (SW <= 96) + a spare word
+    __shared__ uint32_t snz[SH][4];              // bit = the value is not +0.0f
+    __shared__ float rs[SH][TW];                 // row record: sum of the nearest masked values of the row
+    __shared__ uint8_t ri[SH][TW];               // row record: dx (0..R, NONE) | count << 4 | "row part not all +0" << 7
+    const long fpx = (long)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int ly = wid; ly < SH; ly += 8) {
+        const int gy = y0 + ly - R;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int lx = c * 32 + lane, gx = x0 + lx - R;
+            float v = 0.f;
+            bool m = false;
+            if (lx < SW && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = data[fpx + (long)gy * W + gx];
+                m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);      // mask * weight > 0 <=> mask != 0
+            }
+            if (lx < SW) sd[ly][lx] = v;
+            const uint32_t bm = __ballot_sync(0xffffffffu, m);
+            const uint32_t bn = __ballot_sync(0xffffffffu, __float_as_uint(v) != 0u);
+            if (lane == 0) { smk[ly][c] = bm; snz[ly][c] = bn; }
+        }
+        if (lane == 0) { smk[ly][3] = 0u; snz[ly][3] = 0u; }
+    }
+    __syncthreads();
+    // phase 1: row records
+    for (int i = tid; i < SH * TW; i += 256) {
+        const int ly = i >> 6, tx = i & 63, w = tx >> 5, sh = tx & 31;
+        const uint32_t f = __funnelshift_r(smk[ly][w], smk[ly][w + 1], sh) & FM;        // window columns, centre = bit R
+        const uint32_t nzf = __funnelshift_r(snz[ly][w], snz[ly][w + 1], sh) & FM;
+        const uint32_t right = f >> (R + 1), left = f & LOW;
+        const int dxr = right ? __ffs(right) : NONE;
+        const int dxl = left ? R - (31 - __clz(left)) : NONE;
+        const bool centre = (f >> R) & 1u;
+        const int dx = centre ? 0 : min(dxl, dxr);
+        const int a = dx == NONE ? 0 : dx;
+        const bool tl = !centre && dxl == dx && dx != NONE, tr = !centre && dxr == dx && dx != NONE;
+        const float vl = sd[ly][tx + R - a], vr = sd[ly][tx + R + a];
+        rs[ly][tx] = centre ? vl : ((tl ? vl : 0.f) + (tr ? vr : 0.f));
+        ri[ly][tx] = (uint8_t)(dx | ((centre ? 1 : (int)tl + (int)tr) << 4) | (nzf ? 0x80 : 0));
+    }
+    __syncthreads();
+    // phase 2: a thread owns column tx of SR consecutive output rows
+    const int tx = tid & 63, ty0 = (tid >> 6) * SR;
+    const int gx = x0 + tx;
+    if (gx >= W) return;
+    uint32_t e[SR + 2 * R];
+    float v[SR + 2 * R];
+#pragma unroll
+    for (int k = 0; k < SR + 2 * R; ++k) { e[k] = ri[ty0 + k][tx]; v[k] = rs[ty0 + k][tx]; }
+#pragma unroll
+    for (int j = 0; j < SR; ++j) {
+        const int gy = y0 + ty0 + j;
+        if (gy >= H) break;
+        int best = 2 * NONE;
+        uint32_t anynz = 0;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            best = min(best, (k < R ? R - k : k - R) + (int)(e[j + k] & 15u));
+            anynz |= e[j + k];
+        }
+        float sum = 0.f, cnt = 0.f;
+        if (best < NONE) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const bool sel = (k < R ? R - k : k - R) + (int)(e[j + k] & 15u) == best;
+                sum += sel ? v[j + k] : 0.f;
+                cnt += sel ? (float)((e[j + k] >> 4) & 3u) : 0.f;
+            }
+        } else {                             // nothing masked: every window position ties at weight 0
+            if (anynz & 0x80u)
+                for (int dy = 0; dy < T; ++dy)
+                    for (int dx = 0; dx < T; ++dx) sum += sd[ty0 + j + dy][tx + dx];
+            cnt = (float)(T * T);
+        }
+        out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
+    }
+}
+
+}  // namespace dtfill

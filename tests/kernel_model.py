@@ -1,4 +1,4 @@
-"""numpy model of the arithmetic the sm_100a chamfer kernel performs (csrc/dtfill_kernels.cu) -- TEST CODE.
+"""numpy model of the arithmetic the sm_100a chamfer kernel performs (csrc/dtfill_k2_chamfer.cuh) -- TEST CODE.
 
 It mirrors, lane for lane, what one warp does for one task (a band of rows of one frame): packed 32-bit
 keys ``dist:11 | order:4 | label:17``, the 7-candidate stencil as unsigned minima, the in-lane sequential
@@ -148,7 +148,7 @@ def coarse_row_bound(src: np.ndarray, ch: int, cw: int) -> np.ndarray:
 def sky_rows_closed_form(dt: np.ndarray, lbl: np.ndarray, S: int):
     """Rows [0,S) of (dt, lbl) from rows S and S+1 alone, for a frame whose first source row f satisfies S+1 <= f:
     dt(y,x) = dt(S,x) + (S-y); the label follows t(x) diagonal steps down the distance profile of row S towards
-    its valley column, then straight down (see the header of k3_sky in csrc/dtfill_kernels.cuh)."""
+    its valley column, then straight down (see csrc/dtfill_k3_sky.cuh)."""
     H, W = dt.shape
     g = dt[S].astype(np.int64)
     INF = np.int64(1) << 40
