@@ -248,16 +248,20 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
 
     if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
     {   // K1: one warp per row
-        long want = ((long)rows + 7) / 8;
+        // small blocks (2 warps, no shared memory): they fit into the registers the scan's warps of other batches
+        // leave free on an SM, so K1 starts flowing before those drain (measured: 256 -> 64 threads, step -2 %)
+        const int k1_threads = 64;
+        const int wpb = k1_threads / 32;
+        long want = ((long)rows + wpb - 1) / wpb;
         int grid = (int)(want < 1 ? 1 : want);
         if (!h->in_u16) {
             const float* in_s = (const float*)in + npx0;
-            if ((W & 3) == 0) k1_mask_rows_v16<float><<<grid, 256, 0, s>>>(in_s, fp, ws, om, nullptr);
-            else k1_mask_rows<float><<<grid, 256, 0, s>>>(in_s, fp, ws, om, nullptr);
+            if ((W & 3) == 0) k1_mask_rows_v16<float><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
+            else k1_mask_rows<float><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
         } else {
             const uint16_t* in_s = (const uint16_t*)in + (size_t)b0 * h->in_H * W;
-            if ((W & 7) == 0) k1_mask_rows_v16<uint16_t><<<grid, 256, 0, s>>>(in_s, fp, ws, om, olid);
-            else k1_mask_rows<uint16_t><<<grid, 256, 0, s>>>(in_s, fp, ws, om, olid);
+            if ((W & 7) == 0) k1_mask_rows_v16<uint16_t><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
+            else k1_mask_rows<uint16_t><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
         }
         ++*launches;
     }
