@@ -861,8 +861,12 @@ int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B
         if ((rc = ensure(h, h->depth_dev, npx * 4))) return rc;
         o_d = (float*)h->depth_dev.p;
     }
-    dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
-    k6_outlier_removal<<<grid, 256, 0, s>>>(i_d, H, W, o_d);
+    if (i_d == o_d) return fail(DTFILL_E_ARG, "dtfill_outlier_removal: out must not alias in (neighbours are read)");
+    const bool vec = (W & 3) == 0 && ((uintptr_t)i_d & 15) == 0 && ((uintptr_t)o_d & 15) == 0;
+    const long ngroups = vec ? (long)(npx / 4) : (long)npx;
+    const unsigned grid = (unsigned)((ngroups + 255) / 256);
+    if (vec) k6_outlier_removal<true><<<grid, 256, 0, s>>>(i_d, H, W, ngroups, o_d);
+    else k6_outlier_removal<false><<<grid, 256, 0, s>>>(i_d, H, W, ngroups, o_d);
     CU(cudaGetLastError());
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out, o_d, npx * 4, cudaMemcpyDeviceToHost, s));

@@ -18,7 +18,11 @@ def _frames():
     ys, xs = np.nonzero(x > 0)
     pick = rng.choice(len(ys), 200, replace=False)
     x[ys[pick], xs[pick]] += np.float32(30.0)
-    return [x, synth.kitti_frame(3, beam_step=4), x[:9, :13].copy(), x[200:203, :].copy(), x[:, 600:602].copy()]
+    dense = (np.round(rng.uniform(1, 80, (40, 64)) * 256) / 256).astype(np.float32)      # every pixel is evaluated
+    signed = x[150:200, 300:420].copy()
+    signed[::7, ::5] = np.float32(-5.0)                                                   # negative neighbours
+    return [x, synth.kitti_frame(3, beam_step=4), x[:9, :13].copy(), x[200:203, :].copy(), x[:, 600:602].copy(),
+            dense, signed, x[:, 1:1216].copy()]
 
 
 @pytest.mark.skipif(not (os.path.isdir(REF) and O.have_cv2()), reason="reference checkout or cv2 absent")
