@@ -822,14 +822,15 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
     }
     dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
     dim3 tgrid((W + 63) / 64, (H + 31) / 32, B);          // k5_dt_pool_tile: 64 x 32 outputs per block
+    dim3 wgrid((W + 63) / 64, (H + 63) / 64, B);          // k5_dt_pool_win: 64 x 64 outputs per block
     for (int l = 0; l < nl; ++l) {
         const float* src = l == 0 ? d_d : o_d + (size_t)(l - 1) * npx;
         const float* msk = l == 0 ? m_d : nullptr;
         float* dst = o_d + (size_t)l * npx;
         switch (table_size) {
-            case 3: k5_dt_pool_tile<1><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 5: k5_dt_pool_tile<2><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 7: k5_dt_pool_tile<3><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 3: k5_dt_pool_win<1><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 5: k5_dt_pool_win<2><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 7: k5_dt_pool_win<3><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
             case 9: k5_dt_pool_tile<4><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
             default: k5_dt_pool_level<<<grid, 256, 0, s>>>(src, msk, H, W, table_size, dst); break;
         }

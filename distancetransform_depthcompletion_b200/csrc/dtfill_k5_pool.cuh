@@ -174,4 +174,116 @@ __global__ void __launch_bounds__(256) k5_dt_pool_tile(const float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K5w: the same level for window sizes 3, 5, 7 (R = 1..3), the sizes whose T x T mask window fits one 64-bit word
+// (row k of the window in bits 8k .. 8k+T-1).  A thread owns one column of 16 output rows and slides the window
+// word down (shift by one row, OR the new row's T-bit field in); the city-block rings around the centre are
+// compile-time masks, so "nearest masked pixels" is a 3-step search over the cumulative ring masks plus one AND,
+// their number a population count, and only the selected pixels (1-3 as a rule) are read and added, in row-major
+// order.  Tiles that hold neither a masked pixel nor a value other than +0 are written as zeros straight away.
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+struct PoolRings {
+    uint64_t ring[2 * R + 2], disk[2 * R + 2];
+    constexpr PoolRings() : ring{}, disk{} {
+        constexpr int T = 2 * R + 1;
+        for (int d = 0; d <= 2 * R + 1; ++d) {
+            uint64_t m = 0;
+            for (int k = 0; k < T; ++k)
+                for (int c = 0; c < T; ++c)
+                    if ((k < R ? R - k : k - R) + (c < R ? R - c : c - R) == d) m |= 1ull << (8 * k + c);
+            ring[d] = m;
+            disk[d] = m | (d ? disk[d - 1] : 0ull);
+        }
+    }
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ data, const float* __restrict__ mask,
+                                                       int H, int W, float* __restrict__ out)
+{
+    constexpr int T = 2 * R + 1, TW = 64, TH = 64, SW = TW + 2 * R, SH = TH + 2 * R, SR = TH / 4, PITCH = SW + 1;
+    constexpr uint32_t FM = (1u << T) - 1u;
+    constexpr PoolRings<R> rings{};
+    __shared__ float sd[SH][PITCH];              // data, zero outside the frame
+    __shared__ uint32_t smk[SH][4];              // mask bits of a tile row (SW <= 96) + a spare word
+    __shared__ uint32_t snz[SH][4];              // bit = the value is not +0.0f
+    __shared__ uint32_t sany;
+    const long fpx = (long)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) sany = 0u;
+    __syncthreads();
+    uint32_t any = 0;
+    for (int ly = wid; ly < SH; ly += 8) {
+        const int gy = y0 + ly - R;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int lx = c * 32 + lane, gx = x0 + lx - R;
+            float v = 0.f;
+            bool m = false;
+            if (lx < SW && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = data[fpx + (long)gy * W + gx];
+                m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);      // mask * weight > 0 <=> mask != 0
+            }
+            if (lx < SW) sd[ly][lx] = v;
+            const uint32_t bm = __ballot_sync(0xffffffffu, m);
+            const uint32_t bn = __ballot_sync(0xffffffffu, __float_as_uint(v) != 0u);
+            if (lane == 0) { smk[ly][c] = bm; snz[ly][c] = bn; }
+            any |= bm | bn;
+        }
+        if (lane == 0) { smk[ly][3] = 0u; snz[ly][3] = 0u; }
+    }
+    if (lane == 0 && any) atomicOr(&sany, 1u);
+    __syncthreads();
+    const int tx = tid & 63, ty0 = (tid >> 6) * SR;
+    const int gx = x0 + tx;
+    if (gx >= W) return;
+    float* op = out + fpx + (long)(y0 + ty0) * W + gx;
+    if (!sany) {                                 // nothing masked, every value +0: the sums are +0
+        for (int j = 0; j < SR && y0 + ty0 + j < H; ++j) op[(long)j * W] = 0.f;
+        return;
+    }
+    const int w = tx >> 5, sh = tx & 31;
+    auto field = [&](const uint32_t (*bits)[4], int ly) { return __funnelshift_r(bits[ly][w], bits[ly][w + 1], sh) & FM; };
+    uint64_t win = 0;                            // rows ty0 .. ty0+T-2 in window rows 1 .. T-1: one shift completes it
+#pragma unroll
+    for (int k = 0; k < T - 1; ++k) win |= (uint64_t)field(smk, ty0 + k) << (8 * (k + 1));
+#pragma unroll 1
+    for (int j = 0; j < SR; ++j) {
+        win = (win >> 8) | ((uint64_t)field(smk, ty0 + j + T - 1) << (8 * (T - 1)));
+        if (y0 + ty0 + j >= H) break;
+        const float* sdp = &sd[ty0 + j][tx];
+        float sum = 0.f, cnt;
+        if (win) {
+            int best = 0;                        // smallest d whose disk meets the window
+#pragma unroll
+            for (int st = 4; st; st >>= 1)
+                if (best + st <= 2 * R && !(win & rings.disk[best + st - 1])) best += st;
+            const uint64_t sel = win & rings.ring[best];
+            uint32_t a = (uint32_t)sel, b = (uint32_t)(sel >> 32);
+            cnt = (float)(__popc(a) + __popc(b));
+            while (a) {
+                const int bit = __ffs(a) - 1;
+                a &= a - 1;
+                sum += sdp[(bit >> 3) * PITCH + (bit & 7)];
+            }
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                sum += sdp[((bit >> 3) + 4) * PITCH + (bit & 7)];
+            }
+        } else {                                 // nothing masked: every window position ties at weight 0
+            uint32_t nz = 0;
+#pragma unroll
+            for (int k = 0; k < T; ++k) nz |= field(snz, ty0 + j + k);
+            if (nz)
+                for (int dy = 0; dy < T; ++dy)
+                    for (int dx = 0; dx < T; ++dx) sum += sdp[dy * PITCH + dx];
+            cnt = (float)(T * T);
+        }
+        op[(long)j * W] = sum / (0.000001f + cnt);
+    }
+}
+
 }  // namespace dtfill
