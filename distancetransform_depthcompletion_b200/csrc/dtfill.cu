@@ -827,10 +827,11 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
         const float* src = l == 0 ? d_d : o_d + (size_t)(l - 1) * npx;
         const float* msk = l == 0 ? m_d : nullptr;
         float* dst = o_d + (size_t)l * npx;
+        const bool pvec = (W & 3) == 0 && ((uintptr_t)src & 15) == 0 && (!msk || ((uintptr_t)msk & 15) == 0);
         switch (table_size) {
-            case 3: k5_dt_pool_win<1><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 5: k5_dt_pool_win<2><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 7: k5_dt_pool_win<3><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 3: if (pvec) k5_dt_pool_win<1, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<1, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 5: if (pvec) k5_dt_pool_win<2, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<2, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
+            case 7: if (pvec) k5_dt_pool_win<3, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<3, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
             case 9: k5_dt_pool_tile<4><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
             default: k5_dt_pool_level<<<grid, 256, 0, s>>>(src, msk, H, W, table_size, dst); break;
         }

@@ -198,43 +198,72 @@ struct PoolRings {
     }
 };
 
-template <int R>
+template <int R, bool VEC>
 __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ data, const float* __restrict__ mask,
                                                        int H, int W, float* __restrict__ out)
 {
-    constexpr int T = 2 * R + 1, TW = 64, TH = 64, SW = TW + 2 * R, SH = TH + 2 * R, SR = TH / 4, PITCH = SW + 1;
+    // tile columns start at x0 - 4 (16-byte aligned for 128-bit loads); output column tx reads from column tx + OFF
+    constexpr int T = 2 * R + 1, TW = 64, TH = 64, OFF = 4 - R, SW = 72, SH = TH + 2 * R, SR = TH / 4, PITCH = SW;
     constexpr uint32_t FM = (1u << T) - 1u;
     constexpr PoolRings<R> rings{};
-    __shared__ float sd[SH][PITCH];              // data, zero outside the frame
-    __shared__ uint32_t smk[SH][4];              // mask bits of a tile row (SW <= 96) + a spare word
-    __shared__ uint32_t snz[SH][4];              // bit = the value is not +0.0f
+    __shared__ __align__(16) float sd[SH][PITCH];   // data, zero outside the frame
+    __shared__ uint32_t smk[SH][4];                  // mask bits of a tile row (SW <= 96) + a spare word
+    __shared__ uint32_t snz[SH][4];                  // bit = the value is not +0.0f
     __shared__ uint32_t sany;
     const long fpx = (long)blockIdx.z * H * W;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) sany = 0u;
-    __syncthreads();
     uint32_t any = 0;
-    for (int ly = wid; ly < SH; ly += 8) {
-        const int gy = y0 + ly - R;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int lx = c * 32 + lane, gx = x0 + lx - R;
-            float v = 0.f;
-            bool m = false;
-            if (lx < SW && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                v = data[fpx + (long)gy * W + gx];
-                m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);      // mask * weight > 0 <=> mask != 0
+    if (VEC) {                                   // W % 4 == 0, 16-byte aligned pointers: one float4 per item
+        for (int i = tid; i < SH * 4; i += 256) { (&smk[0][0])[i] = 0u; (&snz[0][0])[i] = 0u; }
+        __syncthreads();
+        for (int i = tid; i < SH * (SW / 4); i += 256) {
+            const int ly = i / (SW / 4), q = i - ly * (SW / 4);
+            const int gy = y0 + ly - R, gx = x0 - 4 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t mb = 0;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const long o = fpx + (long)gy * W + gx;
+                v = *reinterpret_cast<const float4*>(data + o);
+                if (mask) {
+                    const float4 m = *reinterpret_cast<const float4*>(mask + o);
+                    mb = (m.x != 0.f) | ((m.y != 0.f) << 1) | ((m.z != 0.f) << 2) | ((m.w != 0.f) << 3);
+                } else {
+                    mb = (v.x > 0.001f) | ((v.y > 0.001f) << 1) | ((v.z > 0.001f) << 2) | ((v.w > 0.001f) << 3);
+                }
             }
-            if (lx < SW) sd[ly][lx] = v;
-            const uint32_t bm = __ballot_sync(0xffffffffu, m);
-            const uint32_t bn = __ballot_sync(0xffffffffu, __float_as_uint(v) != 0u);
-            if (lane == 0) { smk[ly][c] = bm; snz[ly][c] = bn; }
-            any |= bm | bn;
+            *reinterpret_cast<float4*>(&sd[ly][4 * q]) = v;
+            const uint32_t nb = (__float_as_uint(v.x) != 0u) | ((__float_as_uint(v.y) != 0u) << 1) |
+                                ((__float_as_uint(v.z) != 0u) << 2) | ((__float_as_uint(v.w) != 0u) << 3);
+            if (mb) atomicOr(&smk[ly][q >> 3], mb << ((q & 7) * 4));
+            if (nb) atomicOr(&snz[ly][q >> 3], nb << ((q & 7) * 4));
+            any |= mb | nb;
         }
-        if (lane == 0) { smk[ly][3] = 0u; snz[ly][3] = 0u; }
+        if (any) sany = 1u;                      // benign race: every writer stores the same value
+    } else {
+        __syncthreads();
+        for (int ly = wid; ly < SH; ly += 8) {
+            const int gy = y0 + ly - R;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int lx = c * 32 + lane, gx = x0 - 4 + lx;
+                float v = 0.f;
+                bool m = false;
+                if (lx < SW && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    v = data[fpx + (long)gy * W + gx];
+                    m = mask ? (mask[fpx + (long)gy * W + gx] != 0.f) : (v > 0.001f);  // mask * weight > 0 <=> mask != 0
+                }
+                if (lx < SW) sd[ly][lx] = v;
+                const uint32_t bm = __ballot_sync(0xffffffffu, m);
+                const uint32_t bn = __ballot_sync(0xffffffffu, __float_as_uint(v) != 0u);
+                if (lane == 0) { smk[ly][c] = bm; snz[ly][c] = bn; }
+                any |= bm | bn;
+            }
+            if (lane == 0) { smk[ly][3] = 0u; snz[ly][3] = 0u; }
+        }
+        if (lane == 0 && any) atomicOr(&sany, 1u);
     }
-    if (lane == 0 && any) atomicOr(&sany, 1u);
     __syncthreads();
     const int tx = tid & 63, ty0 = (tid >> 6) * SR;
     const int gx = x0 + tx;
@@ -244,8 +273,8 @@ __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ 
         for (int j = 0; j < SR && y0 + ty0 + j < H; ++j) op[(long)j * W] = 0.f;
         return;
     }
-    const int w = tx >> 5, sh = tx & 31;
-    auto field = [&](const uint32_t (*bits)[4], int ly) { return __funnelshift_r(bits[ly][w], bits[ly][w + 1], sh) & FM; };
+    const int w = (tx + OFF) >> 5, sh = (tx + OFF) & 31;
+    auto field = [&](const uint32_t (*bits)[4], int ly) { return __funnelshift_r(bits[ly][w], bits[ly][(w + 1) & 3], sh) & FM; };
     uint64_t win = 0;                            // rows ty0 .. ty0+T-2 in window rows 1 .. T-1: one shift completes it
 #pragma unroll
     for (int k = 0; k < T - 1; ++k) win |= (uint64_t)field(smk, ty0 + k) << (8 * (k + 1));
@@ -253,7 +282,7 @@ __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ 
     for (int j = 0; j < SR; ++j) {
         win = (win >> 8) | ((uint64_t)field(smk, ty0 + j + T - 1) << (8 * (T - 1)));
         if (y0 + ty0 + j >= H) break;
-        const float* sdp = &sd[ty0 + j][tx];
+        const float* sdp = &sd[ty0 + j][tx + OFF];
         float sum = 0.f, cnt;
         if (win) {
             int best = 0;                        // smallest d whose disk meets the window

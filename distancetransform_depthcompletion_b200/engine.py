@@ -44,6 +44,29 @@ class DTFillEngine:
                                      lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
         return dict(depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
 
+    def fill_png(self, png, crop_top: int = 96, src_thr: float = 0.1, val_thr: float = 0.1, want_lidar: bool = True,
+                 want_lbl: bool = False):
+        """png: uint16 CUDA tensor [B,H_in,W] of KITTI depth PNG samples (depth = sample / 256, data_read.py:215);
+        rows [crop_top, H_in) are processed (train.py:211).  Decode and crop happen inside the first kernel.  Returns
+        the dict of fill() plus ``lidar`` (the decoded float32 frames) when asked for; enqueued only."""
+        torch = self.torch
+        assert png.is_cuda and png.dtype == torch.uint16 and png.is_contiguous() and png.dim() == 3
+        B, Hin, W = png.shape
+        H = Hin - int(crop_top)
+        assert 0 <= crop_top < Hin
+        dev = png.device
+        f32 = lambda: torch.empty((B, H, W), dtype=torch.float32, device=dev)       # noqa: E731
+        lidar = f32() if want_lidar else None
+        depth, dt = f32(), f32()
+        mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        lbl = torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_lbl else None
+        counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        self._bind_stream()
+        self.handle.run_device_u16_async(png.data_ptr(), B, Hin, W, int(crop_top), src_thr, val_thr, depth.data_ptr(),
+                                         lidar.data_ptr() if lidar is not None else None, dt.data_ptr(),
+                                         lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
+        return dict(lidar=lidar, depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
+
     def flush(self):
         """Pipelined mode: torch's current stream waits for every fill still in flight."""
         self._bind_stream()

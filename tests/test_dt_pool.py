@@ -54,6 +54,23 @@ def test_gpu_matches_restatement(scale_num, table_size):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("W", [319, 66, 5])
+def test_gpu_odd_widths(W):
+    """Widths that are not a multiple of 4 take the scalar tile load; tiny frames are all halo."""
+    rng = np.random.default_rng(W)
+    x = np.stack([synth.kitti_frame(7)[100:171, 300:300 + W],
+                  ((rng.random((71, W)) < 0.05) * rng.uniform(1, 80, (71, W))).astype(np.float32)])[..., None]
+    mask = (x > 0.1).astype(np.float32)
+    data = (x / np.float32(90.0) * mask).astype(np.float32)
+    for t in (3, 5, 7, 9, 11):
+        got = net_pool.generate_multi_channel(data, mask, table_size=t, scale_num=3)
+        want = O.generate_multi_channel(data[..., 0], mask[..., 0], t, 3)
+        for k in (1, 2):
+            np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=1e-9)
+            assert np.array_equal(got[k] > 0.001, want[k] > 0.001)
+
+
+@pytest.mark.gpu
 def test_gpu_full_size_and_errors():
     x = synth.kitti_batch([11, 12])
     mask = (x > 0.1).astype(np.float32)

@@ -472,3 +472,24 @@ def test_uint16_png_drop_in_and_errors(handle):
         tools.DT_complete_batch_png(png.astype(np.int32))
     with pytest.raises(IndexError):
         tools.DT_complete_batch_png(np.zeros((1, 448, 1216), np.uint16))     # no valid pixel (tools.py:26)
+
+
+def test_uint16_png_device_resident_pipelined(handle):
+    """The uint16 entry on device tensors with batches in flight (k3_sky active) against the float path."""
+    import torch
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    x = synth.kitti_batch([70, 71, 72])[..., 0]
+    png = np.zeros((3, 448, 1216), np.uint16)
+    png[:, 96:] = np.round(x * 256).astype(np.uint16)
+    want = handle.run_host(np.ascontiguousarray(x), 0.1, 0.1, want_dt=True, want_lbl=True, want_mask=True)
+    eng = DTFillEngine(0, pipeline_depth=3)
+    pd = torch.from_numpy(png.view(np.int16)).cuda().view(torch.uint16)
+    outs = [eng.fill_png(pd, want_lbl=True) for _ in range(4)]
+    eng.flush()
+    bad, _ = eng.status()
+    assert bad == -1
+    for o in outs:
+        assert np.array_equal(o["lidar"].cpu().numpy(), x)
+        for k in ("depth", "dt", "lbl", "mask"):
+            assert np.array_equal(o[k].cpu().numpy(), want[k]), k
+        assert np.array_equal(o["counts"].cpu().numpy(), want["counts"])
