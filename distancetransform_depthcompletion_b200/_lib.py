@@ -64,13 +64,14 @@ def load() -> ctypes.CDLL:
         L.dtfill_debug_get_tasks.restype = ci
         L.dtfill_kernel_times.argtypes = [vp, _c_float_p]
         L.dtfill_dt_pool.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
+        L.dtfill_dt_pool_ex.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.dtfill_outlier_removal.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
                      "dtfill_status", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
-                     "dtfill_flush", "dtfill_dt_pool", "dtfill_outlier_removal",
+                     "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
                      "dtfill_kernel_times"):
             getattr(L, name).restype = ci
         _lib = L
@@ -243,17 +244,20 @@ class Handle:
         return dict(zip(self.KERNEL_NAMES, (float(v) for v in ms)))
 
     def dt_pool(self, data, mask, B: int, H: int, W: int, table_size: int, scale_num: int, on_device: bool = False,
-                out_ptr=None):
-        """DT pooling levels 2..scale_num (net.py:83-123).  Host arrays -> numpy [scale_num-1,B,H,W]."""
+                out_ptr=None, want_masks: bool = False, masks_ptr=None):
+        """DT pooling levels 2..scale_num (net.py:83-123).  Host arrays -> numpy [scale_num-1,B,H,W] (with
+        want_masks: a pair, the second the uint8 level masks ``level > 0.001``)."""
         if scale_num <= 1:
-            return np.empty((0, B, H, W), np.float32)
+            e = np.empty((0, B, H, W), np.float32)
+            return (e, np.empty((0, B, H, W), np.uint8)) if want_masks else e
         if not on_device:
             out = np.empty((scale_num - 1, B, H, W), np.float32)
-            _check(self._L.dtfill_dt_pool(self._h, _ptr(data), _ptr(mask), 0, B, H, W, table_size, scale_num,
-                                          _ptr(out), 0), "dtfill_dt_pool")
-            return out
-        _check(self._L.dtfill_dt_pool(self._h, _ptr(data), _ptr(mask), 1, B, H, W, table_size, scale_num,
-                                      _ptr(out_ptr), 1), "dtfill_dt_pool")
+            masks = np.empty((scale_num - 1, B, H, W), np.uint8) if want_masks else None
+            _check(self._L.dtfill_dt_pool_ex(self._h, _ptr(data), _ptr(mask), 0, B, H, W, table_size, scale_num,
+                                             _ptr(out), _ptr(masks), 0), "dtfill_dt_pool")
+            return (out, masks) if want_masks else out
+        _check(self._L.dtfill_dt_pool_ex(self._h, _ptr(data), _ptr(mask), 1, B, H, W, table_size, scale_num,
+                                         _ptr(out_ptr), _ptr(masks_ptr), 1), "dtfill_dt_pool")
         return None
 
     def outlier_removal(self, frames: np.ndarray) -> np.ndarray:

@@ -793,8 +793,8 @@ int dtfill_kernel_times(dtfill_t* h, float* ms) {
     return 0;
 }
 
-int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
-                   int table_size, int scale_num, float* out, int out_is_device) {
+int dtfill_dt_pool_ex(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
+                      int table_size, int scale_num, float* out, uint8_t* out_masks, int out_is_device) {
     if (!h || !data || !mask) return fail(DTFILL_E_ARG, "dtfill_dt_pool: NULL handle, data or mask");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_dt_pool: B, H, W must be positive");
     if (table_size < 1 || (table_size & 1) == 0 || table_size > 2 * K5_MAXR + 1)
@@ -816,9 +816,11 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
         CU(cudaMemcpyAsync(h->gt_dev.p, mask, npx * 4, cudaMemcpyHostToDevice, s));
         d_d = (const float*)h->in_dev.p; m_d = (const float*)h->gt_dev.p;
     }
+    uint8_t* k_d = out_masks;
     if (!out_is_device) {
         if ((rc = ensure(h, h->depth_dev, npx * 4 * nl))) return rc;
         o_d = (float*)h->depth_dev.p;
+        if (out_masks) { if ((rc = ensure(h, h->mask_dev, npx * nl))) return rc; k_d = (uint8_t*)h->mask_dev.p; }
     }
     dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
     dim3 tgrid((W + 63) / 64, (H + 31) / 32, B);          // k5_dt_pool_tile: 64 x 32 outputs per block
@@ -827,21 +829,28 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
         const float* src = l == 0 ? d_d : o_d + (size_t)(l - 1) * npx;
         const float* msk = l == 0 ? m_d : nullptr;
         float* dst = o_d + (size_t)l * npx;
+        uint8_t* dmk = k_d ? k_d + (size_t)l * npx : nullptr;
         const bool pvec = (W & 3) == 0 && ((uintptr_t)src & 15) == 0 && (!msk || ((uintptr_t)msk & 15) == 0);
         switch (table_size) {
-            case 3: if (pvec) k5_dt_pool_win<1, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<1, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 5: if (pvec) k5_dt_pool_win<2, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<2, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 7: if (pvec) k5_dt_pool_win<3, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); else k5_dt_pool_win<3, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            case 9: k5_dt_pool_tile<4><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst); break;
-            default: k5_dt_pool_level<<<grid, 256, 0, s>>>(src, msk, H, W, table_size, dst); break;
+            case 3: if (pvec) k5_dt_pool_win<1, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); else k5_dt_pool_win<1, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); break;
+            case 5: if (pvec) k5_dt_pool_win<2, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); else k5_dt_pool_win<2, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); break;
+            case 7: if (pvec) k5_dt_pool_win<3, true><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); else k5_dt_pool_win<3, false><<<wgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); break;
+            case 9: k5_dt_pool_tile<4><<<tgrid, 256, 0, s>>>(src, msk, H, W, dst, dmk); break;
+            default: k5_dt_pool_level<<<grid, 256, 0, s>>>(src, msk, H, W, table_size, dst, dmk); break;
         }
     }
     CU(cudaGetLastError());
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out, o_d, npx * 4 * nl, cudaMemcpyDeviceToHost, s));
+        if (out_masks) CU(cudaMemcpyAsync(out_masks, k_d, npx * nl, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
     return 0;
+}
+
+int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
+                   int table_size, int scale_num, float* out, int out_is_device) {
+    return dtfill_dt_pool_ex(h, data, mask, in_is_device, B, H, W, table_size, scale_num, out, nullptr, out_is_device);
 }
 
 int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float* out,

@@ -15,7 +15,7 @@ namespace dtfill {
 constexpr int K5_TW = 32, K5_TH = 8, K5_MAXR = 7;      // table_size <= 15
 
 __global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict__ data, const float* __restrict__ mask,
-                                                         int H, int W, int T, float* __restrict__ out)
+                                                         int H, int W, int T, float* __restrict__ out, uint8_t* __restrict__ out_mask)
 {
     __shared__ float sd[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
     __shared__ unsigned long long smk[K5_TH + 2 * K5_MAXR];      // one mask bit per tile column (<= 46 columns)
@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict_
             for (int dx = -R; dx <= R; ++dx) sum += sd[cy + dy][cx + dx];
         cnt = (float)(T * T);
     }
-    out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
+    const float res = sum / (0.000001f + cnt);
+        out[fpx + (long)gy * W + gx] = res;
+        if (out_mask) out_mask[fpx + (long)gy * W + gx] = res > 0.001f;          // net.py:95 mask of the next level
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) k5_dt_pool_level(const float* __restrict_
 // ------------------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(256) k5_dt_pool_tile(const float* __restrict__ data, const float* __restrict__ mask,
-                                                        int H, int W, float* __restrict__ out)
+                                                        int H, int W, float* __restrict__ out, uint8_t* __restrict__ out_mask)
 {
     constexpr int T = 2 * R + 1, TW = 64, TH = 32, SW = TW + 2 * R, SH = TH + 2 * R, NONE = 15, SR = 8;
     constexpr uint32_t FM = (1u << T) - 1u, LOW = (1u << R) - 1u;
@@ -170,7 +172,9 @@ __global__ void __launch_bounds__(256) k5_dt_pool_tile(const float* __restrict__
                     for (int dx = 0; dx < T; ++dx) sum += sd[ty0 + j + dy][tx + dx];
             cnt = (float)(T * T);
         }
-        out[fpx + (long)gy * W + gx] = sum / (0.000001f + cnt);
+        const float res = sum / (0.000001f + cnt);
+        out[fpx + (long)gy * W + gx] = res;
+        if (out_mask) out_mask[fpx + (long)gy * W + gx] = res > 0.001f;          // net.py:95 mask of the next level
     }
 }
 
@@ -200,7 +204,7 @@ struct PoolRings {
 
 template <int R, bool VEC>
 __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ data, const float* __restrict__ mask,
-                                                       int H, int W, float* __restrict__ out)
+                                                       int H, int W, float* __restrict__ out, uint8_t* __restrict__ out_mask)
 {
     // tile columns start at x0 - 4 (16-byte aligned for 128-bit loads); output column tx reads from column tx + OFF
     constexpr int T = 2 * R + 1, TW = 64, TH = 64, OFF = 4 - R, SW = 72, SH = TH + 2 * R, SR = TH / 4, PITCH = SW;
@@ -270,7 +274,10 @@ __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ 
     if (gx >= W) return;
     float* op = out + fpx + (long)(y0 + ty0) * W + gx;
     if (!sany) {                                 // nothing masked, every value +0: the sums are +0
-        for (int j = 0; j < SR && y0 + ty0 + j < H; ++j) op[(long)j * W] = 0.f;
+        for (int j = 0; j < SR && y0 + ty0 + j < H; ++j) {
+            op[(long)j * W] = 0.f;
+            if (out_mask) out_mask[(op - out) + (long)j * W] = 0;
+        }
         return;
     }
     const int w = (tx + OFF) >> 5, sh = (tx + OFF) & 31;
@@ -311,7 +318,9 @@ __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ 
                     for (int dx = 0; dx < T; ++dx) sum += sdp[dy * PITCH + dx];
             cnt = (float)(T * T);
         }
-        op[(long)j * W] = sum / (0.000001f + cnt);
+        const float res = sum / (0.000001f + cnt);
+        op[(long)j * W] = res;
+        if (out_mask) out_mask[(op - out) + (long)j * W] = res > 0.001f;          // net.py:95 mask of the next level
     }
 }
 

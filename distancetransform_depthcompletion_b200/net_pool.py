@@ -4,7 +4,7 @@
     generate_multi_channel(lidar_data, lidar_mask, ...)        net.py:83-123
 
 numpy in, numpy out (the reference runs these lines as TF ops inside the model).  The window
-search and averaging run on the GPU (kernel k5_dt_pool_level behind dtfill_dt_pool).
+search and averaging run on the GPU (kernels k5_dt_pool_* behind dtfill_dt_pool / dtfill_dt_pool_ex).
 """
 from __future__ import annotations
 
@@ -44,3 +44,31 @@ def generate_multi_channel(lidar_data, lidar_mask, table_size: int = 7, scale_nu
     outs = [d] + [levels[k] for k in range(scale_num - 1)]
     outs += [None] * (4 - len(outs))
     return tuple(outs)
+
+
+def dt_pooling_masks(lidar_data, lidar_mask, table_size: int = 7, scale_num: int = 4, device: int | None = None):
+    """The masks generate_multi_channel pools with, as uint8: level 1 is ``lidar_mask != 0``
+    (net.py:131-132 valued_mask), level k >= 2 is ``lidar_k > 0.001`` (net.py:95-96, :105-106, :115-116), written by
+    the same kernels that produce lidar_k.  Returns (levels, masks): the tuple of generate_multi_channel and a
+    tuple of uint8 [B,H,W] arrays (None beyond scale_num)."""
+    d = np.asarray(lidar_data)
+    m = np.asarray(lidar_mask)
+    if d.dtype != np.float32 or m.dtype != np.float32:
+        raise TypeError("dt_pooling_masks: float32 arrays expected")
+    if d.shape != m.shape:
+        raise ValueError(f"dt_pooling_masks: data {d.shape} and mask {m.shape} differ")
+    d3 = d[..., 0] if d.ndim == 4 else d
+    m3 = m[..., 0] if m.ndim == 4 else m
+    if d3.ndim != 3:
+        raise ValueError("dt_pooling_masks: expected [B,H,W,1] or [B,H,W]")
+    assert (table_size + 1) % 2 == 0                                         # net.py:72
+    if not 1 <= scale_num <= 4:
+        raise ValueError("scale_num must be 1..4")
+    B, H, W = d3.shape
+    levels, masks = _lib.get_handle(device).dt_pool(np.ascontiguousarray(d3), np.ascontiguousarray(m3), B, H, W,
+                                                    table_size, scale_num, want_masks=True)
+    outs = [d] + [levels[k] for k in range(scale_num - 1)]
+    mks = [(m3 != 0).astype(np.uint8)] + [masks[k] for k in range(scale_num - 1)]
+    outs += [None] * (4 - len(outs))
+    mks += [None] * (4 - len(mks))
+    return tuple(outs), tuple(mks)

@@ -136,6 +136,11 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
  */
 int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
                    int table_size, int scale_num, float* out, int out_is_device);
+/* Same, and the masks the levels are pooled with: out_masks (nullable) uint8 [scale_num-1][B,H,W],
+ * out_masks[k] = out[k] > 0.001 (net.py:95-96, :105-106) = the "DT-pooling mask" of level k+2, a Chebyshev
+ * dilation of the validity mask by (table_size / 2) pixels per level. */
+int dtfill_dt_pool_ex(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
+                      int table_size, int scale_num, float* out, uint8_t* out_masks, int out_is_device);
 
 /* KITTI outlier filter outlier_removal (data_read.py:103-128), the step just before the path: in, out float32
  * [B,H,W]; a depth more than 1.0 m farther than the average of the valid depths in its 7 x 7 diamond is zeroed. */

@@ -18,7 +18,7 @@ def test_header_declares_the_path():
     syms = declared_symbols()
     for s in ("dtfill_create", "dtfill_destroy", "dtfill_run", "dtfill_run_async", "dtfill_status", "dtfill_metrics",
               "dtfill_last_error", "dtfill_host_alloc", "dtfill_host_free", "dtfill_set_stream",
-              "dtfill_synchronize", "dtfill_abi_version", "dtfill_set_profiling", "dtfill_kernel_times", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_set_subbatches", "dtfill_debug_get_tasks", "dtfill_set_pipeline_depth", "dtfill_flush", "dtfill_dt_pool", "dtfill_debug_read_status", "dtfill_outlier_removal"):
+              "dtfill_synchronize", "dtfill_abi_version", "dtfill_set_profiling", "dtfill_kernel_times", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_set_subbatches", "dtfill_debug_get_tasks", "dtfill_set_pipeline_depth", "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_debug_read_status", "dtfill_outlier_removal"):
         assert s in syms
 
 

@@ -71,6 +71,25 @@ def test_gpu_odd_widths(W):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("table_size", [7, 9, 11])
+def test_gpu_level_masks(table_size):
+    """the level-k DT-pooling masks as uint8, from the kernels that produce the levels."""
+    from scipy.ndimage import binary_dilation
+    x = np.stack([synth.kitti_frame(8)[60:200, 100:420], synth.nyu_frame(3)[:140, :320]])[..., None]
+    mask = (x > 0.1).astype(np.float32)
+    data = (x / np.float32(90.0) * mask).astype(np.float32)
+    levels, masks = net_pool.dt_pooling_masks(data, mask, table_size=table_size, scale_num=4)
+    plain = net_pool.generate_multi_channel(data, mask, table_size=table_size, scale_num=4)
+    m = mask[..., 0] > 0
+    assert np.array_equal(masks[0], m.astype(np.uint8))
+    for k in (1, 2, 3):
+        assert np.array_equal(levels[k], plain[k])
+        assert masks[k].dtype == np.uint8 and np.array_equal(masks[k], (levels[k] > 0.001).astype(np.uint8))
+        m = binary_dilation(m, np.ones((1, table_size, table_size), bool))
+        assert np.array_equal(masks[k].astype(bool), m)
+
+
+@pytest.mark.gpu
 def test_gpu_full_size_and_errors():
     x = synth.kitti_batch([11, 12])
     mask = (x > 0.1).astype(np.float32)
