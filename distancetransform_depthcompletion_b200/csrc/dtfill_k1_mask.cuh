@@ -30,13 +30,17 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = fp.W, WW = fp.WW;
     const long nrows = (long)fp.B * fp.H;
+    const bool rows32 = nrows < (1l << 31);
     const int nchunks = (W + 511) >> 9;
     const float scut = fp.src_cut, vthr = fp.val_thr;
     const bool mask16 = (W & 15) == 0;
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
-        const long frame = row / fp.H;
-        const T* rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
+        const T* rp = in + row * W;
+        if (fp.in_H != fp.H) {                       // cropped input frames (uint16 entry): row -> (frame, y)
+            const long frame = rows32 ? (long)((uint32_t)row / (uint32_t)fp.H) : row / fp.H;
+            rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
+        }
         uint32_t cs = 0, cv = 0;
         // software pipeline over the 512-pixel chunks: the 128-bit loads of the next chunk are issued (volatile
         // asm, so they stay ahead) before the current chunk is processed
@@ -91,47 +95,45 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
             // coarse cells: bit j of the word's nibble = some source among its pixels 8j..8j+7
             const uint32_t cell = ((sw & 0xFFu) != 0) | (((sw & 0xFF00u) != 0) << 1) | (((sw & 0xFF0000u) != 0) << 2) |
                                   (((sw & 0xFF000000u) != 0) << 3);
-            const uint32_t sany = __ballot_sync(0xffffffffu, sb != 0);
-            const uint32_t vany = __ballot_sync(0xffffffffu, vb != 0);
-            uint32_t spre = 0, stot = 0;
-            if (sany) {
-                const uint32_t c = __popc(sb);
+            // one scan for both counts: sources in the low half, valid pixels in the high half (<= 512 each)
+            const uint32_t anybits = __ballot_sync(0xffffffffu, (sb | vb) != 0);
+            uint32_t pre = 0, tot = 0;
+            if (anybits) {
+                const uint32_t c = __popc(sb) | (__popc(vb) << 16);
                 uint32_t inc = c;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
                     if (lane >= d) inc += o;
                 }
-                spre = inc - c;
-                stot = __shfl_sync(0xffffffffu, inc, 31);
+                pre = inc - c;
+                tot = __shfl_sync(0xffffffffu, inc, 31);
             }
             const int w = (ch << 4) + (lane >> 1);
             if ((lane & 1) == 0 && w < WW) {
                 const long wi = row * WW + w;
                 ws.srcbits[wi] = sw;
                 ws.valbits[wi] = vw;
-                ws.wprefix[wi] = (uint16_t)(cs + spre);
+                ws.wprefix[wi] = (uint16_t)(cs + (pre & 0xFFFFu));
                 ws.rowcell[wi] = (uint8_t)cell;
             }
-            cs += stot;
-            if (vany) {
-                const uint32_t c = __popc(vb);
-                uint32_t inc = c;
+            cs += tot & 0xFFFFu;
+            if (tot >> 16) {
+                // the lane's valid values, still in registers, go out with predicated stores (a loop over the set
+                // bits would run as often as the busiest lane has valid pixels, 7 times on a beam row)
+                float* dst = rowvals + row * W + cv + (pre >> 16);
+                uint32_t off = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
+                for (int g = 0; g < 4; ++g) {
+                    const float vv[4] = {q[g].x, q[g].y, q[g].z, q[g].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t p = (vb >> (4 * g + e)) & 1u;
+                        if (p) dst[off] = vv[e];
+                        off += p;
+                    }
                 }
-                // few pixels per lane are valid (~5 % density): walk the set bits and re-read the values (L1 hits)
-                float* dst = rowvals + row * W + cv + (inc - c);
-                const T* xs = rp + col;
-                uint32_t m = vb;
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    *dst++ = load_px(xs + j);
-                }
-                cv += __shfl_sync(0xffffffffu, inc, 31);
+                cv += tot >> 16;
             }
         }
         if (lane == 0) {
@@ -153,12 +155,16 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const T* __restrict__ in, Fr
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = fp.W, WW = fp.WW;
     const long nrows = (long)fp.B * fp.H;
+    const bool rows32 = nrows < (1l << 31);
     const bool vec_mask = (W & 3) == 0;
     const uint32_t ltmask = lanemask_lt();
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
-        const long frame = row / fp.H;
-        const T* rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
+        const T* rp = in + row * W;
+        if (fp.in_H != fp.H) {                       // cropped input frames (uint16 entry): row -> (frame, y)
+            const long frame = rows32 ? (long)((uint32_t)row / (uint32_t)fp.H) : row / fp.H;
+            rp = in + (frame * fp.in_H + fp.in_crop + (row - frame * fp.H)) * W;
+        }
         uint32_t cs = 0, cv = 0;
         for (int c0 = 0; c0 < WW; c0 += 16) {
             float x[16];
