@@ -101,19 +101,18 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 const uint32_t cnt = __shfl_sync(0xffffffffu, mycnt, r);
                 if (cnt == 0) continue;
                 const uint32_t base = __shfl_sync(0xffffffffu, mybase, r);
-                const float* src = rowvals + (long)(yb + r) * W;
+                const float* src = rowvals + (long)(yb + r) * W + lane;
+                float* dst = dl + base + lane;
                 for (uint32_t i0 = 0; i0 < cnt; i0 += 32 * 12) {       // 12 loads in flight per lane
+                    const int rem = (int)(cnt - i0) - lane;            // elements k with 32 k < rem are this lane's
+                    const float* sp = src + i0;
+                    float* dp = dst + i0;
                     float v[12];
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) {
-                        const uint32_t i = i0 + k * 32 + lane;
-                        v[k] = i < cnt ? src[i] : 0.f;
-                    }
+                    for (int k = 0; k < 12; ++k) v[k] = 32 * k < rem ? sp[32 * k] : 0.f;
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) {
-                        const uint32_t i = i0 + k * 32 + lane;
-                        if (i < cnt) dl[base + i] = v[k];
-                    }
+                    for (int k = 0; k < 12; ++k)
+                        if (32 * k < rem) dp[32 * k] = v[k];
                 }
             }
         }
