@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
     const bool plan = kind == TASK_CHAMFER && fp.band_cap > 0 && nh * nw <= MAX_CELLS && nh <= 1024 && H <= 4096 &&
                       2 * H > fp.band_cap;
 
+    // Rows above the first source row f need no scan (k3_sky): S0 = rows handed over, a multiple of the cell height
+    // with S0 + 1 <= f.  The planner's grid then starts at cell row c0row: cells above hold no source and lie on no
+    // shortest path between a cell and a source below them.
+    int S0 = 0;
+    if (plan && fp.sky_min > 0 && W <= SKY_MAX_W) {
+        int f = 0;
+        for (int w = 0; w < 128 && (w << 5) < H; ++w)
+            if (srcrows[w]) { f = (w << 5) + __ffs(srcrows[w]) - 1; break; }
+        const int s4 = f >= 1 ? ((f - 1) / CELL_H) * CELL_H : 0;
+        if (s4 >= fp.sky_min) S0 = s4;
+    }
+    const int c0row = S0 / CELL_H;
+
     if (wid < 8) {
         // ---- warps 0..7: depth_list = in[valid] in raster order (tools.py:24).  K1 left every row's valid depths
         // compacted at the start of the row's slot in ws.scratch; concatenate the non-empty rows.
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
         // rowcell nibbles of CELL_H consecutive rows OR-ed per word, then one distance cell per bit
         const uint8_t* rc = ws.rowcell + (long)b * H * WW;
-        for (int i0 = 0; i0 < nh * WW; i0 += 256 * 8) {           // 32 independent byte loads in flight per thread
+        for (int i0 = c0row * WW; i0 < nh * WW; i0 += 256 * 8) {  // 32 independent byte loads in flight per thread
             uint32_t o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         }
         planner_sync();
         dbg_mark(1);
-        for (int i = ptid; i < nh * nw; i += 256) {
+        for (int i = c0row * nw + ptid; i < nh * nw; i += 256) {
             const int cy = i / nw, cx = i - cy * nw;
             cellD[i] = ((occw[cy * WW + (cx >> 2)] >> (cx & 3)) & 1u) ? 0 : 60000;
         }
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         dbg_mark(2);
         for (int cx = ptid; cx < nw; cx += 256) {        // vertical sweeps, one thread per cell column
             uint32_t d = 60000;
-            for (int c0 = 0; c0 < nh; c0 += 8) {         // 8 loads ahead of the dependent (min,+) chain
+            for (int c0 = c0row; c0 < nh; c0 += 8) {     // 8 loads ahead of the dependent (min,+) chain
                 uint32_t v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] = c0 + k < nh ? (uint32_t)cellD[(c0 + k) * nw + cx] : 60000u;
@@ -168,14 +181,14 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 }
             }
             d = 60000;
-            for (int c0 = nh - 1; c0 >= 0; c0 -= 8) {
+            for (int c0 = nh - 1; c0 >= c0row; c0 -= 8) {
                 uint32_t v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = c0 - k >= 0 ? (uint32_t)cellD[(c0 - k) * nw + cx] : 60000u;
+                for (int k = 0; k < 8; ++k) v[k] = c0 - k >= c0row ? (uint32_t)cellD[(c0 - k) * nw + cx] : 60000u;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     d = min(min(d + CELL_H, v[k]), 60000u);
-                    if (c0 - k >= 0) cellD[(c0 - k) * nw + cx] = (uint16_t)d;
+                    if (c0 - k >= c0row) cellD[(c0 - k) * nw + cx] = (uint16_t)d;
                 }
             }
         }
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         // (min,+) scans across lanes via shuffles; only the row maximum leaves the warp
         const int chunk = (nw + 31) / 32;
         if (chunk <= 8) {
-            for (int cy = pw; cy < nh; cy += 8) {
+            for (int cy = c0row + pw; cy < nh; cy += 8) {
                 const uint16_t* rowp = cellD + cy * nw;
                 const int xa = lane * chunk;
                 uint32_t v[8];
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 if (lane == 0) cellU[cy] = (int)min(mx, 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
             }
         } else {
-            for (int cy = pw * 32 + lane; cy < nh; cy += 256) {      // very wide frames: one thread per cell row
+            for (int cy = c0row + pw * 32 + lane; cy < nh; cy += 256) {      // very wide frames: one thread per cell row
                 uint32_t d = 60000;
                 for (int cx = 0; cx < nw; ++cx) { d = min(d + CELL_W, (uint32_t)cellD[cy * nw + cx]); cellD[cy * nw + cx] = (uint16_t)min(d, 60000u); }
                 d = 60000;
@@ -256,17 +269,9 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
             q.clo = 0; q.c0 = 0; q.c1 = W; q.sky = -2;
             return q;
         };
-        // Rows above the first source row f need no scan: their distance is that of row f plus the row offset and
-        // their label follows a fixed route down to two base rows (see k3_sky).  S = rows handed to k3_sky, a
-        // multiple of the cell height with S + 1 <= f; the tiles below cover rows [S, H).
-        int S = 0;
-        if (plan && fp.sky_min > 0 && W <= SKY_MAX_W) {
-            int f = 0;
-            for (int w = 0; w < 128 && (w << 5) < H; ++w)
-                if (srcrows[w]) { f = (w << 5) + __ffs(srcrows[w]) - 1; break; }
-            const int s4 = f >= 1 ? ((f - 1) / CELL_H) * CELL_H : 0;
-            if (s4 >= fp.sky_min) S = s4;
-        }
+        // S = rows handed to k3_sky (their distance is that of row f plus the row offset, their label follows a fixed
+        // route down to two base rows); the tiles below cover rows [S, H).
+        int S = S0;
         if (plan) {
             const int nwid = fp.narrow_ppl * 32;                 // width of a half-width tile (0: never split)
             int cy = S / CELL_H, scr = 0;
