@@ -39,7 +39,7 @@ struct Buf {
 // scan of the previous call.
 struct Lane {
     static const int MAX_SUB = 8;
-    Buf srcbits, valbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
+    Buf srcbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
     int* status_host = nullptr;          // pinned [2]
     cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
@@ -227,7 +227,6 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     }
     Workspace ws;
     ws.srcbits = (uint32_t*)L->srcbits.p + rows0 * WW;
-    ws.valbits = (uint32_t*)L->valbits.p + rows0 * WW;
     ws.wprefix = (uint16_t*)L->wprefix.p + rows0 * WW;
     ws.rowcell = (uint8_t*)L->rowcell.p + rows0 * WW;
     ws.rowsrc = (uint32_t*)L->rowsrc.p + rows0;
@@ -332,7 +331,6 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
 
     int rc;
     if ((rc = ensure(h, L->srcbits, rows * WW * 4))) return rc;
-    if ((rc = ensure(h, L->valbits, rows * WW * 4))) return rc;
     if ((rc = ensure(h, L->wprefix, rows * WW * 2))) return rc;
     if ((rc = ensure(h, L->rowcell, rows * WW))) return rc;
     if ((rc = ensure(h, L->rowsrc, rows * 4))) return rc;
@@ -496,7 +494,7 @@ void dtfill_destroy(dtfill_t* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (Lane& L : h->lanes) {
-        Buf* lb[] = {&L.srcbits, &L.valbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
+        Buf* lb[] = {&L.srcbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
                      &L.scratch, &L.tasks, &L.status};
         for (Buf* b : lb)
             if (b->p) cudaFree(b->p);

@@ -69,7 +69,6 @@ struct FrameParams {
 
 struct Workspace {
     uint32_t* srcbits;   // [B*H*WW]
-    uint32_t* valbits;   // [B*H*WW]
     uint16_t* wprefix;   // [B*H*WW] sources in the row before this word
     uint8_t* rowcell;    // [B*H*WW] per word: bit j = some source among its pixels 8j..8j+7
     uint32_t* rowsrc;    // [B*H]  K1: row count, K1b: exclusive base within the frame

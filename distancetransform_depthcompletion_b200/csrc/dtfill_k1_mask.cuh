@@ -89,9 +89,8 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
                 }
             }
             // 32-bit words from the halves of 2 neighbouring lanes
-            uint32_t sw = sb << ((lane & 1) * 16), vw = vb << ((lane & 1) * 16);
+            uint32_t sw = sb << ((lane & 1) * 16);
             sw |= __shfl_xor_sync(0xffffffffu, sw, 1);
-            vw |= __shfl_xor_sync(0xffffffffu, vw, 1);
             // coarse cells: bit j of the word's nibble = some source among its pixels 8j..8j+7
             const uint32_t cell = ((sw & 0xFFu) != 0) | (((sw & 0xFF00u) != 0) << 1) | (((sw & 0xFF0000u) != 0) << 2) |
                                   (((sw & 0xFF000000u) != 0) << 3);
@@ -113,7 +112,6 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
             if ((lane & 1) == 0 && w < WW) {
                 const long wi = row * WW + w;
                 ws.srcbits[wi] = sw;
-                ws.valbits[wi] = vw;
                 ws.wprefix[wi] = (uint16_t)(cs + (pre & 0xFFFFu));
                 ws.rowcell[wi] = (uint8_t)cell;
             }
@@ -174,7 +172,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const T* __restrict__ in, Fr
                 x[k] = col < W ? load_px_stream(rp + col) : 0.0f;
                 if (out_lidar && col < W) out_lidar[row * W + col] = x[k];
             }
-            uint32_t mys = 0, myv = 0, mypre = 0;
+            uint32_t mys = 0, mypre = 0;
             uint32_t vq[4];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -185,7 +183,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const T* __restrict__ in, Fr
                 const bool vp = inb && (x[k] > fp.val_thr);           // tools.py:22 with_value
                 const uint32_t sw = __ballot_sync(0xffffffffu, sp);
                 const uint32_t vw = __ballot_sync(0xffffffffu, vp);
-                if (lane == k) { mys = sw; myv = vw; mypre = cs; }
+                if (lane == k) { mys = sw; mypre = cs; }
                 if (vp) rowvals[row * W + cv + __popc(vw & ltmask)] = x[k];
                 cs += __popc(sw);
                 cv += __popc(vw);
@@ -209,7 +207,6 @@ __global__ void __launch_bounds__(256) k1_mask_rows(const T* __restrict__ in, Fr
             if (lane < 16 && c0 + lane < WW) {
                 const long wi = row * WW + c0 + lane;
                 ws.srcbits[wi] = mys;
-                ws.valbits[wi] = myv;
                 ws.wprefix[wi] = (uint16_t)mypre;
                 ws.rowcell[wi] = (uint8_t)(((mys & 0xFFu) != 0) | (((mys & 0xFF00u) != 0) << 1) |
                                            (((mys & 0xFF0000u) != 0) << 2) | (((mys & 0xFF000000u) != 0) << 3));

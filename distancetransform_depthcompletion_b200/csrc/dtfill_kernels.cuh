@@ -1,7 +1,8 @@
 // dtfill_kernels.cuh -- sm_100a kernels of the DT + nearest-neighbour fill path.
 //
 // Pipeline for a batch of frames [B,H,W] float32 (all device resident):
-//   K1  k1_mask_rows      in -> source/valid bit rows, per-word source prefix, row counts, validity mask (u8)
+//   K1  k1_mask_rows      in -> source bit rows, per-word source prefix, row counts, validity mask (u8), row-local
+//                         lists of the valid depths
 //                         (reference: value_mask tools.py:8 / eval_NYU.py:115, with_value tools.py:22, net.py:131)
 //   K1b k1b_scan_compact  per frame: exclusive row bases (= raster ranks, OpenCV's label initialisation),
 //                         depth_list = in[valid] in raster order (tools.py:24), task list for K2
