@@ -255,11 +255,13 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
         int grid = (int)(want < 1 ? 1 : want);
         if (!h->in_u16) {
             const float* in_s = (const float*)in + npx0;
-            if ((W & 3) == 0) k1_mask_rows_v16<float><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
+            if ((W & 15) == 0) k1_mask_rows_v16<float, true><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
+            else if ((W & 3) == 0) k1_mask_rows_v16<float, false><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
             else k1_mask_rows<float><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
         } else {
             const uint16_t* in_s = (const uint16_t*)in + (size_t)b0 * h->in_H * W;
-            if ((W & 7) == 0) k1_mask_rows_v16<uint16_t><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
+            if ((W & 15) == 0) k1_mask_rows_v16<uint16_t, true><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
+            else if ((W & 7) == 0) k1_mask_rows_v16<uint16_t, false><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
             else k1_mask_rows<uint16_t><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
         }
         ++*launches;

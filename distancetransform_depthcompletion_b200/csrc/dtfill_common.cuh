@@ -130,6 +130,14 @@ template <> struct In16<float> {
 #pragma unroll
         for (int g = 0; g < 4; ++g) q[g] = col + 4 * g < W ? ld_stream_v4(p + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __device__ __forceinline__ void load_all(const float* p, bool inside) {     // all 16 pixels inside the row, or none
+#pragma unroll
+        for (int g = 0; g < 4; ++g) q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inside) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) q[g] = ld_stream_v4(p + 4 * g);
+        }
+    }
     __device__ __forceinline__ float4 get(int g) const { return q[g]; }
 };
 template <> struct In16<uint16_t> {
@@ -137,6 +145,10 @@ template <> struct In16<uint16_t> {
     __device__ __forceinline__ void load(const uint16_t* p, int col, int W) {     // W % 8 == 0
 #pragma unroll
         for (int k = 0; k < 2; ++k) r[k] = col + 8 * k < W ? ld_stream_v4u(p + 8 * k) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ __forceinline__ void load_all(const uint16_t* p, bool inside) {
+        r[0] = r[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (inside) { r[0] = ld_stream_v4u(p); r[1] = ld_stream_v4u(p + 8); }
     }
     __device__ __forceinline__ float4 get(int g) const {
         const uint32_t a = (g & 1) ? r[g >> 1].z : r[g >> 1].x, b = (g & 1) ? r[g >> 1].w : r[g >> 1].y;

@@ -21,7 +21,8 @@ __device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, fl
     return (w * 0x00204081u) >> 28;
 }
 
-template <typename T>
+// W16: W % 16 == 0 (KITTI 1216, NYU 640): a lane's 16 pixels are inside the row or outside it as a whole.
+template <typename T, bool W16>
 __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in, FrameParams fp, Workspace ws,
                                                          uint8_t* __restrict__ out_mask, float* __restrict__ out_lidar)
 {
@@ -33,7 +34,6 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
     const bool rows32 = nrows < (1l << 31);
     const int nchunks = (W + 511) >> 9;
     const float scut = fp.src_cut, vthr = fp.val_thr;
-    const bool mask16 = (W & 15) == 0;
     float* rowvals = reinterpret_cast<float*>(ws.scratch);
     for (long row = warp; row < nrows; row += nwarps) {
         const T* rp = in + row * W;
@@ -45,17 +45,21 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
         // software pipeline over the 512-pixel chunks: the 128-bit loads of the next chunk are issued (volatile
         // asm, so they stay ahead) before the current chunk is processed
         In16<T> nq;
-        nq.load(rp + lane * 16, lane * 16, W);
+        if (W16) nq.load_all(rp + lane * 16, lane * 16 < W);
+        else nq.load(rp + lane * 16, lane * 16, W);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int col = (ch << 9) + lane * 16;
             float4 q[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) q[g] = nq.get(g);
-            if (ch + 1 < nchunks) nq.load(rp + col + 512, col + 512, W);
+            if (ch + 1 < nchunks) {
+                if (W16) nq.load_all(rp + col + 512, col + 512 < W);
+                else nq.load(rp + col + 512, col + 512, W);
+            }
             if (out_lidar && col < W) {                  // decoded frame (uint16 input): what the CNN reads as lidar
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                    if (col + 4 * g < W)
+                    if (W16 || col + 4 * g < W)
                         st_stream_v4(out_lidar + row * W + col + 4 * g, __float_as_uint(q[g].x), __float_as_uint(q[g].y),
                                      __float_as_uint(q[g].z), __float_as_uint(q[g].w));
             }
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
                 sb |= ns << (4 * g);
                 vb |= nv << (4 * g);
             }
-            const uint32_t inb = (1u << min(max(W - col, 0), 16)) - 1u;      // pixels of this lane inside the row
+            const uint32_t inb = W16 ? (col < W ? 0xFFFFu : 0u)              // pixels of this lane inside the row
+                                     : (1u << min(max(W - col, 0), 16)) - 1u;
             sb = ~sb & inb;
             vb &= inb;
             if (out_mask && col < W) {
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
 #pragma unroll
                 for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
                 uint8_t* mp = out_mask + row * W + col;
-                if (mask16) {
+                if (W16) {
                     st_stream_v4(mp, m[0], m[1], m[2], m[3]);
                 } else {
 #pragma unroll
