@@ -124,16 +124,19 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
             if (tot >> 16) {
                 // the lane's valid values, still in registers, go out with predicated stores (a loop over the set
                 // bits would run as often as the busiest lane has valid pixels, 7 times on a beam row)
-                float* dst = rowvals + row * W + cv + (pre >> 16);
+                // (addresses as 32 x 32 + 64 multiply-adds with a run-time multiplier: FMA pipe, not the ALU pipe this
+                // kernel saturates)
+                const char* dst = reinterpret_cast<const char*>(rowvals + row * W + cv + (pre >> 16));
                 uint32_t off = 0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const float vv[4] = {q[g].x, q[g].y, q[g].z, q[g].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const uint32_t p = (vb >> (4 * g + e)) & 1u;
-                        if (p) dst[off] = vv[e];
-                        off += p;
+                        const bool p = (vb & (1u << (4 * g + e))) != 0;
+                        float* a = reinterpret_cast<float*>(const_cast<char*>(dst) + (uint64_t)off * fp.four);
+                        if (p) *a = vv[e];
+                        off = p ? off * fp.one + 1u : off;
                     }
                 }
                 cv += tot >> 16;
