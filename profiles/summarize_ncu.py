@@ -39,7 +39,7 @@ if len(sys.argv) > 4:
     k2 = max((k for k in traffic if k.startswith("k2_chamfer<")), key=lambda k: traffic[k])
     json.dump({"kernel": k2 + " (narrow tiles, the dominant kernel)", "dram_bytes_per_launch": traffic[k2],
                "source": out_path + " (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of "
-                                    "one step of the headline configuration: 3 batches in flight, k3_sky on)",
+                                    "one step of the pipelined configuration, k3_sky on)",
                "note": "traffic above the algorithmic bytes = forward-state scratch of the scan (written once, read "
                        "back once) and the bit rows / prefixes / depth_list the first stage leaves for it",
                "dram_bytes_per_step": sum(traffic.values()), "per_kernel_dram_bytes": traffic,

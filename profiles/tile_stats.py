@@ -1,5 +1,5 @@
 """Tile statistics of the planner for the bench workload: how much of K2's row-step work is redundancy (halos,
-column overlap, padded lanes).  Run on the GPU box: python profiles/tile_stats.py [workload]"""
+column overlap, padded lanes).  Run on the GPU box: python profiles/tile_stats.py [workload [pipeline_depth [band_cap]]]"""
 import sys
 import numpy as np
 sys.path.insert(0, '/root/repo')
@@ -13,6 +13,8 @@ B = 256
 x = np.stack([synth.kitti_frame(i, beam_step=step) for i in range(32)])
 x = np.concatenate([x] * (B // 32))
 eng = DTFillEngine(0, pipeline_depth=int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+if len(sys.argv) > 3:
+    eng.handle.set_band_cap(int(sys.argv[3]))
 xd = torch.from_numpy(x).cuda()
 eng.fill(xd); eng.flush(); eng.status()
 t = eng.handle.debug_tasks(1 << 16)
