@@ -205,8 +205,6 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     fp.sky_min = h->sky_min >= 0 ? h->sky_min : (h->cur_pipelined ? 8 : 0);
     fp.max_col_tiles = h->max_col_tiles;
     fp.mul_dist = 1u << (32 - DSH);
-    fp.mul_ord = 1u << (32 - OSH);
-    fp.neg_ord = 0u - (1u << OSH);
     fp.four = 4u;
     fp.one = 1u;
     {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch

@@ -61,8 +61,6 @@ struct FrameParams {
     // Multipliers handed over at run time so that ptxas keeps the multiply-adds below on the FMA pipe instead of
     // strength-reducing them to shifts/LEAs on the ALU pipe, which is the pipe the scan kernel saturates.
     uint32_t mul_dist;         // 1 << (32 - DSH):  umulhi(key, mul_dist)  == key >> DSH
-    uint32_t mul_ord;          // 1 << (32 - OSH):  umulhi(key, mul_ord)   == key >> OSH
-    uint32_t neg_ord;          // -(1 << OSH):      key + (key >> OSH) * neg_ord == key & LMASK
     uint32_t four;             // sizeof(float)
     uint32_t one;              // 1: x * one + c keeps a plain add on the FMA pipe
 };
@@ -95,9 +93,6 @@ __device__ __forceinline__ float ld_stream(const float* p) {
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
-__device__ __forceinline__ void st_stream_v2(void* p, uint32_t a, uint32_t b) {
-    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
-}
 __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d));
 }
@@ -117,8 +112,6 @@ __device__ __forceinline__ uint4 ld_stream_v4u(const void* p) {
 // KITTI depth PNG sample -> metres, data_read.py:215 `depth_png.astype(np.float32) / 256.` (exact in float32):
 // 0x47000000 is 32768.0f, whose mantissa step is 2^-8, so OR-ing the sample into the mantissa gives 32768 + v/256.
 __device__ __forceinline__ float u16_depth(uint32_t v16) { return __uint_as_float(0x47000000u | v16) - 32768.0f; }
-__device__ __forceinline__ float load_px(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float load_px(const uint16_t* p) { return u16_depth(__ldg(p)); }
 __device__ __forceinline__ float load_px_stream(const float* p) { return ld_stream(p); }
 __device__ __forceinline__ float load_px_stream(const uint16_t* p) { return u16_depth(__ldg(p)); }
 

@@ -94,13 +94,6 @@ __device__ __forceinline__ float key_dist_f32(uint32_t key, uint32_t mul_dist) {
     asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(key), "r"(mul_dist), "r"(0x4B000000u));
     return __uint_as_float(t) - 8388608.0f;
 }
-// label field of a key, two multiply-adds on the FMA pipe
-__device__ __forceinline__ uint32_t key_label(uint32_t key, uint32_t mul_ord, uint32_t neg_ord) {
-    uint32_t hi, l;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(key), "r"(mul_ord));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(l) : "r"(hi), "r"(neg_ord), "r"(key));
-    return l;
-}
 
 // Raw words holding this lane's PPL source bits of one row, fetched one row ahead of their use.
 struct RowBits {
