@@ -493,3 +493,35 @@ def test_uint16_png_device_resident_pipelined(handle):
         for k in ("depth", "dt", "lbl", "mask"):
             assert np.array_equal(o[k].cpu().numpy(), want[k]), k
         assert np.array_equal(o["counts"].cpu().numpy(), want["counts"])
+
+
+def test_pipelined_random_shapes_against_oracle(handle):
+    """Batches in flight (k3_sky active where a frame has source-free top rows) over random sizes, densities and
+    top gaps, labels included: every output against the oracle."""
+    import torch
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    rng = np.random.default_rng(2024)
+    eng = DTFillEngine(0, pipeline_depth=4)
+    eng.handle.set_band_cap(48)
+    pending = []
+    for t in range(24):
+        H, W = int(rng.integers(20, 200)), int(rng.integers(8, 1217))
+        if t % 3 == 0:
+            W = (W // 16) * 16 + 16
+        dens = float(rng.choice([0.004, 0.03, 0.2, 0.7]))
+        top = int(rng.integers(0, H - 2))
+        x = ((rng.random((3, H, W)) < dens) * rng.uniform(1, 60, (3, H, W))).astype(np.float32)
+        x[:, :top] = 0
+        x[:, top, rng.integers(0, W)] = 4.0
+        xd = torch.from_numpy(x).cuda()
+        pending.append((x, xd, eng.fill(xd, want_lbl=True)))
+        if len(pending) == 4:
+            eng.flush()
+            assert eng.status()[0] == -1
+            for x_, _, o in pending:
+                want = O.dt_fill(x_, 0.1, 0.1)
+                assert np.array_equal(o["lbl"].cpu().numpy(), want["lbl"]), x_.shape
+                assert np.array_equal(o["dt"].cpu().numpy(), want["dt"]), x_.shape
+                assert np.array_equal(o["depth"].cpu().numpy().view(np.uint32), want["depth"].view(np.uint32)), x_.shape
+                assert np.array_equal(o["mask"].cpu().numpy(), want["mask"]), x_.shape
+            pending = []
