@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdtfill.so")
 E_ARG, E_CUDA, E_INDEX, E_NOMEM = -1, -2, -3, -4
 METRICS_KITTI, METRICS_NYU = 0, 1
 METRIC_COLS = 9
+ABI_VERSION = 2          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
 METRIC_NAMES = ("mse", "rmse", "mae", "irmse", "imae", "delta1", "delta2", "delta3", "count")
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -42,6 +43,9 @@ def load() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
         L.dtfill_abi_version.restype = ci
+        if L.dtfill_abi_version() != ABI_VERSION:
+            raise DTFillError(f"{LIB_PATH} has ABI version {L.dtfill_abi_version()}, this package needs {ABI_VERSION}: "
+                              "rebuild it with `python -m distancetransform_depthcompletion_b200.build`")
         L.dtfill_last_error.restype = ctypes.c_char_p
         L.dtfill_create.argtypes = [ci, ctypes.POINTER(vp)]
         L.dtfill_destroy.argtypes = [vp]

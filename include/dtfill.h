@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTFILL_ABI_VERSION 1
+#define DTFILL_ABI_VERSION 2      /* 2: dtfill_run_u16(_async), dtfill_dt_pool_ex, dtfill_set_sky_min, 5 kernel times */
 
 enum {
     DTFILL_OK = 0,

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(dtfill_lib):
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/dtfill.h but not exported by libdtfill.so"
     L.dtfill_abi_version.restype = ctypes.c_int
-    assert L.dtfill_abi_version() == 1
+    assert L.dtfill_abi_version() == 2
 
 
 def test_binding_declares_every_symbol(dtfill_lib):
