@@ -12,12 +12,13 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdtfill.so")
+# DTFILL_LIB: another build of the same library (kernel experiments); the product is the in-tree libdtfill.so
+LIB_PATH = os.environ.get("DTFILL_LIB") or os.path.join(_HERE, "libdtfill.so")
 
 E_ARG, E_CUDA, E_INDEX, E_NOMEM = -1, -2, -3, -4
 METRICS_KITTI, METRICS_NYU = 0, 1
 METRIC_COLS = 9
-ABI_VERSION = 2          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
+ABI_VERSION = 3          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
 METRIC_NAMES = ("mse", "rmse", "mae", "irmse", "imae", "delta1", "delta2", "delta3", "count")
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -56,12 +57,18 @@ def load() -> ctypes.CDLL:
         L.dtfill_run_async.argtypes = [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp]
         L.dtfill_status.argtypes = [vp, _c_int_p, _c_int_p]
         L.dtfill_metrics.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
+        L.dtfill_metrics_ex.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, ci]
+        L.dtfill_nccl_unique_id.argtypes = [vp]
+        L.dtfill_comm_create.argtypes = [vp, vp, ci, ci, ctypes.POINTER(vp)]
+        L.dtfill_comm_destroy.argtypes = [vp]
+        L.dtfill_allreduce_sums.argtypes = [vp, vp, vp, ci]
         L.dtfill_set_profiling.argtypes = [vp, ci]
         L.dtfill_set_band_cap.argtypes = [vp, ci]
         L.dtfill_set_subbatches.argtypes = [vp, ci]
         L.dtfill_run_u16.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, ci, ctypes.POINTER(ci)]
         L.dtfill_run_u16_async.argtypes = [vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp]
         L.dtfill_set_sky_min.argtypes = [vp, ci]
+        L.dtfill_set_stage_threads.argtypes = [vp, ci]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
         L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
@@ -76,7 +83,8 @@ def load() -> ctypes.CDLL:
         for name in ("dtfill_create", "dtfill_set_stream", "dtfill_synchronize", "dtfill_run", "dtfill_run_async",
                      "dtfill_status", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
-                     "dtfill_kernel_times"):
+                     "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
+                     "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -215,6 +223,10 @@ class Handle:
         8 in pipelined mode, never in strict order."""
         _check(self._L.dtfill_set_sky_min(self._h, int(rows)), "dtfill_set_sky_min")
 
+    def set_stage_threads(self, threads: int):
+        """Host threads per direction that stage pageable numpy buffers through pinned mirrors (-1 auto, 0 never)."""
+        _check(self._L.dtfill_set_stage_threads(self._h, int(threads)), "dtfill_set_stage_threads")
+
     def set_pipeline_depth(self, depth: int):
         """2: consecutive run_device_async calls may overlap (outputs final after flush()/status()); 1: strict."""
         _check(self._L.dtfill_set_pipeline_depth(self._h, int(depth)), "dtfill_set_pipeline_depth")
@@ -272,8 +284,13 @@ class Handle:
         return out
 
     def metrics(self, pred, gt, B: int, H: int, W: int, mode: int, gt_is_f64: bool, on_device: bool = False,
-                per_frame_ptr=None, sums_ptr=None):
-        """Host arrays (on_device False) -> (per_frame [B,9], sums [10]) numpy; device pointers otherwise."""
+                per_frame_ptr=None, sums_ptr=None, accumulate: bool = False):
+        """Host arrays (on_device False) -> (per_frame [B,9], sums [10]) numpy; device pointers otherwise
+        (accumulate: add this batch's totals to the device vector at sums_ptr instead of overwriting it)."""
+        if accumulate:
+            _check(self._L.dtfill_metrics_ex(self._h, _ptr(pred), _ptr(gt), int(gt_is_f64), 1, B, H, W, mode,
+                                             _ptr(per_frame_ptr), _ptr(sums_ptr), 1, 1), "dtfill_metrics_ex")
+            return None
         if not on_device:
             per_frame = np.empty((B, METRIC_COLS), np.float64)
             sums = np.empty(METRIC_COLS + 1, np.float64)
@@ -283,6 +300,34 @@ class Handle:
         _check(self._L.dtfill_metrics(self._h, _ptr(pred), _ptr(gt), int(gt_is_f64), 1, B, H, W, mode,
                                       _ptr(per_frame_ptr), _ptr(sums_ptr), 1), "dtfill_metrics")
         return None
+
+
+    # ---- the one collective of the path (include/dtfill.h: dtfill_allreduce_sums) --------------------------
+    def comm_create(self, unique_id: bytes, nranks: int, rank: int) -> int:
+        """ncclCommInitRank on this handle's device; returns the ncclComm_t as an int."""
+        assert len(unique_id) == NCCL_ID_BYTES
+        buf = ctypes.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        comm = ctypes.c_void_p()
+        _check(self._L.dtfill_comm_create(self._h, buf, int(nranks), int(rank), ctypes.byref(comm)), "dtfill_comm_create")
+        return comm.value
+
+    def allreduce_sums(self, comm: int, sums_ptr: int, n: int):
+        """In-place NCCL sum all-reduce of n float64 at the device pointer, enqueued on the handle's stream."""
+        _check(self._L.dtfill_allreduce_sums(self._h, ctypes.c_void_p(comm), _ptr(sums_ptr), int(n)), "dtfill_allreduce_sums")
+
+
+NCCL_ID_BYTES = 128
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+    _check(load().dtfill_nccl_unique_id(buf), "dtfill_nccl_unique_id")
+    return buf.raw
+
+
+def comm_destroy(comm: int):
+    if comm:
+        _check(load().dtfill_comm_destroy(ctypes.c_void_p(comm)), "dtfill_comm_destroy")
 
 
 _handles: dict[int, Handle] = {}

@@ -5,7 +5,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <string>
+#include <vector>
 
 #include "dtfill_kernels.cuh"
 
@@ -34,13 +42,85 @@ struct Buf {
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side of the numpy-in / numpy-out contract (tools.py:13-35 takes and returns ordinary pageable arrays).
+// A cudaMemcpyAsync from or to pageable memory is staged by the driver on the calling thread, one chunk at a time,
+// and serialises the sliced copy/compute pipeline of dtfill_run.  Pageable buffers are therefore staged here:
+// a small pool of threads copies a slice into a pinned mirror (and out of one), the DMA engines move pinned memory
+// in both directions, and the kernels of other slices run meanwhile.
+// ------------------------------------------------------------------------------------------------------------
+class CopyPool {
+public:
+    explicit CopyPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // dst[0..bytes) = src[0..bytes), split over the pool's threads and the caller; returns when done
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t grain = 2u << 20;
+        const size_t nparts = bytes / grain > 0 ? std::min<size_t>(bytes / grain, (th_.size() + 1) * 4) : 1;
+        if (nparts <= 1 || th_.empty()) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; nparts_ = nparts; next_ = 0; done_ = 0;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return done_ == nparts_; });
+        nparts_ = 0;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            size_t i;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (next_ >= nparts_) return;
+                i = next_++;
+            }
+            const size_t a = bytes_ * i / nparts_, b = bytes_ * (i + 1) / nparts_;
+            memcpy(dst_ + a, src_ + a, b - a);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (++done_ == nparts_) cv_done_.notify_all();
+        }
+    }
+    void loop() {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || next_ < nparts_; });
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, cv_done_;
+    bool stop_ = false;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, nparts_ = 0, next_ = 0, done_ = 0;
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
 // One "lane" = everything a call needs while it is in flight: workspace, streams, events.  A handle has two, so
 // that in pipelined mode (dtfill_set_pipeline_depth 2) the HBM-bound first stage of one call overlaps the ALU-bound
 // scan of the previous call.
 struct Lane {
-    static const int MAX_SUB = 8;
+    static const int MAX_SUB = 16;
     Buf srcbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
-    int* status_host = nullptr;          // pinned [2]
     cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
     cudaStream_t side[MAX_SUB] = {};     // narrow tiles run next to the full-width tasks of the same sub-batch
@@ -48,7 +128,6 @@ struct Lane {
     cudaStream_t pipe = nullptr;         // pipelined mode: the stream this lane's calls run on
     cudaEvent_t done = nullptr;          // ... and the end of its last call
     bool pending = false;                // done not yet waited for by the handle's stream
-    bool dirty = false;                  // status_host not yet examined by dtfill_status
     int last_launches = 0;
     int last_B = 0;
 };
@@ -62,6 +141,18 @@ struct dtfill_ctx {
     Lane lanes[MAX_LANES];
     int ncalls = 0;                   // calls enqueued so far (pipelined mode alternates lanes)
     int last_lane = 0;
+    // Outcome of every call since the last dtfill_status: call n copies its two status words (first bad frame, wide
+    // tasks) into slot n % STATUS_RING of a pinned ring that only the device writes after the host armed it, so no call's
+    // IndexError can be overwritten by a later call.  A slot still unexamined when the ring wraps is folded into
+    // `sticky_bad` after waiting for its call.
+    static const int STATUS_RING = 64;
+    int* status_ring = nullptr;       // pinned [STATUS_RING][2]
+    int* status_init = nullptr;       // pinned {INT_MAX, 0}: what every call's device status words start from
+    bool slot_dirty[STATUS_RING] = {};
+    cudaEvent_t slot_done[STATUS_RING] = {};
+    int sticky_bad = INT_MAX;
+    std::vector<void*> retired;       // device buffers replaced by larger ones; freed at the next synchronisation point
+    size_t wide_smem_configured = 0;  // dynamic shared memory limit of k2_chamfer_wide raised so far on this device
     bool cur_pipelined = false;       // the call being enqueued runs on a lane's own stream
     // input of the call being enqueued: float32 frames [B,H,W], or uint16 PNG samples [B,in_H,W] of which rows
     // [in_crop, in_crop + H) are the frame (dtfill_run_u16); lidar_dev: decoded float32 frames, optional
@@ -72,6 +163,11 @@ struct dtfill_ctx {
     cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums;
+    // pinned mirrors of pageable caller buffers (see CopyPool) and the threads that fill / drain them
+    PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar;
+    CopyPool* pool_in = nullptr;
+    CopyPool* pool_out = nullptr;
+    int stage_threads = -1;           // threads per direction; -1: automatic; 0: never stage (driver-staged copies)
     int32_t* counts_host = nullptr;   // pinned staging for out_counts (a pageable destination would serialise the
     size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
     bool profiling = false;
@@ -90,9 +186,8 @@ namespace {
 int ensure(dtfill_t* h, Buf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) {
-        (void)h;
-        CU(cudaDeviceSynchronize());
-        CU(cudaFree(b.p));
+        // work in flight may still use the old buffer: park it, dtfill_synchronize / dtfill_destroy free it
+        h->retired.push_back(b.p);
         b.p = nullptr;
         b.cap = 0;
     }
@@ -116,7 +211,31 @@ struct HostIO {
     int32_t* lbl = nullptr;
     uint8_t* mask = nullptr;
     int32_t* counts = nullptr;
+    // pinned mirrors for the buffers above that are pageable (nullptr: the caller's buffer is pinned, copy directly)
+    void* in_pin = nullptr;
+    float* lidar_pin = nullptr;
+    float* depth_pin = nullptr;
+    float* dt_pin = nullptr;
+    int32_t* lbl_pin = nullptr;
+    uint8_t* mask_pin = nullptr;
+    bool any_out_pin() const { return lidar_pin || depth_pin || dt_pin || lbl_pin || mask_pin; }
 };
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_pinned(PinBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = bytes + bytes / 16 + 4096;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(DTFILL_E_NOMEM, std::string("cudaHostAlloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+    b.cap = want;
+    return 0;
+}
 
 struct Plan {
     int ppl = 0;        // pixels per lane of the full-width instance; 0: 64-bit-key path only
@@ -314,14 +433,17 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
 
 // Enqueue the whole path on h->stream; all pointers are device pointers.
 int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, float val_thr, float* out_depth,
-            float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts, const HostIO* hio = nullptr) {
+            float* out_dt, int32_t* out_lbl, uint8_t* out_mask, int32_t* out_counts, const HostIO* hio = nullptr,
+            bool force_strict = false) {
     if (!h || !in || !out_depth) return fail(DTFILL_E_ARG, "dtfill_run: NULL handle, input or out_depth");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_run: B, H, W must be positive");
     if ((long)H + W >= 60000 || (long)H * W >= (1l << 31) || W > 28000)
         return fail(DTFILL_E_ARG, "dtfill_run: frame size not supported (H + W < 60000, W <= 28000)");
     CU(cudaSetDevice(h->device));
     // lane and stream of this call
-    const bool pipelined = h->pipeline_depth > 1 && !h->profiling && !hio;
+    // synchronous entries (dtfill_run*) always run in strict order on the handle's stream: their device-to-host copies
+    // and their status follow the kernels in stream order
+    const bool pipelined = h->pipeline_depth > 1 && !h->profiling && !hio && !force_strict;
     Lane* L = &h->lanes[pipelined ? (h->ncalls % h->pipeline_depth) : 0];
     h->cur_pipelined = pipelined;
     const Plan plan = make_plan(H, W);
@@ -347,11 +469,10 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     if ((rc = ensure(h, L->skykeys, (size_t)B * 2 * W * 4))) return rc;
     {
         const size_t smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
-        static size_t configured = 0;
         if (smem > 227 * 1024) return fail(DTFILL_E_ARG, "dtfill_run: frame too wide for the wide path");
-        if (smem > 48 * 1024 && smem > configured) {
+        if (smem > 48 * 1024 && smem > h->wide_smem_configured) {     // the attribute is per device: track it per handle
             CU(cudaFuncSetAttribute(k2_chamfer_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+            h->wide_smem_configured = smem;
         }
     }
 
@@ -368,63 +489,108 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
             if (o.pending) { CU(cudaStreamWaitEvent(h->stream, o.done, 0)); o.pending = false; }
     }
     int launches = 0;
-    L->status_host[0] = INT_MAX;
-    L->status_host[1] = 0;
-    CU(cudaMemcpyAsync(L->status.p, L->status_host, 8, cudaMemcpyHostToDevice, s));
+    // this call's slot of the status ring; a slot that dtfill_status has not examined yet keeps its verdict
+    const int slot = h->ncalls % dtfill_ctx::STATUS_RING;
+    if (h->slot_dirty[slot]) {
+        CU(cudaEventSynchronize(h->slot_done[slot]));
+        if (h->status_ring[2 * slot] < h->sticky_bad) h->sticky_bad = h->status_ring[2 * slot];
+        h->slot_dirty[slot] = false;
+    }
+    CU(cudaMemcpyAsync(L->status.p, h->status_init, 8, cudaMemcpyHostToDevice, s));
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
     // device-resident data: sub-batches do not pay (the scan is bound by per-task latency).  Host buffers: slices
     // pipeline the PCIe copies in both directions with the kernels.
-    if (nsub <= 0) nsub = hio ? (B >= 32 ? 8 : (B >= 4 ? 4 : 1)) : 1;
+    if (nsub <= 0) nsub = hio ? (B >= 64 ? 16 : (B >= 32 ? 8 : (B >= 4 ? 4 : 1))) : 1;
     if (nsub > Lane::MAX_SUB) nsub = Lane::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
     auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
         const size_t frame_bytes = h->in_u16 ? (size_t)h->in_H * W * 2 : (size_t)H * W * 4;
-        CU(cudaMemcpyAsync((char*)const_cast<void*>(in) + b0 * frame_bytes, (const char*)hio->in + b0 * frame_bytes,
-                           nb * frame_bytes, cudaMemcpyHostToDevice, st));
+        const char* src = (const char*)hio->in + b0 * frame_bytes;
+        if (hio->in_pin) {         // pageable input: this slice -> pinned mirror (pool threads), DMA from there
+            char* pin = (char*)hio->in_pin + b0 * frame_bytes;
+            h->pool_in->copy(pin, src, nb * frame_bytes);
+            src = pin;
+        }
+        CU(cudaMemcpyAsync((char*)const_cast<void*>(in) + b0 * frame_bytes, src, nb * frame_bytes, cudaMemcpyHostToDevice, st));
         return 0;
     };
     auto copy_out = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
         const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
-        CU(cudaMemcpyAsync(hio->depth + o, out_depth + o, n * 4, cudaMemcpyDeviceToHost, st));
-        if (hio->lidar) CU(cudaMemcpyAsync(hio->lidar + o, h->lidar_dev + o, n * 4, cudaMemcpyDeviceToHost, st));
-        if (hio->dt) CU(cudaMemcpyAsync(hio->dt + o, out_dt + o, n * 4, cudaMemcpyDeviceToHost, st));
-        if (hio->lbl) CU(cudaMemcpyAsync(hio->lbl + o, out_lbl + o, n * 4, cudaMemcpyDeviceToHost, st));
-        if (hio->mask) CU(cudaMemcpyAsync(hio->mask + o, out_mask + o, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync((hio->depth_pin ? hio->depth_pin : hio->depth) + o, out_depth + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->lidar) CU(cudaMemcpyAsync((hio->lidar_pin ? hio->lidar_pin : hio->lidar) + o, h->lidar_dev + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->dt) CU(cudaMemcpyAsync((hio->dt_pin ? hio->dt_pin : hio->dt) + o, out_dt + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->lbl) CU(cudaMemcpyAsync((hio->lbl_pin ? hio->lbl_pin : hio->lbl) + o, out_lbl + o, n * 4, cudaMemcpyDeviceToHost, st));
+        if (hio->mask) CU(cudaMemcpyAsync((hio->mask_pin ? hio->mask_pin : hio->mask) + o, out_mask + o, n, cudaMemcpyDeviceToHost, st));
         if (hio->counts)
             CU(cudaMemcpyAsync(hio->counts + 2 * (size_t)b0, out_counts + 2 * (size_t)b0, (size_t)nb * 8,
                                cudaMemcpyDeviceToHost, st));
         return 0;
     };
-    if (nsub == 1) {
+    if (nsub == 1 && !(hio && hio->any_out_pin())) {
         if ((rc = copy_in(s, 0, B))) return rc;
         if ((rc = enqueue_range(h, L, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
                                 out_counts, scratch_units_per_frame, 0, &launches))) return rc;
         if ((rc = copy_out(s, 0, B))) return rc;
     } else {
-        CU(cudaEventRecord(L->fork_ev, s));
-        for (int i = 0; i < nsub; ++i) {
-            const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
-            CU(cudaStreamWaitEvent(L->sub[i], L->fork_ev, 0));
-            if ((rc = copy_in(L->sub[i], b0, b1 - b0))) return rc;
-            if ((rc = enqueue_range(h, L, L->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
-                                    out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return rc;
-            if ((rc = copy_out(L->sub[i], b0, b1 - b0))) return rc;
-            CU(cudaEventRecord(L->join_ev[i], L->sub[i]));
-            CU(cudaStreamWaitEvent(s, L->join_ev[i], 0));
+        // pageable outputs: a drain thread waits for each slice's device-to-host copies and moves the slice from the
+        // pinned mirrors into the caller's arrays while the later slices are still being copied in and computed
+        std::atomic<int> enqueued{0};
+        std::atomic<bool> abort_drain{false};
+        std::thread drain;
+        const bool draining = hio && hio->any_out_pin();
+        if (draining) {
+            drain = std::thread([&, L] {
+                cudaSetDevice(h->device);
+                for (int i = 0; i < nsub; ++i) {
+                    while (enqueued.load(std::memory_order_acquire) <= i) {
+                        if (abort_drain.load()) return;
+                        std::this_thread::yield();
+                    }
+                    if (cudaEventSynchronize(L->join_ev[i]) != cudaSuccess) return;
+                    const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
+                    const size_t o = (size_t)b0 * H * W, n = (size_t)(b1 - b0) * H * W;
+                    if (hio->depth_pin) h->pool_out->copy(hio->depth + o, hio->depth_pin + o, n * 4);
+                    if (hio->lidar_pin) h->pool_out->copy(hio->lidar + o, hio->lidar_pin + o, n * 4);
+                    if (hio->dt_pin) h->pool_out->copy(hio->dt + o, hio->dt_pin + o, n * 4);
+                    if (hio->lbl_pin) h->pool_out->copy(hio->lbl + o, hio->lbl_pin + o, n * 4);
+                    if (hio->mask_pin) h->pool_out->copy(hio->mask + o, hio->mask_pin + o, n);
+                }
+            });
         }
+        auto body = [&]() -> int {
+            CU(cudaEventRecord(L->fork_ev, s));
+            for (int i = 0; i < nsub; ++i) {
+                const int b0 = (int)((long)B * i / nsub), b1 = (int)((long)B * (i + 1) / nsub);
+                CU(cudaStreamWaitEvent(L->sub[i], L->fork_ev, 0));
+                int r;
+                if ((r = copy_in(L->sub[i], b0, b1 - b0))) return r;
+                if ((r = enqueue_range(h, L, L->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
+                                       out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return r;
+                if ((r = copy_out(L->sub[i], b0, b1 - b0))) return r;
+                CU(cudaEventRecord(L->join_ev[i], L->sub[i]));
+                CU(cudaStreamWaitEvent(s, L->join_ev[i], 0));
+                enqueued.store(i + 1, std::memory_order_release);
+            }
+            return 0;
+        };
+        rc = body();
+        if (rc) abort_drain.store(true);
+        if (drain.joinable()) drain.join();
+        if (rc) return rc;
     }
-    CU(cudaMemcpyAsync(L->status_host, L->status.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->status_ring + 2 * slot, L->status.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(h->slot_done[slot], s));
+    h->slot_dirty[slot] = true;
     CU(cudaGetLastError());
     if (pipelined) {
         CU(cudaEventRecord(L->done, s));
         L->pending = true;
     }
-    L->dirty = true;
     L->last_launches = launches;
     L->last_B = B;
     h->last_lane = (int)(L - h->lanes);
@@ -461,10 +627,12 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     h->stream = h->own_stream;
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&h->pipe_fork, cudaEventDisableTiming));
+    CU(cudaHostAlloc((void**)&h->status_ring, dtfill_ctx::STATUS_RING * 8 + 8, cudaHostAllocDefault));
+    h->status_init = h->status_ring + 2 * dtfill_ctx::STATUS_RING;
+    h->status_init[0] = INT_MAX;
+    h->status_init[1] = 0;
+    for (auto& e : h->slot_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (Lane& L : h->lanes) {
-        CU(cudaHostAlloc((void**)&L.status_host, 16, cudaHostAllocDefault));
-        L.status_host[0] = INT_MAX;
-        L.status_host[1] = 0;
         CU(cudaStreamCreateWithFlags(&L.pipe, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&L.fork_ev, cudaEventDisableTiming));
@@ -481,6 +649,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_MAX_COL_TILES")) h->max_col_tiles = atoi(e);
     if (const char* e = getenv("DTFILL_SKY_MIN")) h->sky_min = atoi(e) < -1 ? -1 : atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
+    if (const char* e = getenv("DTFILL_STAGE_THREADS")) h->stage_threads = atoi(e);
     if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
         const int d = atoi(e);
         h->pipeline_depth = d < 1 ? 1 : (d > dtfill_ctx::MAX_LANES ? dtfill_ctx::MAX_LANES : d);
@@ -495,10 +664,9 @@ void dtfill_destroy(dtfill_t* h) {
     cudaDeviceSynchronize();
     for (Lane& L : h->lanes) {
         Buf* lb[] = {&L.srcbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
-                     &L.scratch, &L.tasks, &L.status};
+                     &L.scratch, &L.tasks, &L.status, &L.sky, &L.skykeys};
         for (Buf* b : lb)
             if (b->p) cudaFree(b->p);
-        if (L.status_host) cudaFreeHost(L.status_host);
         if (L.fork_ev) cudaEventDestroy(L.fork_ev);
         if (L.done) cudaEventDestroy(L.done);
         if (L.pipe) cudaStreamDestroy(L.pipe);
@@ -510,11 +678,19 @@ void dtfill_destroy(dtfill_t* h) {
             if (L.side[i]) cudaStreamDestroy(L.side[i]);
         }
     }
-    Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->gt_dev,
-                   &h->partial, &h->per_frame, &h->sums};
+    Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->lidar_out_dev,
+                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
+    for (void* q : h->retired) cudaFree(q);
     if (h->counts_host) cudaFreeHost(h->counts_host);
+    delete h->pool_in;
+    delete h->pool_out;
+    for (PinBuf* b : {&h->pin_in, &h->pin_depth, &h->pin_dt, &h->pin_lbl, &h->pin_mask, &h->pin_lidar})
+        if (b->p) cudaFreeHost(b->p);
+    if (h->status_ring) cudaFreeHost(h->status_ring);
+    for (auto& e : h->slot_done)
+        if (e) cudaEventDestroy(e);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->pipe_fork) cudaEventDestroy(h->pipe_fork);
@@ -555,6 +731,10 @@ int dtfill_synchronize(dtfill_t* h) {
     int rc = dtfill_flush(h);
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
+    if (!h->retired.empty()) {            // buffers outgrown by an earlier call: nothing in flight uses them any more
+        for (void* q : h->retired) cudaFree(q);
+        h->retired.clear();
+    }
     return 0;
 }
 
@@ -570,10 +750,14 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
     int rc = dtfill_synchronize(h);
     if (rc) return rc;
     if (kernel_launches) *kernel_launches = h->lanes[h->last_lane].last_launches;
-    // calls examined: every one since the previous dtfill_status (one per lane at most in pipelined mode)
-    int bad = INT_MAX;
-    for (Lane& L : h->lanes)
-        if (L.dirty) { bad = L.status_host[0] < bad ? L.status_host[0] : bad; L.dirty = false; }
+    // calls examined: every one since the previous dtfill_status (each has its own slot of the status ring)
+    int bad = h->sticky_bad;
+    h->sticky_bad = INT_MAX;
+    for (int i = 0; i < dtfill_ctx::STATUS_RING; ++i)
+        if (h->slot_dirty[i]) {
+            if (h->status_ring[2 * i] < bad) bad = h->status_ring[2 * i];
+            h->slot_dirty[i] = false;
+        }
     if (first_bad_frame) *first_bad_frame = (bad == INT_MAX) ? -1 : bad;
     if (bad != INT_MAX)
         return fail(DTFILL_E_INDEX, "frame " + std::to_string(bad) +
@@ -622,6 +806,27 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
     if (pipelined) {
         HostIO hio;
         hio.in = in; hio.lidar = out_lidar; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask;
+        // pageable buffers go through pinned mirrors (DTFILL_STAGE_THREADS=0 / dtfill_set_stage_threads(h, 0): never)
+        if (h->stage_threads != 0) {
+            const bool pin_i = is_pageable(in);
+            const bool pin_d = is_pageable(out_depth), pin_t = out_dt && is_pageable(out_dt);
+            const bool pin_l = out_lbl && is_pageable(out_lbl), pin_m = out_mask && is_pageable(out_mask);
+            const bool pin_x = out_lidar && is_pageable(out_lidar);
+            if (pin_i || pin_d || pin_t || pin_l || pin_m || pin_x) {
+                if (!h->pool_in) {
+                    int n = h->stage_threads;
+                    if (n < 0) { n = (int)std::thread::hardware_concurrency() / 4; n = n < 2 ? 2 : (n > 8 ? 8 : n); }
+                    h->pool_in = new CopyPool(n - 1);       // the calling thread works too
+                    h->pool_out = new CopyPool(n - 1);
+                }
+                if (pin_i) { if ((rc = ensure_pinned(h->pin_in, in_bytes))) return rc; hio.in_pin = h->pin_in.p; }
+                if (pin_d) { if ((rc = ensure_pinned(h->pin_depth, npx * 4))) return rc; hio.depth_pin = (float*)h->pin_depth.p; }
+                if (pin_t) { if ((rc = ensure_pinned(h->pin_dt, npx * 4))) return rc; hio.dt_pin = (float*)h->pin_dt.p; }
+                if (pin_l) { if ((rc = ensure_pinned(h->pin_lbl, npx * 4))) return rc; hio.lbl_pin = (int32_t*)h->pin_lbl.p; }
+                if (pin_m) { if ((rc = ensure_pinned(h->pin_mask, npx))) return rc; hio.mask_pin = (uint8_t*)h->pin_mask.p; }
+                if (pin_x) { if ((rc = ensure_pinned(h->pin_lidar, npx * 4))) return rc; hio.lidar_pin = (float*)h->pin_lidar.p; }
+            }
+        }
         if (out_counts) {
             if (h->counts_host_cap < (size_t)B * 2) {
                 if (h->counts_host) cudaFreeHost(h->counts_host);
@@ -632,12 +837,12 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
             }
             hio.counts = h->counts_host;
         }
-        if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc, &hio))) return rc;
+        if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc, &hio, true))) return rc;
         rc = dtfill_status(h, first_bad_frame, nullptr);
         if (out_counts && (rc == 0 || rc == DTFILL_E_INDEX)) memcpy(out_counts, h->counts_host, (size_t)B * 8);
         return rc;
     }
-    if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc))) return rc;
+    if ((rc = enqueue(h, in_d, B, H, W, src_thr, val_thr, od, odt, ol, om, oc, nullptr, true))) return rc;
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out_depth, od, npx * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out_lidar) CU(cudaMemcpyAsync(out_lidar, olid, npx * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -690,7 +895,14 @@ int dtfill_run_u16_async(dtfill_t* h, const uint16_t* in_dev, int B, int H_in, i
 
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device, int B, int H, int W,
                    int mode, double* per_frame, double* sums, int out_is_device) {
+    return dtfill_metrics_ex(h, pred, gt, gt_is_f64, in_is_device, B, H, W, mode, per_frame, sums, out_is_device, 0);
+}
+
+int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device, int B, int H, int W,
+                      int mode, double* per_frame, double* sums, int out_is_device, int accumulate) {
     if (!h || !pred || !gt) return fail(DTFILL_E_ARG, "dtfill_metrics: NULL handle or input");
+    if (accumulate && !(out_is_device && sums))
+        return fail(DTFILL_E_ARG, "dtfill_metrics_ex: accumulate needs a device-resident sums vector");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_metrics: B, H, W must be positive");
     if (mode != DTFILL_METRICS_KITTI && mode != DTFILL_METRICS_NYU) return fail(DTFILL_E_ARG, "dtfill_metrics: bad mode");
     CU(cudaSetDevice(h->device));
@@ -728,7 +940,7 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
         if (mode == 0) k4_metrics_partial<float, 0><<<grid, 256, 0, s>>>(p_d, (const float*)g_d, npx, chunks, part);
         else k4_metrics_partial<float, 1><<<grid, 256, 0, s>>>(p_d, (const float*)g_d, npx, chunks, part);
     }
-    k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, mode, pf_d, sm_d);
+    k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, mode, pf_d, sm_d, accumulate);
     CU(cudaGetLastError());
     if (!out_is_device) {
         if (per_frame) CU(cudaMemcpyAsync(per_frame, pf_d, (size_t)B * 9 * 8, cudaMemcpyDeviceToHost, s));
@@ -773,6 +985,16 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n) {
 int dtfill_set_subbatches(dtfill_t* h, int n) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_subbatches: NULL handle");
     h->nsub = n;
+    return 0;
+}
+
+int dtfill_set_stage_threads(dtfill_t* h, int threads) {
+    if (!h || threads < -1 || threads > 64) return fail(DTFILL_E_ARG, "dtfill_set_stage_threads: NULL handle or thread count outside -1..64");
+    if (threads != h->stage_threads) {
+        delete h->pool_in; delete h->pool_out;
+        h->pool_in = h->pool_out = nullptr;
+        h->stage_threads = threads;
+    }
     return 0;
 }
 
@@ -894,6 +1116,95 @@ int dtfill_host_alloc(void** out_ptr, size_t bytes) {
 
 void dtfill_host_free(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// The one collective of the path: an NCCL sum all-reduce of the running metric totals, issued on
+// the handle's stream right behind k4_metrics_final.  libnccl is resolved at run time (dlopen of "libnccl.so.2":
+// the copy a host framework already loaded is found first), so the library itself has no link-time dependency.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ struct Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct Id128 { char b[128]; };
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return 0;
+    const char* names[] = {getenv("DTFILL_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names)
+        if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) return fail(DTFILL_E_CUDA, std::string("dtfill: cannot load libnccl.so.2 (") + dlerror() + ")");
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(DTFILL_E_CUDA, "dtfill: libnccl lacks ncclGetUniqueId / ncclCommInitRank / ncclAllReduce");
+    g_nccl.lib = lib;
+    return 0;
+}
+
+int nccl_fail(const char* what, int rc) {
+    return fail(DTFILL_E_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error") +
+                                   " (" + std::to_string(rc) + ")");
+}
+
+}  // namespace
+
+extern "C" {
+
+int dtfill_nccl_unique_id(void* out_id) {
+    if (!out_id) return fail(DTFILL_E_ARG, "dtfill_nccl_unique_id: NULL out_id");
+    int rc = nccl_load();
+    if (rc) return rc;
+    rc = g_nccl.GetUniqueId(out_id);
+    return rc ? nccl_fail("ncclGetUniqueId", rc) : 0;
+}
+
+int dtfill_comm_create(dtfill_t* h, const void* id, int nranks, int rank, void** out_comm) {
+    if (!h || !id || !out_comm || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(DTFILL_E_ARG, "dtfill_comm_create: bad argument");
+    *out_comm = nullptr;
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    Id128 u;
+    memcpy(u.b, id, sizeof(u.b));
+    rc = g_nccl.CommInitRank(out_comm, nranks, u, rank);
+    return rc ? nccl_fail("ncclCommInitRank", rc) : 0;
+}
+
+int dtfill_comm_destroy(void* comm) {
+    if (!comm) return 0;
+    int rc = nccl_load();
+    if (rc) return rc;
+    rc = g_nccl.CommDestroy(comm);
+    return rc ? nccl_fail("ncclCommDestroy", rc) : 0;
+}
+
+int dtfill_allreduce_sums(dtfill_t* h, void* nccl_comm, double* sums_dev, int n) {
+    if (!h || !nccl_comm || !sums_dev || n <= 0) return fail(DTFILL_E_ARG, "dtfill_allreduce_sums: bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if ((rc = dtfill_flush(h))) return rc;
+    // in place, float64 sum, on the stream the metric kernels ran on: stream order is the only synchronisation
+    rc = g_nccl.AllReduce(sums_dev, sums_dev, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, h->stream);
+    return rc ? nccl_fail("ncclAllReduce", rc) : 0;
 }
 
 }  // extern "C"

@@ -137,8 +137,105 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
     rank = r.base + r.pre + __popc(r.a & ((1u << sh) - 1u)) + 1u;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// The 7 (forward) / 1 + 7 (backward) candidates of a pixel.  All candidates are full keys with distinct order
+// fields, so their minimum is OpenCV's "first strictly smaller candidate wins" however it is grouped.  The ALU pipe
+// (VIADDMNMX, VIMNMX3, LOP3: one warp instruction per 2 cycles and SM sub-partition) is what the scan saturates;
+// the FMA pipe (IMAD) runs beside it at the same rate (profiles/ubench/pipes.cu: 3.8 warp instructions per clock
+// and SM for a 1:1 mix against 1.9 for either alone).  DTFILL_STENCIL chooses how many of the additions are plain
+// IMADs whose results meet in a 3-input minimum:
+//   0: 1 IMAD + 6 VIADDMNMX                    (forward; backward 7 VIADDMNMX)
+//   1: 3 IMAD + 4 VIADDMNMX + 1 VIMNMX3        (backward 2 IMAD + 5 VIADDMNMX + 1 VIMNMX3)
+//   2: 5 IMAD + 2 VIADDMNMX + 2 VIMNMX3        (backward 4 IMAD + 3 VIADDMNMX + 2 VIMNMX3)
+//   3: 7 IMAD + 3 VIMNMX3                      (backward 6 IMAD + 1 VIADDMNMX + 3 VIMNMX3)
+// ------------------------------------------------------------------------------------------------------
+#ifndef DTFILL_STENCIL
+#define DTFILL_STENCIL 1
+#endif
+#ifndef DTFILL_SPLITSCAN
+#define DTFILL_SPLITSCAN 1
+#endif
+#ifndef DTFILL_FAKE_SCRATCH_DIV
+#define DTFILL_FAKE_SCRATCH_DIV 1   // > 1: timing experiment only (part of the forward state is dropped: wrong results)
+#endif
+#ifndef DTFILL_K2_WARPS
+#define DTFILL_K2_WARPS 20      // resident warps per SM the PPL = 20 instance is compiled for (register budget)
+#endif
+
+template <int PPL>
+__device__ __forceinline__ uint32_t stencil_fwd(const Row<PPL>& A /*row y-1*/, const Row<PPL>& Bq /*row y-2*/, int i, uint32_t one)
+{
+    const uint32_t b0 = at(Bq, i - 1), b1 = at(Bq, i + 1);
+    const uint32_t a0 = at(A, i - 2), a1 = at(A, i - 1), a2 = at(A, i), a3 = at(A, i + 1), a4 = at(A, i + 2);
+    // OpenCV's order: (-2,-1) (-2,+1) (-1,-2) (-1,-1) (-1,0) (-1,+1) (-1,+2); orders 0,2,..,12 (even: see header)
+#if DTFILL_STENCIL == 0
+    uint32_t m = b0 * one + KC(3, 0);
+    m = __viaddmin_u32(b1, KC(3, 2), m);
+    m = __viaddmin_u32(a0, KC(3, 4), m);
+    m = __viaddmin_u32(a1, KC(2, 6), m);
+    m = __viaddmin_u32(a2, KC(1, 8), m);
+    m = __viaddmin_u32(a3, KC(2, 10), m);
+    m = __viaddmin_u32(a4, KC(3, 12), m);
+    return m;
+#elif DTFILL_STENCIL == 1
+    const uint32_t m0 = __viaddmin_u32(b1, KC(3, 2), b0 * one + KC(3, 0));
+    const uint32_t m1 = __viaddmin_u32(a1, KC(2, 6), a0 * one + KC(3, 4));
+    uint32_t m2 = __viaddmin_u32(a3, KC(2, 10), a2 * one + KC(1, 8));
+    m2 = __viaddmin_u32(a4, KC(3, 12), m2);
+    return __vimin3_u32(m0, m1, m2);
+#elif DTFILL_STENCIL == 2
+    const uint32_t p = __vimin3_u32(b0 * one + KC(3, 0), b1 * one + KC(3, 2), a0 * one + KC(3, 4));
+    const uint32_t q = __viaddmin_u32(a1, KC(2, 6), a2 * one + KC(1, 8));
+    const uint32_t r = __viaddmin_u32(a3, KC(2, 10), a4 * one + KC(3, 12));
+    return __vimin3_u32(p, q, r);
+#else
+    const uint32_t p = __vimin3_u32(b0 * one + KC(3, 0), b1 * one + KC(3, 2), a0 * one + KC(3, 4));
+    const uint32_t q = __vimin3_u32(a1 * one + KC(2, 6), a2 * one + KC(1, 8), a3 * one + KC(2, 10));
+    return __vimin3_u32(p, q, a4 * one + KC(3, 12));
+#endif
+}
+
+template <int PPL>
+__device__ __forceinline__ uint32_t stencil_bwd(uint32_t own /*forward key, order <= 1*/, const Row<PPL>& A /*row y+1*/,
+                                                const Row<PPL>& Bq /*row y+2*/, int i, uint32_t one)
+{
+    const uint32_t b0 = at(Bq, i + 1), b1 = at(Bq, i - 1);
+    const uint32_t a0 = at(A, i + 2), a1 = at(A, i + 1), a2 = at(A, i), a3 = at(A, i - 1), a4 = at(A, i - 2);
+    // own value first, then (+2,+1) (+2,-1) (+1,+2) (+1,+1) (+1,0) (+1,-1) (+1,-2); orders 2,4,..,14
+#if DTFILL_STENCIL == 0
+    uint32_t m = own;
+    m = __viaddmin_u32(b0, KC(3, 2), m);
+    m = __viaddmin_u32(b1, KC(3, 4), m);
+    m = __viaddmin_u32(a0, KC(3, 6), m);
+    m = __viaddmin_u32(a1, KC(2, 8), m);
+    m = __viaddmin_u32(a2, KC(1, 10), m);
+    m = __viaddmin_u32(a3, KC(2, 12), m);
+    m = __viaddmin_u32(a4, KC(3, 14), m);
+    return m;
+#elif DTFILL_STENCIL == 1
+    uint32_t m0 = __viaddmin_u32(b0, KC(3, 2), own);
+    m0 = __viaddmin_u32(b1, KC(3, 4), m0);
+    const uint32_t m1 = __viaddmin_u32(a1, KC(2, 8), a0 * one + KC(3, 6));
+    uint32_t m2 = __viaddmin_u32(a3, KC(2, 12), a2 * one + KC(1, 10));
+    m2 = __viaddmin_u32(a4, KC(3, 14), m2);
+    return __vimin3_u32(m0, m1, m2);
+#elif DTFILL_STENCIL == 2
+    const uint32_t p = __vimin3_u32(own, b0 * one + KC(3, 2), b1 * one + KC(3, 4));
+    const uint32_t q = __viaddmin_u32(a1, KC(2, 8), a0 * one + KC(3, 6));
+    uint32_t r = __viaddmin_u32(a3, KC(2, 12), a2 * one + KC(1, 10));
+    r = __viaddmin_u32(a4, KC(3, 14), r);
+    return __vimin3_u32(p, q, r);
+#else
+    const uint32_t p = __vimin3_u32(own, b0 * one + KC(3, 2), b1 * one + KC(3, 4));
+    const uint32_t q = __vimin3_u32(a0 * one + KC(3, 6), a1 * one + KC(2, 8), a2 * one + KC(1, 10));
+    const uint32_t r = __viaddmin_u32(a4, KC(3, 14), a3 * one + KC(2, 12));
+    return __vimin3_u32(p, q, r);
+#endif
+}
+
 template <int PPL, bool PAD, bool WANT_LBL, bool VEC>
-__global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
+__global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_WARPS : 32))) k2_chamfer(FrameParams fp, Workspace ws, float* __restrict__ out_depth,
                                                   float* __restrict__ out_dt, int32_t* __restrict__ out_lbl, int my_kind)
 {
     // Transposition buffer for the keys of an output row.  Keeping shared memory small matters: what is left of the
@@ -191,16 +288,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
         }
         uint32_t c[PPL];
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) {
-            uint32_t m = at(Bq, i - 1) * fp.one + KC(3, 0);              // (-2,-1) cost 3 (IMAD: FMA pipe)
-            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 2), m);              // (-2,+1) cost 3
-            m = __viaddmin_u32(at(A, i - 2), KC(3, 4), m);               // (-1,-2) cost 3
-            m = __viaddmin_u32(at(A, i - 1), KC(2, 6), m);               // (-1,-1) cost 2
-            m = __viaddmin_u32(at(A, i), KC(1, 8), m);                   // (-1, 0) cost 1
-            m = __viaddmin_u32(at(A, i + 1), KC(2, 10), m);              // (-1,+1) cost 2
-            m = __viaddmin_u32(at(A, i + 2), KC(3, 12), m);              // (-1,+2) cost 3
-            c[i] = m;
-        }
+        for (int i = 0; i < PPL; ++i) c[i] = stencil_fwd<PPL>(A, Bq, i, fp.one);
         if (__any_sync(0xffffffffu, bits != 0)) {                         // sources: dist 0, own raster rank
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
@@ -210,6 +298,29 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
             }
         }
         // in-lane scan: T[x] = min(c[x], T[x-1] + 1); the left neighbour is OpenCV's last candidate (order 14)
+#if DTFILL_SPLITSCAN
+        // two independent half-lane chains (twice the instruction-level parallelism of one chain of PPL dependent
+        // steps), joined afterwards: a value entering the second half from the first is one more "left" candidate
+        // (order 1, loses ties against anything the second half holds itself)
+        constexpr int HF = PPL / 2;
+        uint32_t u = c[0] & ORDCLR, u2 = c[HF] & ORDCLR;
+        c[0] = u; c[HF] = u2;
+#pragma unroll
+        for (int i = 1; i < PPL - HF; ++i) {
+            if (i < HF) { u = __viaddmin_u32(u, KC(1, 14), c[i]) & ORDCLR; c[i] = u; }
+            u2 = __viaddmin_u32(u2, KC(1, 14), c[HF + i]) & ORDCLR; c[HF + i] = u2;
+        }
+        const uint32_t e = __viaddmin_u32(u | (1u << OSH), uint32_t(PPL - HF) << DSH, u2) & ORDCLR;    // lane's last column
+        const uint32_t cin = lane_carry<PPL, +1>(e, lane, clamp_dist);
+        const uint32_t cin2 = __viaddmin_u32(cin, uint32_t(HF) << DSH, u) | (1u << OSH);               // column HF-1, final
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t t = i < HF ? __viaddmin_u32(cin, uint32_t(i + 1) << DSH, c[i])
+                                : __viaddmin_u32(cin2, uint32_t(i - HF + 1) << DSH, c[i]);   // order bit 0/1 stays (see header)
+            if (PAD && x0 + i >= W) t = init_key;
+            Bq.v[i] = t;
+        }
+#else
         uint32_t u = c[0] & ORDCLR;
         c[0] = u;
 #pragma unroll
@@ -224,13 +335,14 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
             if (PAD && x0 + i >= W) t = init_key;
             Bq.v[i] = t;
         }
+#endif
         refresh_halo(Bq, lane, init_key);
         // forward state -> scratch, [vector j][lane] so that every store instruction is fully coalesced; the rows of
         // the upper halo are never read back (the backward pass ends at r0)
         if (y >= task.r0) {
             char* dst = reinterpret_cast<char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
-            for (int j = 0; j < PPL / VW; ++j) {
+            for (int j = 0; j < PPL / VW / DTFILL_FAKE_SCRATCH_DIV; ++j) {
                 if (VW == 4) st_scratch_v4(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3]);
                 else st_scratch_v2(dst + j * 256, Bq.v[2 * j], Bq.v[2 * j + 1]);
             }
@@ -271,7 +383,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
         if (y >= task.fstart && y >= task.lo) {
             const char* src = reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
-            for (int j = 0; j < PPL / VW; ++j) {
+            for (int j = 0; j < PPL / VW / DTFILL_FAKE_SCRATCH_DIV; ++j) {
                 if (VW == 4) cp_async16_l2only(fwdbuf_lane + j * 512, src + j * 512);
                 else cp_async8(fwdbuf_lane + j * 256, src + j * 256);
             }
@@ -291,7 +403,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
     issue_fwd_row(task.hi - 1);
 
     auto bwd_step = [&](const Row<PPL>& A /*row y+1*/, Row<PPL>& Bq /*row y+2 in, row y out*/, int y) {
-        if (lane < PPL && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
+        if (lane < PPL / DTFILL_FAKE_SCRATCH_DIV && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(scr) +
                                                           (long)(y - 3 - task.lo) * (128 * PPL) + lane * 128));
         if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
@@ -313,18 +425,27 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
             for (int i = 0; i < PPL; ++i) c[i] = init_key;      // rows the forward pass skipped: unreached
         }
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) {
-            uint32_t m = c[i];                                            // own forward value first (order <= 1)
-            m = __viaddmin_u32(at(Bq, i + 1), KC(3, 2), m);              // (+2,+1)
-            m = __viaddmin_u32(at(Bq, i - 1), KC(3, 4), m);              // (+2,-1)
-            m = __viaddmin_u32(at(A, i + 2), KC(3, 6), m);               // (+1,+2)
-            m = __viaddmin_u32(at(A, i + 1), KC(2, 8), m);               // (+1,+1)
-            m = __viaddmin_u32(at(A, i), KC(1, 10), m);                  // (+1, 0)
-            m = __viaddmin_u32(at(A, i - 1), KC(2, 12), m);              // (+1,-1)
-            m = __viaddmin_u32(at(A, i - 2), KC(3, 14), m);              // (+1,-2)
-            c[i] = m & ORDCLR;
-        }
+        for (int i = 0; i < PPL; ++i) c[i] = stencil_bwd<PPL>(c[i], A, Bq, i, fp.one) & ORDCLR;
         issue_fwd_row(y - 1);                        // A(y-1): fwdbuf has been consumed above
+#if DTFILL_SPLITSCAN
+        constexpr int HF = PPL / 2;                  // chains over columns [HF, PPL) and [0, HF), both right to left
+        uint32_t u = c[PPL - 1], u2 = c[HF - 1];
+#pragma unroll
+        for (int i = 1; i < PPL - HF; ++i) {
+            u = __viaddmin_u32(u, KC(1, 1), c[PPL - 1 - i]) & ORDCLR; c[PPL - 1 - i] = u;     // right neighbour is compared last
+            if (i < HF) { u2 = __viaddmin_u32(u2, KC(1, 1), c[HF - 1 - i]) & ORDCLR; c[HF - 1 - i] = u2; }
+        }
+        const uint32_t e = __viaddmin_u32(u | (1u << OSH), uint32_t(HF) << DSH, u2) & ORDCLR;          // lane's first column
+        const uint32_t cin = lane_carry<PPL, -1>(e, lane, clamp_dist);
+        const uint32_t cin2 = __viaddmin_u32(cin, uint32_t(PPL - HF) << DSH, u) | (1u << OSH);         // column HF, final
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            uint32_t t = i >= HF ? __viaddmin_u32(cin, uint32_t(PPL - i) << DSH, c[i])
+                                 : __viaddmin_u32(cin2, uint32_t(HF - i) << DSH, c[i]);     // order bit 0/1 stays
+            if (PAD && x0 + i >= W) t = init_key;
+            Bq.v[i] = t;
+        }
+#else
         uint32_t u = c[PPL - 1];
 #pragma unroll
         for (int i = PPL - 2; i >= 0; --i) {
@@ -338,6 +459,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? 20 : 32))) 
             if (PAD && x0 + i >= W) t = init_key;
             Bq.v[i] = t;
         }
+#endif
         refresh_halo(Bq, lane, init_key);
 
         // ---- output of row y: keys -> shared memory (transpose), then per lane 4 consecutive pixels per group:

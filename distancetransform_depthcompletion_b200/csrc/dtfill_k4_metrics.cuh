@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k4_metrics_partial(const float* __restric
 // one block; thread t handles frames t, t+blockDim, ...; then a fixed-order column sum
 __global__ void __launch_bounds__(256) k4_metrics_final(const double* __restrict__ partial, int B, int chunks, int mode,
                                                          double* __restrict__ per_frame /*[B][9]*/,
-                                                         double* __restrict__ sums /*[10]*/)
+                                                         double* __restrict__ sums /*[10]*/, int accumulate)
 {
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         double a[ACC];
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256) k4_metrics_final(const double* __restrict
             for (int b = 0; b < B; ++b) s += per_frame[(long)b * 9 + threadIdx.x];
         else
             s = (double)B;
-        sums[threadIdx.x] = s;
+        // accumulate: running totals of an evaluation loop (eval.py:212-232), one fixed-order addition per batch
+        sums[threadIdx.x] = accumulate ? sums[threadIdx.x] + s : s;
     }
 }
 

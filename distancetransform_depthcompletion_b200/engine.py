@@ -76,16 +76,18 @@ class DTFillEngine:
         """Synchronise; (first_bad_frame or -1, kernel launches of the last fill)."""
         return self.handle.status()
 
-    def metrics(self, pred, gt, mode: int = _lib.METRICS_KITTI):
-        """pred float32 [B,H,W], gt float32/float64 [B,H,W] CUDA tensors -> (per_frame [B,9], sums [10]) CUDA f64."""
+    def metrics(self, pred, gt, mode: int = _lib.METRICS_KITTI, totals=None):
+        """pred float32 [B,H,W], gt float32/float64 [B,H,W] CUDA tensors -> (per_frame [B,9], sums [10]) CUDA f64.
+        totals: float64 CUDA tensor [10] of running totals; this batch's sums are ADDED to it on the device
+        (eval.py:212-232) and it is returned in place of sums."""
         torch = self.torch
         assert pred.is_cuda and gt.is_cuda and pred.is_contiguous() and gt.is_contiguous() and pred.shape == gt.shape
         assert pred.dtype == torch.float32 and gt.dtype in (torch.float32, torch.float64)
         B = pred.shape[0]
         n = pred[0].numel()
         per_frame = torch.empty((B, _lib.METRIC_COLS), dtype=torch.float64, device=pred.device)
-        sums = torch.empty((_lib.METRIC_COLS + 1,), dtype=torch.float64, device=pred.device)
+        sums = totals if totals is not None else torch.empty((_lib.METRIC_COLS + 1,), dtype=torch.float64, device=pred.device)
         self._bind_stream()
         self.handle.metrics(pred.data_ptr(), gt.data_ptr(), B, 1, n, mode, gt.dtype == torch.float64, on_device=True,
-                            per_frame_ptr=per_frame.data_ptr(), sums_ptr=sums.data_ptr())
+                            per_frame_ptr=per_frame.data_ptr(), sums_ptr=sums.data_ptr(), accumulate=totals is not None)
         return per_frame, sums

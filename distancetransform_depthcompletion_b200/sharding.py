@@ -26,6 +26,35 @@ def allreduce_sums(sums, group=None):
     return sums
 
 
+class MetricsComm:
+    """The NCCL communicator behind dtfill_allreduce_sums (include/dtfill.h), one rank per process / GPU.
+
+    Rank 0 draws the ncclUniqueId, torch.distributed (any backend, it only carries 128 bytes) hands it to the other
+    ranks, every rank calls ncclCommInitRank through the C ABI.  ``allreduce(engine, sums)`` then enqueues the
+    float64 sum all-reduce of the totals vector on the engine's stream, right behind the metric kernels."""
+
+    def __init__(self, handle, rank: int, world: int, group=None):
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.world = int(rank), int(world)
+        ident = [_lib.nccl_unique_id() if rank == 0 else None]
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(ident, src=0, group=group)
+        self.comm = handle.comm_create(ident[0], world, rank)
+
+    def allreduce(self, engine, sums):
+        """sums: float64 CUDA tensor (the running totals, e.g. the 10 columns of dtfill_metrics); in place."""
+        engine._bind_stream()
+        engine.handle.allreduce_sums(self.comm, sums.data_ptr(), sums.numel())
+        return sums
+
+    def close(self):
+        if self.comm:
+            self._lib.comm_destroy(self.comm)
+            self.comm = 0
+
+
 def finalize_means(sums) -> dict:
     """Mean of per-frame metrics from the all-reduced totals [mse, rmse, mae, irmse, imae, d1, d2, d3, count, n]."""
     s = np.asarray(sums.detach().cpu() if hasattr(sums, "detach") else sums, dtype=np.float64)

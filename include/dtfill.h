@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTFILL_ABI_VERSION 2      /* 2: dtfill_run_u16(_async), dtfill_dt_pool_ex, dtfill_set_sky_min, 5 kernel times */
+#define DTFILL_ABI_VERSION 3      /* 3: dtfill_metrics_ex, dtfill_allreduce_sums + dtfill_comm_*, status ring */
 
 enum {
     DTFILL_OK = 0,
@@ -108,8 +108,10 @@ int dtfill_run_u16_async(dtfill_t* h, const uint16_t* in_dev, int B, int H_in, i
                          float* out_lidar_dev, float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev,
                          uint8_t* out_mask_dev, int32_t* out_counts_dev);
 
-/* Synchronise and report the outcome of the last dtfill_run_async: DTFILL_OK or DTFILL_E_INDEX
- * (with *first_bad_frame set).  *kernel_launches receives the number of kernels launched by that call. */
+/* Synchronise and report the outcome of EVERY dtfill_run_async / dtfill_run_u16_async since the previous dtfill_status:
+ * DTFILL_OK, or DTFILL_E_INDEX with *first_bad_frame = the smallest frame index (within its call) that any of those
+ * calls flagged.  Each call owns a slot of a status ring, so no call's verdict is lost however many calls are in
+ * flight or how deep the pipeline is.  *kernel_launches receives the number of kernels launched by the last call. */
 int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
 
 /*
@@ -125,6 +127,29 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches);
  */
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                    int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device);
+
+/* dtfill_metrics with running totals: accumulate != 0 adds this batch's column sums and frame count to the device
+ * vector `sums` (out_is_device required) instead of overwriting it -- the `+=` of eval.py:212-232 /
+ * eval_NYU.py:207-229, one batch per call, no host synchronisation. */
+int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
+                      int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device,
+                      int accumulate);
+
+/*
+ * Multi-GPU: frames shard contiguously over one process per GPU with no data-path exchange; the only
+ * collective is a sum all-reduce of the metric totals {sum rmse_f, sum mae_f, ..., n_frames} (mean-of-per-frame-metrics
+ * rule of eval.py:212-232, 252-259).  dtfill_allreduce_sums issues ncclAllReduce(sum, float64, in place) over `n`
+ * doubles at the device pointer `sums_dev` on the handle's stream, i.e. right behind the kernels of dtfill_metrics(_ex)
+ * that produced them; nothing is synchronised on the host.  `nccl_comm` is an ncclComm_t: one the caller already owns,
+ * or one made by dtfill_comm_create from the 128-byte ncclUniqueId that rank 0 obtained with dtfill_nccl_unique_id and
+ * sent to the other ranks by any means (torch.distributed broadcast in sharding.py).  libnccl.so.2 is resolved with
+ * dlopen at the first of these calls (DTFILL_NCCL_LIB overrides the name); without it they return DTFILL_E_CUDA.
+ */
+#define DTFILL_NCCL_ID_BYTES 128
+int dtfill_nccl_unique_id(void* out_id /* DTFILL_NCCL_ID_BYTES */);
+int dtfill_comm_create(dtfill_t* h, const void* id, int nranks, int rank, void** out_nccl_comm);
+int dtfill_comm_destroy(void* nccl_comm);
+int dtfill_allreduce_sums(dtfill_t* h, void* nccl_comm, double* sums_dev, int n);
 
 /*
  * DT pooling of the CNN input stage: generate_multi_channel (solution_DeepNet/net.py:83-123, identical in all
@@ -187,6 +212,14 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n);
 #define DTFILL_NUM_KERNELS 5
 int dtfill_set_profiling(dtfill_t* h, int enabled);
 int dtfill_kernel_times(dtfill_t* h, float* ms);
+
+/* Pageable host buffers handed to dtfill_run / dtfill_run_u16 (what numpy allocates: the reference's contract,
+ * tools.py:13-35) are staged through pinned mirrors owned by the handle: `threads` host threads per direction copy a
+ * slice into / out of the mirror while the DMA engines move the previous slices and the kernels run, so a pageable
+ * caller gets close to the PCIe limit.  -1 (default): hardware threads / 4, clamped to 2..8; 0: no staging (the
+ * driver stages the copies on the calling thread).  Buffers that are already pinned (dtfill_host_alloc,
+ * cudaHostRegister) are copied directly in either case. */
+int dtfill_set_stage_threads(dtfill_t* h, int threads);
 
 /* Pinned host memory for fast host<->device copies (cudaHostAlloc / cudaFreeHost). */
 int  dtfill_host_alloc(void** out_ptr, size_t bytes);
