@@ -68,6 +68,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_run_u16.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, ci, ctypes.POINTER(ci)]
         L.dtfill_run_u16_async.argtypes = [vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp]
         L.dtfill_set_sky_min.argtypes = [vp, ci]
+        L.dtfill_debug_set_skip.argtypes = [vp, ci]
         L.dtfill_set_stage_threads.argtypes = [vp, ci]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
@@ -84,7 +85,7 @@ def load() -> ctypes.CDLL:
                      "dtfill_status", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
-                     "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads"):
+                     "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -217,6 +218,10 @@ class Handle:
     def set_band_cap(self, cap: int):
         """Band planner target (row steps per task): >0 explicit, 0 never split frames, -1 automatic."""
         _check(self._L.dtfill_set_band_cap(self._h, int(cap)), "dtfill_set_band_cap")
+
+    def debug_set_skip(self, mask: int):
+        """Tuning only: stages whose bit is set (0 K1, 1 K1b, 2 K2, 3 k3_sky) are not launched by the next runs."""
+        _check(self._L.dtfill_debug_set_skip(self._h, int(mask)), "dtfill_debug_set_skip")
 
     def set_sky_min(self, rows: int):
         """Least number of source-free top rows handed to the closed-form kernel k3_sky; 0: never; -1 (default):

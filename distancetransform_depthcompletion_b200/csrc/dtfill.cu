@@ -126,6 +126,8 @@ struct Lane {
     cudaStream_t side[MAX_SUB] = {};     // narrow tiles run next to the full-width tasks of the same sub-batch
     cudaEvent_t side_fork[MAX_SUB] = {}, side_join[MAX_SUB] = {};
     cudaStream_t pipe = nullptr;         // pipelined mode: the stream this lane's calls run on
+    cudaStream_t pipe_front = nullptr;   // pipelined mode: low-priority stream of the first stage (k1_mask_rows)
+    cudaEvent_t front_done = nullptr;
     cudaEvent_t done = nullptr;          // ... and the end of its last call
     bool pending = false;                // done not yet waited for by the handle's stream
     int last_launches = 0;
@@ -171,6 +173,12 @@ struct dtfill_ctx {
     int32_t* counts_host = nullptr;   // pinned staging for out_counts (a pageable destination would serialise the
     size_t counts_host_cap = 0;       // sliced copies: cudaMemcpyAsync to pageable memory blocks the host)
     bool profiling = false;
+#ifdef DTFILL_TRACE
+    unsigned long long* trace_dev = nullptr;   // [TRACE_CALLS][4 kernels][4]
+    static const int TRACE_CALLS = 256;
+#endif
+    bool prio_split = false;          // pipelined mode: first stage on a low-priority stream, the rest on a high-priority one
+    int debug_skip = 0;               // tuning only (dtfill_debug_set_skip): bit 0 K1, 1 K1b, 2 K2, 3 k3_sky are not launched
     bool tiles2d = true;
     int max_col_tiles = 4;
     int sky_min = -1;             // source-free top rows go to k3_sky when there are at least this many; 0: never;
@@ -303,7 +311,7 @@ static float source_cut(float thr) {
 
 // Enqueue the path for frames [b0, b0+nb) of the batch on stream s; all pointers are device pointers to the whole
 // batch, the workspace is sliced per frame so sub-batches never share anything but the status words.
-int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0, int nb, int Btot, const void* in, int H, int W,
+int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, const Plan& plan, int b0, int nb, int Btot, const void* in, int H, int W,
                   float src_thr, float val_thr, float* out_depth, float* out_dt, int32_t* out_lbl, uint8_t* out_mask,
                   int32_t* out_counts, int scratch_units_per_frame, int sub_index, int* launches) {
     const int WW = (W + 31) / 32;
@@ -326,12 +334,16 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     fp.mul_dist = 1u << (32 - DSH);
     fp.four = 4u;
     fp.one = 1u;
+#ifdef DTFILL_TRACE
+    fp.trace = h->trace_dev ? h->trace_dev + (size_t)(h->ncalls % dtfill_ctx::TRACE_CALLS) * 16 : nullptr;
+#endif
     {   // band planner target: enough independent tiles to keep ~24 warps per SM busy over the whole batch
         int cap = h->band_cap;
         if (cap < 0) {
             // tiles wanted per frame; with batches overlapping (pipelined mode) fewer, taller tiles do: they carry
             // less halo redundancy and the other batches in flight fill the SMs
-            const long beff = h->pipeline_depth > 1 ? (3L * Btot + 1) / 2 : Btot;
+            // (measured on 256 KITTI frames, 4 batches in flight: target 260 -> 0.417 ms per step, 202 -> 0.426, 330 -> 0.419)
+            const long beff = h->pipeline_depth > 1 ? (9L * Btot + 3) / 4 : Btot;
             const long per_frame = ((long)h->sm_count * 28 + beff - 1) / beff;
             if (per_frame <= 1) cap = 0;                                              // batch alone fills the GPU
             else {
@@ -363,7 +375,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     int32_t* oc = out_counts ? out_counts + 2 * (size_t)b0 : nullptr;
 
     if (h->profiling) CU(cudaEventRecord(h->ev[0], s));
-    {   // K1: one warp per row
+    if (!(h->debug_skip & 1)) {   // K1: one warp per row
         // small blocks (2 warps, no shared memory): they fit into the registers the scan's warps of other batches
         // leave free on an SM, so K1 starts flowing before those drain (measured: 256 -> 64 threads, step -2 %)
         const int k1_threads = 64;
@@ -372,26 +384,33 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
         int grid = (int)(want < 1 ? 1 : want);
         if (!h->in_u16) {
             const float* in_s = (const float*)in + npx0;
-            if ((W & 15) == 0) k1_mask_rows_v16<float, true><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
-            else if ((W & 3) == 0) k1_mask_rows_v16<float, false><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
-            else k1_mask_rows<float><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, nullptr);
+            if ((W & 15) == 0) k1_mask_rows_v16<float, true><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, nullptr);
+            else if ((W & 3) == 0) k1_mask_rows_v16<float, false><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, nullptr);
+            else k1_mask_rows<float><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, nullptr);
         } else {
             const uint16_t* in_s = (const uint16_t*)in + (size_t)b0 * h->in_H * W;
-            if ((W & 15) == 0) k1_mask_rows_v16<uint16_t, true><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
-            else if ((W & 7) == 0) k1_mask_rows_v16<uint16_t, false><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
-            else k1_mask_rows<uint16_t><<<grid, k1_threads, 0, s>>>(in_s, fp, ws, om, olid);
+            if ((W & 15) == 0) k1_mask_rows_v16<uint16_t, true><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, olid);
+            else if ((W & 7) == 0) k1_mask_rows_v16<uint16_t, false><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, olid);
+            else k1_mask_rows<uint16_t><<<grid, k1_threads, 0, s_front>>>(in_s, fp, ws, om, olid);
         }
         ++*launches;
+        if (s_front != s) {                 // the later stages run on the lane's high-priority stream
+            CU(cudaEventRecord(L->front_done, s_front));
+            CU(cudaStreamWaitEvent(s, L->front_done, 0));
+        }
     }
     if (h->profiling) CU(cudaEventRecord(h->ev[1], s));
-    k1b_scan_compact<<<nb, K1B_THREADS, 0, s>>>(fp, ws, oc);
-    ++*launches;
+    if (!(h->debug_skip & 2)) {
+        k1b_scan_compact<<<nb, K1B_THREADS, 0, s>>>(fp, ws, oc);
+        ++*launches;
+    }
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
     const bool want_lbl = ol != nullptr;
     // half-width tiles run on a side stream next to the full-width tasks (different kernel instances)
     cudaStream_t s2 = s;
-    if (fp.narrow_ppl) {
+    const bool run_k2 = !(h->debug_skip & 4);
+    if (fp.narrow_ppl && run_k2) {
         s2 = L->side[sub_index];
         CU(cudaEventRecord(L->side_fork[sub_index], s));
         CU(cudaStreamWaitEvent(s2, L->side_fork[sub_index], 0));
@@ -400,21 +419,21 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
         ++*launches;
         CU(cudaEventRecord(L->side_join[sub_index], s2));
     }
-    switch (plan.ppl) {
+    if (run_k2) switch (plan.ppl) {
         case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
         case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
         case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
         default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;  // NOSRC only
     }
-    ++*launches;
+    if (run_k2) ++*launches;
     // 64-bit-key fallback: returns immediately for every task the fast kernels handle.  It touches other frames
     // than they do, so it runs next to the narrow tiles; only per-kernel profiling serialises it behind the join.
     const size_t wide_smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
-    if (!h->profiling) {
+    if (!h->profiling && run_k2) {
         k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
-    if (fp.narrow_ppl) CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
+    if (fp.narrow_ppl && run_k2) CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
     if (h->profiling) {
         CU(cudaEventRecord(h->ev[3], s));
         k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
@@ -423,7 +442,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, const Plan& plan, int b0
     }
     // rows above the first source row, from the two base rows the scan left in ws.skykeys (blocks of frames without
     // such rows return at once)
-    if (fp.band_cap > 0 && fp.sky_min > 0 && W <= SKY_MAX_W) {
+    if (fp.band_cap > 0 && fp.sky_min > 0 && W <= SKY_MAX_W && !(h->debug_skip & 8)) {
         k3_sky<<<dim3(nb, (H + SKY_ROWS - 1) / SKY_ROWS), 256, 0, s>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
@@ -476,13 +495,24 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
         }
     }
 
-    cudaStream_t s = h->stream;
+    cudaStream_t s = h->stream, s_front = h->stream;
     if (pipelined) {
         // this call runs on the lane's own stream, behind whatever the caller queued so far and behind the lane's
-        // previous call (stream order); the handle's stream only joins at dtfill_flush / dtfill_status
+        // previous call (stream order); the handle's stream only joins at dtfill_flush / dtfill_status.
+        // DTFILL_PRIO_SPLIT=1 (experiment, off): the first stage (HBM bound, thousands of small blocks) on a low-priority
+        // stream and the later stages on a high-priority one.  The calls then form a clean staggered pipeline instead of
+        // running in rounds (all K1, all K1b, all K2 ... of the calls in flight), but the low-priority stage starves and
+        // the step is 2 % slower (profiles/r02_timeline_*.txt).
         CU(cudaEventRecord(h->pipe_fork, h->stream));
-        CU(cudaStreamWaitEvent(L->pipe, h->pipe_fork, 0));
         s = L->pipe;
+        if (h->prio_split) {
+            s_front = L->pipe_front;
+            CU(cudaStreamWaitEvent(s_front, h->pipe_fork, 0));
+            if (L->pending) CU(cudaStreamWaitEvent(s_front, L->done, 0));      // workspace of the call `depth` back
+        } else {
+            s_front = s;
+            CU(cudaStreamWaitEvent(s, h->pipe_fork, 0));
+        }
     } else {
         // strict mode: everything still in flight on the lanes joins the handle's stream first
         for (Lane& o : h->lanes)
@@ -496,7 +526,7 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
         if (h->status_ring[2 * slot] < h->sticky_bad) h->sticky_bad = h->status_ring[2 * slot];
         h->slot_dirty[slot] = false;
     }
-    CU(cudaMemcpyAsync(L->status.p, h->status_init, 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(L->status.p, h->status_init, 8, cudaMemcpyHostToDevice, s_front));
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
@@ -533,7 +563,7 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     };
     if (nsub == 1 && !(hio && hio->any_out_pin())) {
         if ((rc = copy_in(s, 0, B))) return rc;
-        if ((rc = enqueue_range(h, L, s, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
+        if ((rc = enqueue_range(h, L, s, s_front, plan, 0, B, B, in, H, W, src_thr, val_thr, out_depth, out_dt, out_lbl, out_mask,
                                 out_counts, scratch_units_per_frame, 0, &launches))) return rc;
         if ((rc = copy_out(s, 0, B))) return rc;
     } else {
@@ -569,7 +599,7 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
                 CU(cudaStreamWaitEvent(L->sub[i], L->fork_ev, 0));
                 int r;
                 if ((r = copy_in(L->sub[i], b0, b1 - b0))) return r;
-                if ((r = enqueue_range(h, L, L->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
+                if ((r = enqueue_range(h, L, L->sub[i], L->sub[i], plan, b0, b1 - b0, B, in, H, W, src_thr, val_thr, out_depth, out_dt,
                                        out_lbl, out_mask, out_counts, scratch_units_per_frame, i, &launches))) return r;
                 if ((r = copy_out(L->sub[i], b0, b1 - b0))) return r;
                 CU(cudaEventRecord(L->join_ev[i], L->sub[i]));
@@ -632,18 +662,23 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     h->status_init[0] = INT_MAX;
     h->status_init[1] = 0;
     for (auto& e : h->slot_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // numerically lower = higher priority
     for (Lane& L : h->lanes) {
-        CU(cudaStreamCreateWithFlags(&L.pipe, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&L.pipe, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithPriority(&L.pipe_front, cudaStreamNonBlocking, prio_lo));
+        CU(cudaEventCreateWithFlags(&L.front_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&L.fork_ev, cudaEventDisableTiming));
         for (int i = 0; i < Lane::MAX_SUB; ++i) {
             CU(cudaStreamCreateWithFlags(&L.sub[i], cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&L.join_ev[i], cudaEventDisableTiming));
-            CU(cudaStreamCreateWithFlags(&L.side[i], cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithPriority(&L.side[i], cudaStreamNonBlocking, prio_hi));
             CU(cudaEventCreateWithFlags(&L.side_fork[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&L.side_join[i], cudaEventDisableTiming));
         }
     }
+    if (const char* e = getenv("DTFILL_PRIO_SPLIT")) h->prio_split = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_TILES2D")) h->tiles2d = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_SUBBATCHES")) h->nsub = atoi(e);
     if (const char* e = getenv("DTFILL_MAX_COL_TILES")) h->max_col_tiles = atoi(e);
@@ -670,6 +705,8 @@ void dtfill_destroy(dtfill_t* h) {
         if (L.fork_ev) cudaEventDestroy(L.fork_ev);
         if (L.done) cudaEventDestroy(L.done);
         if (L.pipe) cudaStreamDestroy(L.pipe);
+        if (L.pipe_front) cudaStreamDestroy(L.pipe_front);
+        if (L.front_done) cudaEventDestroy(L.front_done);
         for (int i = 0; i < Lane::MAX_SUB; ++i) {
             if (L.join_ev[i]) cudaEventDestroy(L.join_ev[i]);
             if (L.sub[i]) cudaStreamDestroy(L.sub[i]);
@@ -979,6 +1016,33 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(out, h->lanes[h->last_lane].status.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+#ifdef DTFILL_TRACE
+// tuning build: (re)arm the trace buffer / read it back: out[calls][4 kernels][4] u64 = first start, last end, sum, blocks
+extern "C" int dtfill_debug_trace_arm(dtfill_t* h) {
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)dtfill_ctx::TRACE_CALLS * 16;
+    if (!h->trace_dev) CU(cudaMalloc(&h->trace_dev, n * 8));
+    std::vector<unsigned long long> init(n);
+    for (size_t i = 0; i < n; ++i) init[i] = (i % 4 == 0) ? ~0ull : 0ull;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->trace_dev, init.data(), n * 8, cudaMemcpyHostToDevice));
+    h->ncalls = 0;
+    return 0;
+}
+extern "C" int dtfill_debug_trace_read(dtfill_t* h, unsigned long long* out) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, h->trace_dev, (size_t)dtfill_ctx::TRACE_CALLS * 16 * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+#endif
+
+int dtfill_debug_set_skip(dtfill_t* h, int mask) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_debug_set_skip: NULL handle");
+    h->debug_skip = mask;
     return 0;
 }
 

@@ -63,6 +63,9 @@ struct FrameParams {
     uint32_t mul_dist;         // 1 << (32 - DSH):  umulhi(key, mul_dist)  == key >> DSH
     uint32_t four;             // sizeof(float)
     uint32_t one;              // 1: x * one + c keeps a plain add on the FMA pipe
+#ifdef DTFILL_TRACE
+    unsigned long long* trace; // tuning build only: per launch {first block start, last block end, sum of block times, blocks}
+#endif
 };
 
 struct Workspace {
@@ -148,6 +151,54 @@ template <> struct In16<uint16_t> {
         return make_float4(u16_depth(a & 0xFFFFu), u16_depth(a >> 16), u16_depth(b & 0xFFFFu), u16_depth(b >> 16));
     }
 };
+
+// Tuning build (-DDTFILL_TRACE): every block that does work records its start and end (globaltimer, ns) into the
+// launch's trace slot, so that the overlap of the kernels of consecutive calls can be reconstructed without a profiler.
+#ifdef DTFILL_TRACE
+struct TraceScope {
+    unsigned long long* t; unsigned long long t0;
+    __device__ __forceinline__ TraceScope(const FrameParams& fp, int kernel) : t(fp.trace ? fp.trace + 4 * kernel : nullptr), t0(0) {
+        if (t && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); atomicMin(t, t0); }
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if (t && threadIdx.x == 0) {
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            atomicMax(t + 1, t1); atomicAdd(t + 2, t1 - t0); atomicAdd(t + 3, 1ull);
+        }
+    }
+};
+#define DTFILL_TRACE_SCOPE(fp, k) TraceScope trace_scope_(fp, k)
+#else
+#define DTFILL_TRACE_SCOPE(fp, k)
+#endif
+
+// depth_list is the one buffer of the path that is read at random (the gather depth_list[lbl - 1], tools.py:26) and
+// read more than once: 21 MB per batch of 256 KITTI frames.  Its stores and loads carry an L2 evict-last policy so that
+// the streaming traffic of the step (2 GB) does not push it out of the 126 MB L2 before the gather comes.
+#ifndef DTFILL_DLIST_KEEP
+#define DTFILL_DLIST_KEEP 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ld_keep_f32(const void* p, uint64_t pol) {
+    float v;
+#if DTFILL_DLIST_KEEP
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#else
+    v = *reinterpret_cast<const float*>(p);
+#endif
+    return v;
+}
+__device__ __forceinline__ void st_keep_f32(float* p, float v, uint64_t pol) {
+#if DTFILL_DLIST_KEEP
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+    *p = v;
+#endif
+}
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;

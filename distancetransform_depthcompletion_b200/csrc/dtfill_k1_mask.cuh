@@ -26,6 +26,7 @@ template <typename T, bool W16>
 __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in, FrameParams fp, Workspace ws,
                                                          uint8_t* __restrict__ out_mask, float* __restrict__ out_lidar)
 {
+    DTFILL_TRACE_SCOPE(fp, 0);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;

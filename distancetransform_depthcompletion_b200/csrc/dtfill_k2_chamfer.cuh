@@ -83,6 +83,28 @@ __device__ __forceinline__ void st_scratch_v4(void* p, uint32_t a, uint32_t b, u
 __device__ __forceinline__ void st_scratch_v2(void* p, uint32_t a, uint32_t b) {
     asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
+// L2 residency of the forward state (DTFILL_L2POLICY): the scratch is written once and read back once in LIFO order, so
+// its most recent rows can live and die in the 126 MB L2 without ever reaching HBM: stores carry an evict-last policy,
+// the read-back an evict-first one, and a consumed row is discarded (dropped from L2 without write-back).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_scratch_v4_hint(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t smem_addr, const void* gptr, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void l2_discard_128(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -159,6 +181,12 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
 #ifndef DTFILL_FAKE_SCRATCH_DIV
 #define DTFILL_FAKE_SCRATCH_DIV 1   // > 1: timing experiment only (part of the forward state is dropped: wrong results)
 #endif
+#ifndef DTFILL_L2POLICY
+#define DTFILL_L2POLICY 0       // 1: evict-last stores + evict-first read-back of the scratch; 2: and discard of consumed rows
+#endif
+#ifndef DTFILL_FLUSH_LATE
+#define DTFILL_FLUSH_LATE 0     // where a step stores the depths gathered by the previous one: 0 at its start, 1 after the
+#endif                          // stencil, 2 after the scan (the gather's latency is then covered by the whole step)
 #ifndef DTFILL_K2_WARPS
 #define DTFILL_K2_WARPS 20      // resident warps per SM the PPL = 20 instance is compiled for (register budget)
 #endif
@@ -245,6 +273,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
 
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
+    DTFILL_TRACE_SCOPE(fp, 2);
     const int lane = threadIdx.x;
     const int H = fp.H, W = fp.W, WW = fp.WW;
     const int b = task.frame;
@@ -272,6 +301,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     constexpr int VW = (PPL % 4 == 0) ? 4 : 2;   // keys per scratch vector
     uint2* scr = reinterpret_cast<uint2*>(ws.scratch) + (long)task.scratch_off * 16;   // 32*PPL keys per row
 
+#if DTFILL_L2POLICY
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+#endif
     Row<PPL> ra, rb;
     fill_row(ra, init_key);
     fill_row(rb, init_key);
@@ -343,7 +375,11 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
             char* dst = reinterpret_cast<char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
             for (int j = 0; j < PPL / VW / DTFILL_FAKE_SCRATCH_DIV; ++j) {
+#if DTFILL_L2POLICY
+                if (VW == 4) st_scratch_v4_hint(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3], pol_keep);
+#else
                 if (VW == 4) st_scratch_v4(dst + j * 512, Bq.v[4 * j], Bq.v[4 * j + 1], Bq.v[4 * j + 2], Bq.v[4 * j + 3]);
+#endif
                 else st_scratch_v2(dst + j * 256, Bq.v[2 * j], Bq.v[2 * j + 1]);
             }
         }
@@ -364,6 +400,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     fill_row(ra, init_key);
     fill_row(rb, init_key);
     const float* dl = ws.dlist + fpx;
+    const uint64_t pol_dlist = l2_policy_keep();
     const char* dlm1_bytes = reinterpret_cast<const char*>(dl - 1);       // depth_list[lbl - 1]
     // output addressing that does not depend on the row: which 4-pixel groups of the transposed row this lane
     // writes (inside [c0,c1)), and where
@@ -384,7 +421,11 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
             const char* src = reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
             for (int j = 0; j < PPL / VW / DTFILL_FAKE_SCRATCH_DIV; ++j) {
+#if DTFILL_L2POLICY
+                if (VW == 4) cp_async16_hint(fwdbuf_lane + j * 512, src + j * 512, pol_drop);
+#else
                 if (VW == 4) cp_async16_l2only(fwdbuf_lane + j * 512, src + j * 512);
+#endif
                 else cp_async8(fwdbuf_lane + j * 256, src + j * 256);
             }
         }
@@ -406,13 +447,21 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         if (lane < PPL / DTFILL_FAKE_SCRATCH_DIV && y - 3 >= task.fstart)      // forward row three steps ahead -> L2 (one 128 B line per lane)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(scr) +
                                                           (long)(y - 3 - task.lo) * (128 * PPL) + lane * 128));
+#if DTFILL_FLUSH_LATE == 0
         if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
+#endif
         cp_async_wait<0>();                          // A(y), the only group in flight, has landed
+#if DTFILL_L2POLICY >= 2
+        if (VW == 4 && lane < PPL && y >= task.fstart && y >= task.lo)     // row y of the scratch is dead: one 128 B line per lane
+            l2_discard_128(reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * 128);
+#endif
         uint32_t c[PPL];
         if (y >= task.fstart) {
 #pragma unroll
             for (int j = 0; j < PPL / VW; ++j) {
-                if (VW == 4) {
+                if (DTFILL_FAKE_SCRATCH_DIV > 1 && j >= PPL / VW / DTFILL_FAKE_SCRATCH_DIV) {
+                    for (int e = 0; e < VW; ++e) c[VW * j + e] = init_key;
+                } else if (VW == 4) {
                     const uint4 f = reinterpret_cast<const uint4*>(fwdbuf)[j * 32 + lane];
                     c[4 * j] = f.x; c[4 * j + 1] = f.y; c[4 * j + 2] = f.z; c[4 * j + 3] = f.w;
                 } else {
@@ -427,6 +476,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
 #pragma unroll
         for (int i = 0; i < PPL; ++i) c[i] = stencil_bwd<PPL>(c[i], A, Bq, i, fp.one) & ORDCLR;
         issue_fwd_row(y - 1);                        // A(y-1): fwdbuf has been consumed above
+#if DTFILL_FLUSH_LATE == 1
+        if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
+#endif
 #if DTFILL_SPLITSCAN
         constexpr int HF = PPL / 2;                  // chains over columns [HF, PPL) and [0, HF), both right to left
         uint32_t u = c[PPL - 1], u2 = c[HF - 1];
@@ -461,6 +513,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         }
 #endif
         refresh_halo(Bq, lane, init_key);
+#if DTFILL_FLUSH_LATE == 2
+        if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
+#endif
 
         // ---- output of row y: keys -> shared memory (transpose), then per lane 4 consecutive pixels per group:
         // dt / lbl stores and the gather depth_list[lbl-1] (tools.py:26).  In this layout neighbouring lanes ask
@@ -487,8 +542,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
                         const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint32_t l = kk[e] & LMASK;                                // >= 1 inside [c0,c1)
-                            g[4 * j + e] = __float_as_uint(*reinterpret_cast<const float*>(dlm1_bytes + (uint64_t)l * fp.four));
+                            uint32_t l = kk[e] & LMASK;                                      // >= 1 inside [c0,c1)
+                            if (DTFILL_FAKE_SCRATCH_DIV > 1) l = max(l, 1u);
+                            g[4 * j + e] = __float_as_uint(ld_keep_f32(dlm1_bytes + (uint64_t)l * fp.four, pol_dlist));
                         }
                     }
                 }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) k3_sky(FrameParams fp, Workspace ws, floa
     const int b = blockIdx.x, S = ws.sky[b];
     const int y0 = blockIdx.y * SKY_ROWS;
     if (y0 >= S) return;
+    DTFILL_TRACE_SCOPE(fp, 3);
     const int H = fp.H, W = fp.W, tid = threadIdx.x;
     const long fpx = (long)b * H * W;
     const uint32_t* sk = ws.skykeys + (long)b * 2 * W;
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(256) k3_sky(FrameParams fp, Workspace ws, floa
     for (int x = tid; x < W; x += 256) {
         const uint32_t k0 = sk[x], k1 = sk[W + x];
         d0[x + 1] = (uint16_t)(k0 >> DSH);
-        dep[0][x] = dl[(k0 & LMASK) - 1u];
-        dep[1][x] = dl[(k1 & LMASK) - 1u];
+        dep[0][x] = dl[max(k0 & LMASK, 1u) - 1u];
+        dep[1][x] = dl[max(k1 & LMASK, 1u) - 1u];
     }
     if (tid == 0) { d0[0] = 0xFFFFu; d0[W + 1] = 0xFFFFu; }
     __syncthreads();

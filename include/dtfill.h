@@ -206,6 +206,11 @@ int dtfill_debug_get_tasks(dtfill_t* h, int32_t* out, int max_tasks);
  * the library is built with -DDTFILL_PLANNER_CLOCKS. */
 int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n);
 
+/* Tuning only: the stages whose bit is set are not launched by the following runs (bit 0 k1_mask_rows, 1 k1b_scan_compact,
+ * 2 k2_chamfer*, 3 k3_sky), so that one stage can be timed against the workspace a complete run left behind.  Outputs
+ * of such runs are meaningless. */
+int dtfill_debug_set_skip(dtfill_t* h, int mask);
+
 /* Per-kernel timing of the hot path with CUDA events recorded on the handle's stream between the launches of
  * dtfill_run / dtfill_run_async (off by default).  dtfill_kernel_times waits for the last run and writes the
  * milliseconds of k1_mask_rows, k1b_scan_compact, k2_chamfer, k2_chamfer_wide, k3_sky into ms[0..4]. */
