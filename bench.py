@@ -3,11 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's CPU path on host cores
+    python bench.py --workload sweep [--gpus N]                         BASELINE.json configs[4] only
 
 A step = one pass of the hot path over one batch of synthetic KITTI-shaped frames (BASELINE.json configs[1]:
 256 frames of 352x1216, 64-beam pattern, ~5 % density; outputs filled depth + distance channel + validity mask).
 Weak scaling: every rank processes its own batch of 256 frames per step; `value` = total frames of all ranks /
-max-over-ranks device time.  Prints ONE JSON line on rank 0.
+max-over-ranks device time.  The K-step block is repeated until the timed region has lasted >= 1 s; the median
+block is reported.  After the timed region 64 frames of the timed run's own outputs are compared with the CPU
+oracle, bit for bit (`parity_checked`).  `e2e` is the drop-in call `tools.DT_complete_batch(x)` with pageable numpy
+arrays in and out (tools.py:13-35); `e2e_pinned` is the C ABI with pinned buffers and all three outputs.
+The same line carries `sweep`: BASELINE.json configs[4] (8192 frames sharded over the ranks, fill + per-frame
+metrics on the GPU, one NCCL sum all-reduce of the totals inside the timed region; strong scaling).
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -135,15 +142,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference CPU path (the reference's own lines with the real cv2 call; C oracle if cv2 is absent)
+# reference CPU path: the reference's own tools.DT_complete_batch when a checkout is reachable, else the
+# line-by-line port with the real cv2 call (oracle/oracle.py), else the C oracle
 # ------------------------------------------------------------------------------------------------------------
 _CPU_FRAMES = None      # frames shared with the forked workers (no pickling of pixel data)
+_REF_TOOLS = None       # the reference's tools module (imported before the fork)
+
+
+def load_reference_tools():
+    """solution_DeepNet/tools.py of a reference checkout: $DTFILL_REFERENCE, baseline/_ref, /root/reference (the build
+    container).  The module imports tensorflow without using it on this path and forgets to import cv2 (tools.py:1-9):
+    a stub module and the real cv2 are supplied.  Returns (module, where) or (None, why)."""
+    import importlib.util
+    import types
+    try:
+        import cv2
+    except Exception as e:          # noqa: BLE001
+        return None, f"cv2 not importable ({e})"
+    for root in (os.environ.get("DTFILL_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if not root:
+            continue
+        for rel in ("solution_DeepNet/tools.py", "tools.py"):
+            p = os.path.join(root, rel)
+            if os.path.isfile(p):
+                try:
+                    if "tensorflow" not in sys.modules:
+                        sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+                    spec = importlib.util.spec_from_file_location("_reference_tools", p)
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    mod.cv2 = cv2
+                    return mod, p
+                except Exception as e:      # noqa: BLE001
+                    return None, f"{p}: {e}"
+    return None, "no reference checkout on this box (it cannot travel: Python source outside the repo)"
 
 
 def _cpu_worker(args):
     kind, lo, hi = args
-    from oracle import oracle as O
     frames = _CPU_FRAMES[lo:hi]
+    if kind == "reference":
+        import cv2
+        cv2.setNumThreads(1)
+        out = _REF_TOOLS.DT_complete_batch(frames[:, :, :, None])          # tools.py:13-35, unmodified
+        return float(out[0, 0, 0, 0])
+    from oracle import oracle as O
     if kind == "cv2":
         import cv2
         cv2.setNumThreads(1)
@@ -158,14 +201,18 @@ def _cpu_worker(args):
 
 
 class CpuReference:
-    """The reference's per-frame work (tools.py:7-35: mask, cv2 DT with labels, compaction, gather) restated in
-    oracle/oracle.py, frames split evenly over a fork()ed process pool with one cv2 thread each."""
+    """The reference's per-frame work (tools.py:7-35: mask, cv2 DT with labels, compaction, gather), frames split evenly
+    over a fork()ed process pool with one cv2 thread each (the reference itself loops over the frames on one core)."""
 
     def __init__(self, frames: np.ndarray):
-        global _CPU_FRAMES
+        global _CPU_FRAMES, _REF_TOOLS
         from oracle import oracle as O
         O.build()
-        self.kind = "cv2" if O.have_cv2() else "c_oracle"
+        mod, self.where = load_reference_tools()
+        if mod is not None:
+            _REF_TOOLS, self.kind = mod, "reference"
+        else:
+            self.kind = "cv2" if O.have_cv2() else "c_oracle"
         self.cores = os.cpu_count() or 1
         try:
             self.cores = len(os.sched_getaffinity(0))
@@ -187,9 +234,12 @@ class CpuReference:
         self.pool.terminate()
 
     def describe(self):
+        if self.kind == "reference":
+            return ("reference", f"the reference's own tools.DT_complete_batch ({self.where}) with cv2 "
+                                 f"{__import__('cv2').__version__}, frames split over one process per core")
         if self.kind == "cv2":
             return ("port", "reference lines tools.py:7-35 restated with the real cv2.distanceTransformWithLabels "
-                            "(oracle/oracle.py cv2_port_fill_frame), one process per core")
+                            f"(oracle/oracle.py cv2_port_fill_frame; {self.where}), one process per core")
         return ("port", "C restatement oracle/dtfill_oracle.c (cv2 not importable here), one process per core")
 
 
@@ -221,35 +271,147 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     batch = args.batch or 256
-    cores = os.cpu_count() or 1
-    sample = min(batch, max(cores * 4, 32))
-    ref = CpuReference(make_frames(sample, 0))
+    ref = CpuReference(make_frames(batch, 0))
     for _ in range(args.warmup):
-        ref.run(min(sample, max(ref.cores, 8)))
+        ref.run(min(batch, max(ref.cores, 8)))
     t = 0.0
     for _ in range(args.steps):
-        t += ref.run(sample)
+        t += ref.run(batch)
     ref.close()
-    fps = sample * args.steps / t
+    fps = batch * args.steps / t
     kind, how = ref.describe()
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 keys (integer chamfer) + f32 copy", "data": "synthetic",
-        "config": {"workload": f"kitti64 352x1216 ~5% density, {sample}-frame sample of the {batch}-frame batch per step",
-                   "outputs": "filled depth + distance channel + validity mask", "host_cores": ref.cores},
+        "config": {"workload": f"kitti64: batch of {batch} synthetic KITTI 64-beam frames 352x1216 (~5% density) "
+                               "(BASELINE.json configs[1]), the whole batch per step",
+                   "outputs": "filled depth (tools.DT_complete_batch); the cv2 call also yields the distance channel",
+                   "host_cores": ref.cores},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ref.cores, "kind": kind,
-                         "sample": f"{sample} frames x {args.steps} steps; {how}"},
+                         "sample": f"{batch} frames x {args.steps} steps; {how}"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def run_ours(args, rank, world, local_rank):
+def pin_to_gpu_numa(local_rank: int):
+    """Bind this process (and the threads it creates later: the pinned-staging pools) to the CPUs next to its GPU, before
+    any pinned host memory is allocated, so that eight ranks do not share one socket's memory.  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = local_rank
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            phys = int(vis.split(",")[local_rank])
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}", "n": len(cpus)}
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:80]}
+    return {"cpus": "unchanged"}
+
+
+def run_sweep(args, eng, dev, rank, world, dist, comm, barrier, min_seconds):
+    """BASELINE.json configs[4]: 8192 synthetic KITTI frames sharded contiguously over the ranks (sharding.shard_range),
+    per batch fill -> per-frame Result.evaluate on the GPU -> running totals, no host synchronisation; one NCCL sum
+    all-reduce of the 10 totals (dtfill_allreduce_sums) INSIDE the timed region (eval.py:212-232, evaluation.py:82-123)."""
     import torch
-    from distancetransform_depthcompletion_b200 import _lib
+    from distancetransform_depthcompletion_b200 import sharding, synth
+    from oracle import oracle as O
+    Hs, Ws = 352, 1216
+    frames, batch, pool = args.sweep_frames, args.sweep_batch, 32
+    begin, end = sharding.shard_range(frames, rank, world)
+    xp = torch.from_numpy(np.stack([synth.kitti_frame(i) for i in range(pool)])).to(dev)
+    gp = torch.from_numpy(np.stack([synth.kitti_gt(i) for i in range(pool)])).to(dev)
+
+    def make(first, n):      # global frames first..first+n: pool frame (i % pool) rolled by 8 * (i // pool) columns
+        idx = torch.arange(first, first + n, device=dev)
+        shifts = ((idx // pool) * 8) % Ws
+        cols = ((torch.arange(Ws, device=dev)[None, :] - shifts[:, None]) % Ws)[:, None, :].expand(n, Hs, Ws)
+        return torch.gather(xp[idx % pool], 2, cols).contiguous(), torch.gather(gp[idx % pool], 2, cols).contiguous()
+
+    batches = []             # this rank's whole shard, resident in HBM before the clock starts
+    for f in range(begin, end, batch):
+        batches.append(make(f, min(batch, end - f)))
+    depth = args.pipeline
+    eng.handle.set_pipeline_depth(depth)
+    outs = [None] * max(1, depth)
+    totals = torch.zeros(10, dtype=torch.float64, device=dev)
+
+    def one_sweep():
+        for i, (xb, gb) in enumerate(batches):
+            outs[i % len(outs)] = eng.fill_eval(xb, gb, out=outs[i % len(outs)] if outs[i % len(outs)] is not None and
+                                                outs[i % len(outs)]["depth"].shape == xb.shape else None)
+        eng.eval_totals(totals)                       # joins the calls in flight, writes the rank's totals
+        if comm is not None:
+            comm.allreduce(eng, totals)               # ncclAllReduce(sum, f64) on the same stream
+
+    for _ in range(2):
+        totals.zero_()
+        one_sweep()
+    bad, _ = eng.status()
+    assert bad == -1
+    times = []
+    total_ms = 0.0
+    while total_ms < min_seconds * 1e3 and len(times) < 400:
+        totals.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_sweep()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times.append(ms)
+        total_ms += ms
+    bad, _ = eng.status()
+    assert bad == -1, f"sweep: unexpected bad frame {bad}"
+    eng.handle.set_pipeline_depth(1)
+    means = sharding.finalize_means(totals)
+    # spot check on rank 0: the first frames of its shard against the oracle (fill) and evaluation.py's numbers
+    checked = 0
+    if rank == 0:
+        xb, gb = batches[0]
+        o = eng.fill(xb[:4])
+        pf, _ = eng.metrics(o["depth"], gb[:4])
+        ref = O.dt_fill(xb[:4].cpu().numpy())
+        assert np.array_equal(o["depth"].cpu().numpy(), ref["depth"]), "sweep: filled depth differs from the oracle"
+        for i in range(4):
+            m = O.result_kitti(ref["depth"][i], gb[i].cpu().numpy())
+            got = pf[i].cpu().numpy()
+            for k, name in enumerate(("mse", "rmse", "mae", "irmse", "imae")):
+                assert abs(got[k] - m[name]) <= 1e-9 * abs(m[name]), (i, name, got[k], m[name])
+        checked = 4
+    med = statistics.median(times)
+    return {"workload": f"configs[4]: {frames} synthetic KITTI 64-beam frames 352x1216 sharded over {world} GPU(s) "
+                        f"(contiguous ranges), batches of {batch}, {depth} batches in flight, fill + Result.evaluate per "
+                        "frame on the GPU, one NCCL sum all-reduce of the 10 totals inside the timed region",
+            "value": frames / (med * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_sweep": med, "sweeps_timed": len(times),
+            "timed_region_s": total_ms * 1e-3, "frames": means["frames"], "mean_rmse_mm": means["rmse"],
+            "mean_mae_mm": means["mae"], "mean_irmse_1_per_km": means["irmse"], "mean_imae_1_per_km": means["imae"],
+            "valid_pixels": means["valid_pixels"], "collective": "ncclAllReduce(sum, float64 x 10) via dtfill_allreduce_sums"
+            if comm is not None else "none (1 rank)", "metrics_checked": checked}
+
+
+def run_ours(args, rank, world, local_rank):
+    numa = pin_to_gpu_numa(local_rank)
+    import torch
+    from distancetransform_depthcompletion_b200 import _lib, sharding, tools
     from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    from oracle import oracle as O
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -258,22 +420,13 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("DTFILL_DEVICE", str(local_rank))
+    sweep_only = args.workload == "sweep"
+    workload = "kitti64" if sweep_only else args.workload
     global H, W
-    _, H, W, src_thr, default_batch = WORKLOADS[args.workload]
+    _, H, W, src_thr, default_batch = WORKLOADS[workload]
     B = args.batch or default_batch
-    frames_np = make_frames(B, 1000 * rank, args.workload)
-    pin_in = _lib.pinned_empty((B, H, W), np.float32)
-    pin_in[...] = frames_np
-    x = torch.from_numpy(frames_np).to(dev)
     eng = DTFillEngine(local_rank)
-    if args.band_cap is not None:
-        eng.handle.set_band_cap(args.band_cap)
-    if args.subbatches is not None:
-        eng.handle.set_subbatches(args.subbatches)
-    out = dict(depth=torch.empty((B, H, W), dtype=torch.float32, device=dev),
-               dt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
-               mask=torch.empty((B, H, W), dtype=torch.uint8, device=dev),
-               counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -281,12 +434,44 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # two output sets: with two batches in flight (pipeline depth 2) consecutive steps must not share outputs
-    outs = [out] + [{k: torch.empty_like(v) for k, v in out.items()} for _ in range(max(1, args.pipeline - 1))]
-    no = len(outs)
+    comm = sharding.MetricsComm(eng.handle, rank, world) if world > 1 else None
+    if sweep_only:
+        sw = run_sweep(args, eng, dev, rank, world, dist, comm, barrier, args.min_seconds)
+        if rank == 0:
+            print(json.dumps({"metric": "DT+NN-fill+metrics frames/s, 8192-frame sweep (BASELINE.json configs[4])",
+                              "value": sw["value"], "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+                              "scaling": "strong", "data": "synthetic", "config": {"workload": sw["workload"]},
+                              "sweep": sw}))
+        if comm is not None:
+            comm.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
-    def timed_steps(depth):
-        """Exactly K steps between two events on the launching stream; max over ranks."""
+    frames_np = make_frames(B, 1000 * rank, workload)
+    x = torch.from_numpy(frames_np).to(dev)
+    if args.band_cap is not None:
+        eng.handle.set_band_cap(args.band_cap)
+    if args.subbatches is not None:
+        eng.handle.set_subbatches(args.subbatches)
+
+    def new_outs(with_lbl=False):
+        o = dict(depth=torch.empty((B, H, W), dtype=torch.float32, device=dev),
+                 dt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
+                 mask=torch.empty((B, H, W), dtype=torch.uint8, device=dev),
+                 counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
+        if with_lbl:
+            o["lbl"] = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+        return o
+
+    # one output set per batch in flight: consecutive steps of a pipelined run must not share outputs
+    outs = [new_outs() for _ in range(max(2, args.pipeline))]
+    no = len(outs)
+    K = args.steps
+
+    def timed_blocks(depth, min_seconds):
+        """Blocks of exactly K steps between two events on the launching stream (max over ranks per block), repeated
+        until the timed region has lasted min_seconds; clocks are sampled over the whole region."""
         eng.handle.set_pipeline_depth(depth)
         for i in range(args.warmup):
             eng.fill(x, src_thr=src_thr, out=outs[i % no])
@@ -295,32 +480,60 @@ def run_ours(args, rank, world, local_rank):
         sampler_ = ClockSampler(local_rank)
         barrier()
         sampler_.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            eng.fill(x, src_thr=src_thr, out=outs[i % no])
-        eng.flush()                                   # every step's outputs are complete at e1
-        e1.record()
-        barrier()
+        blocks, total = [], 0.0
+        while total < min_seconds * 1e3 and len(blocks) < 2000:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                eng.fill(x, src_thr=src_thr, out=outs[i % no])
+            eng.flush()                                   # every step's outputs are complete at e1
+            e1.record()
+            barrier()
+            ms_ = e0.elapsed_time(e1)
+            if dist is not None:
+                t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                ms_ = float(t_.item())
+            blocks.append(ms_)
+            total += ms_
         clocks_ = sampler_.stop()
-        ms_ = e0.elapsed_time(e1)
-        if dist is not None:
-            t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            ms_ = float(t_.item())
-        return ms_, launches_, clocks_
+        bad_, _ = eng.status()
+        assert bad_ == -1, f"unexpected bad frame {bad_}"
+        return blocks, launches_, clocks_
 
-    ms_strict, launches_per_step, clocks_strict = timed_steps(1)
+    blocks_strict, launches_per_step, clocks_strict = timed_blocks(1, min(args.min_seconds, 0.3))
     if args.pipeline > 1:
-        ms, launches_per_step, clocks = timed_steps(args.pipeline)
+        blocks, launches_per_step, clocks = timed_blocks(args.pipeline, args.min_seconds)
     else:
-        ms, clocks = ms_strict, clocks_strict
+        blocks, clocks = blocks_strict, clocks_strict
+    ms = statistics.median(blocks)
+    ms_strict = statistics.median(blocks_strict)
+    ms_per_step = ms / K
+    value = world * B * K / (ms * 1e-3)
+    strict = {"value": world * B * K / (ms_strict * 1e-3), "ms_per_step": ms_strict / K, "blocks": len(blocks_strict),
+              "what": "same K-step blocks with strict stream order between steps (pipeline depth 1, the API default)"}
+
+    # ---- parity at the benchmarked configuration: 64 frames of the timed run's own outputs against the oracle ----
+    # (the last block wrote output set (K-1) % no last; every step has the same input)
+    sel = np.unique(np.linspace(0, B - 1, min(B, args.parity_frames)).astype(int))
+    want = O.dt_fill(frames_np[sel], src_thr=src_thr)
+    last = outs[(K - 1) % no]
+    tsel = torch.from_numpy(sel).to(dev)
+    ok = all(np.array_equal(last[k][tsel].cpu().numpy(), want[k]) for k in ("depth", "dt", "mask"))
+    eng.handle.set_pipeline_depth(args.pipeline)           # second pass, same mode, with the label map
+    ol = [new_outs(with_lbl=True) for _ in range(2)]
+    for i in range(2):
+        r_l = eng.fill(x, src_thr=src_thr, want_lbl=True, out=ol[i])
+    eng.flush(); eng.status()
+    ok = ok and all(np.array_equal(r_l[k][tsel].cpu().numpy(), want[k]) for k in ("depth", "dt", "mask", "lbl"))
+    del ol, r_l
+    if dist is not None:
+        t_ = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+        ok = bool(t_.item() > 0.5)
+    assert ok, "parity: the timed run's outputs differ from the oracle"
     eng.handle.set_pipeline_depth(1)
     assert torch.equal(outs[0]["depth"], outs[1]["depth"]) and torch.equal(outs[0]["dt"], outs[1]["dt"])
-    ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms * 1e-3)
-    strict = {"value": world * B * args.steps / (ms_strict * 1e-3), "ms_per_step": ms_strict / args.steps,
-              "what": "same K steps with strict stream order between steps (pipeline depth 1)"}
 
     # ---- per-kernel shares (CUDA events between the launches, same stream), separate untimed steps ----
     # (the kernels of the timed configuration: with batches in flight the rows above the first source row go to
@@ -329,9 +542,9 @@ def run_ours(args, rank, world, local_rank):
     if args.pipeline > 1:
         eng.handle.set_sky_min(8)
     kt = {}
-    reps = min(args.steps, 5)
+    reps = 5
     for _ in range(reps):
-        eng.fill(x, src_thr=src_thr, out=out)
+        eng.fill(x, src_thr=src_thr, out=outs[0])
         for k, v in eng.handle.kernel_times().items():
             kt[k] = kt.get(k, 0.0) + v / reps
     eng.handle.set_profiling(False)
@@ -340,25 +553,70 @@ def run_ours(args, rank, world, local_rank):
     k2_px = int(((tasks[:, 4] - tasks[:, 3]).astype(np.int64) * (tasks[:, 10] - tasks[:, 9])).sum())
     ktot = sum(kt.values())
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
-    h = _lib.Handle(local_rank)           # the numpy-facing API on its own handle and stream, like a user's call
+    # ---- end to end, the drop-in call: tools.DT_complete_batch(pageable numpy) -> fresh pageable numpy (tools.py:13-35)
+    e2e = e2e_pinned = None
+    if workload.startswith("kitti"):
+        x4 = frames_np[:, :, :, None]                 # [B,352,1216,1], ordinary (pageable) memory
+        tools.DT_complete_batch(x4, device=local_rank)                 # warm-up (allocates staging)
+        e2e_steps = max(3, min(K, 8))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r4 = tools.DT_complete_batch(x4, device=local_rank)
+        t_e2e = time.perf_counter() - t0
+        t_own = t_e2e
+        if dist is not None:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        assert np.array_equal(r4[sel, :, :, 0], want["depth"]), "drop-in call differs from the oracle"
+        nbytes = int(B * H * W * 4)
+        per_rank = [nbytes * e2e_steps / t_own / 1e9]
+        if dist is not None:
+            g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(g, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
+            per_rank = [float(v.item()) for v in g]
+        e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+               "what": "tools.DT_complete_batch(x): pageable numpy [B,352,1216,1] in, fresh pageable numpy out, synchronous "
+                       "(the reference's contract, tools.py:13-35); staged through pinned mirrors by the library",
+               "per_rank_gbs_each_direction": [round(v, 2) for v in per_rank], "numa": numa}
+        del r4
+    # ---- the C ABI with pinned host buffers and all three outputs (what round 1 reported as e2e) ----
+    h = _lib.Handle(local_rank)
+    pin_in = _lib.pinned_empty((B, H, W), np.float32)
+    pin_in[...] = frames_np
     pin_out = dict(depth=_lib.pinned_empty((B, H, W), np.float32), dt=_lib.pinned_empty((B, H, W), np.float32),
                    mask=_lib.pinned_empty((B, H, W), np.uint8))
-    e2e_steps = max(2, min(args.steps, 5))
-    h.run_host(pin_in, src_thr, 0.1, want_dt=True, want_mask=True, out=pin_out)      # warm-up (allocates staging)
+    h.run_host(pin_in, src_thr, 0.1, want_dt=True, want_mask=True, out=pin_out)
+    pin_steps = max(3, min(K, 8))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(pin_steps):
         r = h.run_host(pin_in, src_thr, 0.1, want_dt=True, want_mask=True, out=pin_out)
-    t_e2e = time.perf_counter() - t0
+    t_pin = time.perf_counter() - t0
     if dist is not None:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_pin], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = world * B * e2e_steps / t_e2e
-    assert np.array_equal(r["depth"], out["depth"].cpu().numpy()), "host path and device path disagree"
+        t_pin = float(t.item())
+    assert np.array_equal(r["depth"][sel], want["depth"]) and np.array_equal(r["dt"][sel], want["dt"])
+    e2e_pinned = {"value": world * B * pin_steps / t_pin, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W * 4),
+                  "d2h_bytes_per_step": int(B * H * W * 9), "steps": pin_steps,
+                  "what": "dtfill_run (C ABI) with pinned host numpy buffers in and out, depth + dt + mask, synchronous"}
+    if e2e is None:
+        e2e = e2e_pinned
+    h.close()
+
+    # ---- BASELINE.json configs[4] on the same clock ----
+    sweep = None
+    if workload == "kitti64" and not args.no_sweep:
+        del outs
+        torch.cuda.empty_cache()
+        sweep = run_sweep(args, eng, dev, rank, world, dist, comm, barrier, min(args.min_seconds, 0.5))
 
     if rank != 0:
+        if comm is not None:
+            comm.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -368,7 +626,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = ALG_BYTES_PER_PX * px_step / (ms_per_step * 1e-3) / 1e9 * 1.0      # per GPU (rank-0 clock = max)
     traffic = traffic_k2 = None          # DRAM bytes from the committed ncu --set full capture (batch 256 only)
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and B == 256 and args.workload == "kitti64":
+    if os.path.exists(tp) and B == 256 and workload == "kitti64":
         try:
             tj = json.load(open(tp))
             traffic, traffic_k2 = tj.get("dram_bytes_per_step"), tj.get("dram_bytes_per_launch")
@@ -379,9 +637,10 @@ def run_ours(args, rank, world, local_rank):
         "traffic": traffic, "traffic_what": "dram__bytes_read+write of all kernels of one step (profiles/traffic.json); "
                                               "algorithmic bytes per step = 13 B/px x px",
         "algorithmic_bytes": ALG_BYTES_PER_PX * px_step, "peak_source": peak_src,
+        "strict_frac": ALG_BYTES_PER_PX * px_step / (ms_strict / K * 1e-3) / 1e9 / peak,
         "what": "whole fused path of one step (k1_mask_rows + k1b_scan_compact + k2_chamfer + k3_sky [+ k2_chamfer_wide "
-                f"no-op]): {ALG_BYTES_PER_PX} B/px x {px_step} px per step / step time; dominant kernel k2_chamfer; "
-                "kernel_ms = CUDA events between the launches of separate, strictly ordered steps",
+                f"no-op]): {ALG_BYTES_PER_PX} B/px x {px_step} px per step / step time (median K-step block); dominant "
+                "kernel k2_chamfer; kernel_ms = CUDA events between the launches of separate, strictly ordered steps",
         "kernel_ms": kt, "kernel_share": {k: (v / ktot if ktot else None) for k, v in kt.items()},
         "dominant_kernel": {"name": "k2_chamfer", "ms": kt.get("k2_chamfer"),
                             "alg_bytes": 8 * k2_px, "traffic": traffic_k2,
@@ -394,10 +653,10 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(frames_np)        # (the port uses the KITTI thresholds; NYU frames have depths >= 1 m)
-        sample = min(B, max(ref.cores * 4, 32))
+        sample = B if workload.startswith("kitti") else min(B, 256)
         ref.run(min(sample, max(ref.cores, 8)))
         reps_cpu, t_cpu = 0, 0.0
-        while t_cpu < 8.0 and reps_cpu < 20:
+        while t_cpu < 10.0 and reps_cpu < 100:
             t_cpu += ref.run(sample)
             reps_cpu += 1
         ref.close()
@@ -406,26 +665,33 @@ def run_ours(args, rank, world, local_rank):
                "sample": f"{sample} frames x {reps_cpu} repeats ({t_cpu:.1f} s); {how}"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 keys (integer chamfer) + f32 copy", "data": "synthetic",
         "config": {"workload": (f"kitti64: batch of {B} synthetic KITTI 64-beam frames 352x1216 (~5% density) per GPU "
-                                "(BASELINE.json configs[1])") if args.workload == "kitti64" else
-                               f"{args.workload}: batch of {B} synthetic frames {H}x{W} per GPU",
+                                "(BASELINE.json configs[1])") if workload == "kitti64" else
+                               f"{workload}: batch of {B} synthetic frames {H}x{W} per GPU",
                    "outputs": "filled depth f32 + distance channel f32 + validity mask u8 (13 B/px algorithmic)",
                    "l2": f"inputs+outputs per step {ALG_BYTES_PER_PX * px_step / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                    "frames_per_step_per_gpu": B,
                    "pipeline": (f"{args.pipeline} batches in flight (dtfill_set_pipeline_depth): K1/K1b of step n+1 "
-                                f"overlap K2 of step n; {args.pipeline} output sets rotate; all outputs complete at the end "
-                                "of the timed region") if args.pipeline > 1 else "strict stream order between steps"},
-        "strict": strict,
+                                f"overlap K2 of step n; {no} output sets rotate; all outputs complete at the end "
+                                "of every timed block") if args.pipeline > 1 else "strict stream order between steps",
+                   "timing": f"blocks of {K} steps between CUDA events (max over ranks), repeated until the timed region "
+                             "has lasted min_seconds; value = median block"},
+        "timed_region_s": sum(blocks) * 1e-3, "blocks": len(blocks),
+        "block_ms": {"median": ms, "min": min(blocks), "max": max(blocks)},
+        "strict": strict, "parity_checked": int(len(sel)),
+        "parity_what": f"{len(sel)} frames of the timed run's own outputs (depth, dt, mask; lbl in a second pass in the "
+                       "same mode) bit-identical to oracle/dtfill_oracle.c, on every rank",
         "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W * 4),
-                "d2h_bytes_per_step": int(B * H * W * 9), "steps": e2e_steps,
-                "what": "dtfill_run (C ABI) with pinned host numpy buffers in and out, synchronous"},
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "e2e": e2e, "e2e_pinned": e2e_pinned, "sweep": sweep,
+        "gpu_launches": launches_per_step * K * len(blocks), "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks, "clocks_strict": clocks_strict,
     }
     print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -437,11 +703,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU and step (default: the workload's)")
-    ap.add_argument("--workload", default="kitti64", choices=sorted(WORKLOADS),
-                    help="kitti64 is the BASELINE.json metric; the others are the remaining configs")
+    ap.add_argument("--workload", default="kitti64", choices=sorted(WORKLOADS) + ["sweep"],
+                    help="kitti64 is the BASELINE.json metric (its line also carries the sweep); sweep runs configs[4] alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--pipeline", type=int, default=4, choices=[1, 2, 3, 4],
                     help="batches in flight in the device-resident timing (1 = strict stream order)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="least duration of the timed region")
+    ap.add_argument("--parity-frames", type=int, default=64)
+    ap.add_argument("--sweep-frames", type=int, default=8192)
+    ap.add_argument("--sweep-batch", type=int, default=256)
     ap.add_argument("--band-cap", type=int, default=None, help="override the band planner target (row steps)")
     ap.add_argument("--subbatches", type=int, default=None, help="override the number of sub-batch streams")
     args = ap.parse_args()

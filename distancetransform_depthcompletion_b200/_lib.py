@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("DTFILL_LIB") or os.path.join(_HERE, "libdtfill.so")
 E_ARG, E_CUDA, E_INDEX, E_NOMEM = -1, -2, -3, -4
 METRICS_KITTI, METRICS_NYU = 0, 1
 METRIC_COLS = 9
-ABI_VERSION = 3          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
+ABI_VERSION = 4          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
 METRIC_NAMES = ("mse", "rmse", "mae", "irmse", "imae", "delta1", "delta2", "delta3", "count")
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -56,6 +56,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_run.argtypes = [vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, ci, _c_int_p]
         L.dtfill_run_async.argtypes = [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp]
         L.dtfill_status.argtypes = [vp, _c_int_p, _c_int_p]
+        L.dtfill_run_eval_async.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp, vp]
+        L.dtfill_eval_totals.argtypes = [vp, vp, ci]
         L.dtfill_metrics.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.dtfill_metrics_ex.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, ci]
         L.dtfill_nccl_unique_id.argtypes = [vp]
@@ -85,7 +87,8 @@ def load() -> ctypes.CDLL:
                      "dtfill_status", "dtfill_run_u16", "dtfill_run_u16_async", "dtfill_metrics", "dtfill_host_alloc", "dtfill_set_profiling", "dtfill_set_band_cap", "dtfill_set_sky_min", "dtfill_set_subbatches", "dtfill_set_pipeline_depth",
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
-                     "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip"):
+                     "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip",
+                     "dtfill_run_eval_async", "dtfill_eval_totals"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -204,6 +207,18 @@ class Handle:
         _check(self._L.dtfill_run_async(self._h, _ptr(in_ptr), B, H, W, float(src_thr), float(val_thr), _ptr(depth_ptr),
                                         _ptr(dt_ptr), _ptr(lbl_ptr), _ptr(mask_ptr), _ptr(counts_ptr)),
                "dtfill_run_async")
+
+    def run_eval_async(self, in_ptr: int, gt_ptr: int, gt_is_f64: bool, B: int, H: int, W: int, src_thr: float,
+                       val_thr: float, mode: int, depth_ptr: int, dt_ptr=None, lbl_ptr=None, mask_ptr=None,
+                       counts_ptr=None):
+        """Fill + per-frame metrics of the filled depth against gt, added to the handle's running totals."""
+        _check(self._L.dtfill_run_eval_async(self._h, _ptr(in_ptr), _ptr(gt_ptr), int(bool(gt_is_f64)), B, H, W,
+                                             float(src_thr), float(val_thr), int(mode), _ptr(depth_ptr), _ptr(dt_ptr),
+                                             _ptr(lbl_ptr), _ptr(mask_ptr), _ptr(counts_ptr)), "dtfill_run_eval_async")
+
+    def eval_totals(self, sums_ptr: int, accumulate: bool = False):
+        """Join the calls in flight and write / add the running totals [10] to the device vector at sums_ptr."""
+        _check(self._L.dtfill_eval_totals(self._h, _ptr(sums_ptr), int(bool(accumulate))), "dtfill_eval_totals")
 
     def status(self):
         """Synchronise; returns (first_bad_frame or -1, kernel launches of the last run)."""

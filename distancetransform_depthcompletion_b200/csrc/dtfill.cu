@@ -121,6 +121,8 @@ struct PinBuf {
 struct Lane {
     static const int MAX_SUB = 16;
     Buf srcbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
+    Buf ev_partial, ev_per_frame, ev_totals;   // dtfill_run_eval_async: metric partial sums / per-frame metrics / running totals
+    bool ev_dirty = false;                     // ev_totals holds sums not yet collected by dtfill_eval_totals
     cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
     cudaStream_t side[MAX_SUB] = {};     // narrow tiles run next to the full-width tasks of the same sub-batch
@@ -161,6 +163,9 @@ struct dtfill_ctx {
     bool in_u16 = false;
     int in_H = 0, in_crop = 0;
     float* lidar_dev = nullptr;
+    // evaluation fused behind the call being enqueued (dtfill_run_eval_async): ground truth, mode
+    const void* ev_gt = nullptr;
+    int ev_gt_f64 = 0, ev_mode = 0;
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
     cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
@@ -613,6 +618,33 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
         if (drain.joinable()) drain.join();
         if (rc) return rc;
     }
+    if (h->ev_gt) {
+        // evaluation.py:82-123 / :196-239 on the filled depth of this call, on the call's own stream: per-frame metrics,
+        // their column sums added to the lane's running totals (eval.py:212-232 `+=`), no host synchronisation
+        const long fnpx = (long)H * W;
+        int chunks = (int)((fnpx + 16383) / 16384);
+        if (chunks < 1) chunks = 1;
+        if (chunks > 64) chunks = 64;
+        while (chunks > 1 && (((fnpx + chunks - 1) / chunks) & 3)) --chunks;
+        if ((rc = ensure(h, L->ev_partial, (size_t)B * chunks * ACC * 8))) return rc;
+        if ((rc = ensure(h, L->ev_per_frame, (size_t)B * 9 * 8))) return rc;
+        if (!L->ev_totals.p) {
+            if ((rc = ensure(h, L->ev_totals, 10 * 8))) return rc;
+            CU(cudaMemsetAsync(L->ev_totals.p, 0, 10 * 8, s));
+        }
+        dim3 grid(chunks, B);
+        double* part = (double*)L->ev_partial.p;
+        if (h->ev_gt_f64) {
+            if (h->ev_mode == 0) k4_metrics_partial<double, 0><<<grid, 256, 0, s>>>(out_depth, (const double*)h->ev_gt, fnpx, chunks, part);
+            else k4_metrics_partial<double, 1><<<grid, 256, 0, s>>>(out_depth, (const double*)h->ev_gt, fnpx, chunks, part);
+        } else {
+            if (h->ev_mode == 0) k4_metrics_partial<float, 0><<<grid, 256, 0, s>>>(out_depth, (const float*)h->ev_gt, fnpx, chunks, part);
+            else k4_metrics_partial<float, 1><<<grid, 256, 0, s>>>(out_depth, (const float*)h->ev_gt, fnpx, chunks, part);
+        }
+        k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, h->ev_mode, (double*)L->ev_per_frame.p, (double*)L->ev_totals.p, 1);
+        launches += 2;
+        L->ev_dirty = true;
+    }
     CU(cudaMemcpyAsync(h->status_ring + 2 * slot, L->status.p, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(h->slot_done[slot], s));
     h->slot_dirty[slot] = true;
@@ -699,7 +731,7 @@ void dtfill_destroy(dtfill_t* h) {
     cudaDeviceSynchronize();
     for (Lane& L : h->lanes) {
         Buf* lb[] = {&L.srcbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
-                     &L.scratch, &L.tasks, &L.status, &L.sky, &L.skykeys};
+                     &L.scratch, &L.tasks, &L.status, &L.sky, &L.skykeys, &L.ev_partial, &L.ev_per_frame, &L.ev_totals};
         for (Buf* b : lb)
             if (b->p) cudaFree(b->p);
         if (L.fork_ev) cudaEventDestroy(L.fork_ev);
@@ -928,6 +960,48 @@ int dtfill_run_u16_async(dtfill_t* h, const uint16_t* in_dev, int B, int H_in, i
     InputScope scope(h, true, H_in, crop_top, out_lidar_dev);
     return enqueue(h, in_dev, B, H_in - crop_top, W, src_thr, val_thr, out_depth_dev, out_dt_dev, out_lbl_dev, out_mask_dev,
                    out_counts_dev);
+}
+
+namespace {
+struct LaneTotals { const double* p[dtfill_ctx::MAX_LANES]; };
+__global__ void k4_fold_totals(LaneTotals lanes, double* __restrict__ sums, int accumulate) {
+    const int i = threadIdx.x;
+    if (i >= 10) return;
+    double s = accumulate ? sums[i] : 0.0;
+    for (int l = 0; l < dtfill_ctx::MAX_LANES; ++l)
+        if (lanes.p[l]) s += lanes.p[l][i];       // fixed order: lane 0, 1, 2, 3
+    sums[i] = s;
+}
+struct EvalScope {
+    dtfill_t* h;
+    EvalScope(dtfill_t* h_, const void* gt, int f64, int mode) : h(h_) { h->ev_gt = gt; h->ev_gt_f64 = f64; h->ev_mode = mode; }
+    ~EvalScope() { h->ev_gt = nullptr; }
+};
+}  // namespace
+
+int dtfill_run_eval_async(dtfill_t* h, const float* in_dev, const void* gt_dev, int gt_is_f64, int B, int H, int W,
+                          float src_thr, float val_thr, int mode, float* out_depth_dev, float* out_dt_dev,
+                          int32_t* out_lbl_dev, uint8_t* out_mask_dev, int32_t* out_counts_dev) {
+    if (!h || !gt_dev) return fail(DTFILL_E_ARG, "dtfill_run_eval_async: NULL handle or ground truth");
+    if (mode != DTFILL_METRICS_KITTI && mode != DTFILL_METRICS_NYU) return fail(DTFILL_E_ARG, "dtfill_run_eval_async: bad mode");
+    EvalScope scope(h, gt_dev, gt_is_f64, mode);
+    return enqueue(h, in_dev, B, H, W, src_thr, val_thr, out_depth_dev, out_dt_dev, out_lbl_dev, out_mask_dev,
+                   out_counts_dev);
+}
+
+int dtfill_eval_totals(dtfill_t* h, double* sums_dev, int accumulate) {
+    if (!h || !sums_dev) return fail(DTFILL_E_ARG, "dtfill_eval_totals: NULL handle or sums");
+    CU(cudaSetDevice(h->device));
+    int rc = dtfill_flush(h);                 // the handle's stream now follows every call in flight
+    if (rc) return rc;
+    LaneTotals lt;
+    for (int l = 0; l < dtfill_ctx::MAX_LANES; ++l)
+        lt.p[l] = h->lanes[l].ev_dirty ? (const double*)h->lanes[l].ev_totals.p : nullptr;
+    k4_fold_totals<<<1, 32, 0, h->stream>>>(lt, sums_dev, accumulate);
+    for (Lane& L : h->lanes)
+        if (L.ev_dirty) { CU(cudaMemsetAsync(L.ev_totals.p, 0, 10 * 8, h->stream)); L.ev_dirty = false; }
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device, int B, int H, int W,

@@ -44,6 +44,36 @@ class DTFillEngine:
                                      lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
         return dict(depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
 
+    def fill_eval(self, frames, gt, mode: int = _lib.METRICS_KITTI, src_thr: float = 0.1, val_thr: float = 0.1, out=None):
+        """One step of an evaluation sweep (eval.py:212-232): fill ``frames`` and add the per-frame metrics of the filled
+        depth against ``gt`` (float32/float64 CUDA tensor [B,H,W]) to the engine's running totals; enqueued only,
+        pipelined like fill().  Collect with eval_totals()."""
+        torch = self.torch
+        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 3
+        assert gt.is_cuda and gt.is_contiguous() and gt.shape == frames.shape and gt.dtype in (torch.float32, torch.float64)
+        B, H, W = frames.shape
+        out = out or {}
+        dev = frames.device
+        depth = out.get("depth") if out.get("depth") is not None else torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        dt = out.get("dt") if out.get("dt") is not None else torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        mask = out.get("mask") if out.get("mask") is not None else torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        counts = out.get("counts") if out.get("counts") is not None else torch.empty((B, 2), dtype=torch.int32, device=dev)
+        self._bind_stream()
+        self.handle.run_eval_async(frames.data_ptr(), gt.data_ptr(), gt.dtype == torch.float64, B, H, W, src_thr, val_thr,
+                                   mode, depth.data_ptr(), dt.data_ptr(), None, mask.data_ptr(), counts.data_ptr())
+        return dict(depth=depth, dt=dt, mask=mask, lbl=None, counts=counts)
+
+    def eval_totals(self, totals=None):
+        """Running totals [mse, rmse, mae, irmse, imae, d1, d2, d3, valid px, frames] of the fill_eval() calls since the
+        last collection, as a float64 CUDA tensor (added to ``totals`` if given); enqueued on torch's current stream."""
+        torch = self.torch
+        acc = totals is not None
+        if totals is None:
+            totals = torch.empty((_lib.METRIC_COLS + 1,), dtype=torch.float64, device=torch.device("cuda", self.device))
+        self._bind_stream()
+        self.handle.eval_totals(totals.data_ptr(), accumulate=acc)
+        return totals
+
     def fill_png(self, png, crop_top: int = 96, src_thr: float = 0.1, val_thr: float = 0.1, want_lidar: bool = True,
                  want_lbl: bool = False):
         """png: uint16 CUDA tensor [B,H_in,W] of KITTI depth PNG samples (depth = sample / 256, data_read.py:215);

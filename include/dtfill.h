@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTFILL_ABI_VERSION 3      /* 3: dtfill_metrics_ex, dtfill_allreduce_sums + dtfill_comm_*, status ring */
+#define DTFILL_ABI_VERSION 4      /* 4: dtfill_run_eval_async + dtfill_eval_totals, dtfill_edt; 3: metrics_ex, allreduce, status ring */
 
 enum {
     DTFILL_OK = 0,
@@ -134,6 +134,23 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
 int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64, int in_is_device,
                       int B, int H, int W, int mode, double* per_frame, double* sums, int out_is_device,
                       int accumulate);
+
+/*
+ * One step of an evaluation sweep, fused (BASELINE.json configs[4]; the loop body of eval.py:212-232: DT_complete_batch,
+ * Result.evaluate per frame, running `+=` of the per-frame metrics): dtfill_run_async followed, on the same internal
+ * stream, by the metric kernels on the filled depth against gt_dev (float64 when gt_is_f64, else float32, [B,H,W]).  The
+ * column sums of the per-frame metrics and the frame count are added to running totals the handle keeps per pipeline
+ * lane, so in pipelined mode consecutive steps overlap like plain fills and nothing synchronises with the host.
+ * dtfill_eval_totals collects them: it joins the calls in flight (dtfill_flush) and writes (accumulate == 0) or adds
+ * (accumulate != 0) the totals [DTFILL_METRIC_COLS + 1] to the device vector sums_dev on the handle's stream, in a fixed
+ * order, and clears the handle's running totals -- ready for dtfill_allreduce_sums.  Bad frames (IndexError) are
+ * reported by dtfill_status as for dtfill_run_async; their metrics are undefined.
+ */
+int dtfill_run_eval_async(dtfill_t* h, const float* in_dev, const void* gt_dev, int gt_is_f64, int B, int H, int W,
+                          float src_thr, float val_thr, int mode,
+                          float* out_depth_dev, float* out_dt_dev, int32_t* out_lbl_dev, uint8_t* out_mask_dev,
+                          int32_t* out_counts_dev);
+int dtfill_eval_totals(dtfill_t* h, double* sums_dev, int accumulate);
 
 /*
  * Multi-GPU: frames shard contiguously over one process per GPU with no data-path exchange; the only
