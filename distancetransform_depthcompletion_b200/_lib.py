@@ -80,6 +80,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_dt_pool.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
         L.dtfill_dt_pool_ex.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.dtfill_outlier_removal.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci]
+        L.dtfill_edt.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, ci]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
         L.dtfill_host_free.restype = None
@@ -88,7 +89,7 @@ def load() -> ctypes.CDLL:
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
                      "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip",
-                     "dtfill_run_eval_async", "dtfill_eval_totals"):
+                     "dtfill_run_eval_async", "dtfill_eval_totals", "dtfill_edt"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -120,11 +121,32 @@ def _ptr(a):
     return ctypes.c_void_p(int(a))
 
 
+class _Serialised:
+    """The library's entry points behind one lock: a dtfill_t is used from one host thread at a time (include/dtfill.h)
+    and ctypes releases the GIL during a call, so two Python threads sharing the per-device handle of get_handle()
+    (a loader thread and an evaluation thread, say) would otherwise interleave on its staging buffers."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock = lib, lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lock = self._lock
+
+        def call(*args):
+            with lock:
+                return fn(*args)
+        setattr(self, name, call)
+        return call
+
+
 class Handle:
-    """One dtfill_t: a CUDA device, a stream and a growing workspace (include/dtfill.h)."""
+    """One dtfill_t: a CUDA device, a stream and a growing workspace (include/dtfill.h).  Calls are serialised per
+    handle, so a Handle may be shared between Python threads."""
 
     def __init__(self, device: int = 0):
-        self._L = load()
+        self._lock = threading.RLock()
+        self._L = _Serialised(load(), self._lock)
         h = ctypes.c_void_p()
         _check(self._L.dtfill_create(int(device), ctypes.byref(h)), "dtfill_create")
         self._h = h
@@ -296,6 +318,14 @@ class Handle:
                                          _ptr(out_ptr), _ptr(masks_ptr), 1), "dtfill_dt_pool")
         return None
 
+    def edt(self, frames: np.ndarray, src_thr: float, want_idx: bool = True):
+        """Exact Euclidean feature transform (extension): frames float32 [B,H,W] -> (d2 int32, idx int32 or None)."""
+        B, H, W = frames.shape
+        d2 = np.empty((B, H, W), np.int32)
+        idx = np.empty((B, H, W), np.int32) if want_idx else None
+        _check(self._L.dtfill_edt(self._h, _ptr(frames), 0, B, H, W, float(src_thr), _ptr(d2), _ptr(idx), 0), "dtfill_edt")
+        return d2, idx
+
     def outlier_removal(self, frames: np.ndarray) -> np.ndarray:
         """frames float32 [B,H,W] -> filtered float32 [B,H,W] (data_read.py:103-128)."""
         B, H, W = frames.shape
@@ -371,28 +401,72 @@ def get_handle(device: int | None = None) -> Handle:
     return h
 
 
-def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
-    """numpy array backed by page-locked host memory (dtfill_host_alloc): fast host<->device copies."""
+class _PinnedBlock:
+    """Owner of one page-locked host buffer; numpy arrays made from it keep it alive through ``.base``.  When the last
+    array goes away the buffer returns to the pool (pooled blocks) or is freed."""
+
+    def __init__(self, ptr: int, nbytes: int, shape, dtype, pooled: bool):
+        self.ptr, self.nbytes, self.pooled = ptr, nbytes, pooled
+        self.__array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": np.dtype(dtype).str,
+                                    "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_release(self.ptr, self.nbytes, self.pooled)
+        except Exception:       # interpreter shutdown
+            pass
+
+
+_pin_lock = threading.Lock()
+_pin_free: dict[int, list[int]] = {}      # size -> free pooled buffers
+_pin_free_bytes = 0
+# most page-locked memory kept for reuse by pinned_empty(pooled=True) (outputs handed to numpy callers)
+PINNED_POOL_MAX = int(os.environ.get("DTFILL_PINNED_POOL_MAX", str(4 << 30)))
+# largest single output that is handed out as page-locked memory at all (larger ones are ordinary numpy arrays)
+PINNED_OUT_MAX = int(os.environ.get("DTFILL_PINNED_OUT_MAX", str(1 << 30)))
+
+
+def _pinned_release(ptr: int, nbytes: int, pooled: bool):
+    global _pin_free_bytes
+    if pooled:
+        with _pin_lock:
+            if _pin_free_bytes + nbytes <= PINNED_POOL_MAX:
+                _pin_free.setdefault(nbytes, []).append(ptr)
+                _pin_free_bytes += nbytes
+                return
+    load().dtfill_host_free(ctypes.c_void_p(ptr))
+
+
+def pinned_empty(shape, dtype=np.float32, pooled: bool = False) -> np.ndarray:
+    """numpy array backed by page-locked host memory (dtfill_host_alloc): host<->device copies run at PCIe speed and
+    need no staging.  The memory is released when the array (and every view of it) is gone; with ``pooled`` it goes
+    back to a free list instead, so that a loop which receives a fresh output array per call does not pay for page
+    locking (or for the page faults of a fresh pageable array) every time."""
+    global _pin_free_bytes
     L = load()
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = ctypes.c_void_p()
-    _check(L.dtfill_host_alloc(ctypes.byref(p), n), "dtfill_host_alloc")
-    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                L.dtfill_host_free(self.ptr)
-            except Exception:
-                pass
-
-    _owners[arr.ctypes.data] = _Owner(p)
-    return arr
+    n = max(int(np.prod(shape)) * dtype.itemsize, 1)
+    ptr = None
+    if pooled:
+        with _pin_lock:
+            lst = _pin_free.get(n)
+            if lst:
+                ptr = lst.pop()
+                _pin_free_bytes -= n
+    if ptr is None:
+        p = ctypes.c_void_p()
+        _check(L.dtfill_host_alloc(ctypes.byref(p), n), "dtfill_host_alloc")
+        ptr = p.value
+    return np.asarray(_PinnedBlock(ptr, n, shape, dtype, pooled))
 
 
-_owners: dict[int, object] = {}
+def output_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A fresh array for a result handed to a numpy caller (tools.py:13-35 returns a new array every call): page-locked
+    and pooled up to PINNED_OUT_MAX bytes, so the device-to-host copy lands in it directly; ordinary memory above that."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if 0 < n <= PINNED_OUT_MAX:
+        try:
+            return pinned_empty(shape, dtype, pooled=True)
+        except (MemoryError, DTFillError):
+            pass
+    return np.empty(shape, dtype)

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -50,6 +51,38 @@ struct Buf {
 // a small pool of threads copies a slice into a pinned mirror (and out of one), the DMA engines move pinned memory
 // in both directions, and the kernels of other slices run meanwhile.
 // ------------------------------------------------------------------------------------------------------------
+// memcpy whose stores bypass the cache (the destination is a staging mirror the CPU does not read back, or the caller's
+// array): no read-for-ownership of the destination lines, one third less memory traffic than a plain copy of a buffer
+// that does not fit the cache.  Falls back to memcpy on CPUs without AVX2.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void copy_stream_avx2(char* dst, const char* src, size_t n) {
+    size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+    if (head > n) head = n;
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i));
+        const __m256i b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64));
+        const __m256i d = _mm256_loadu_si256((const __m256i*)(src + i + 96));
+        _mm256_stream_si256((__m256i*)(dst + i), a);
+        _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+        _mm256_stream_si256((__m256i*)(dst + i + 64), c);
+        _mm256_stream_si256((__m256i*)(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+static void copy_stream(void* dst, const void* src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && n >= 4096) copy_stream_avx2((char*)dst, (const char*)src, n);
+    else memcpy(dst, src, n);
+}
+#else
+static void copy_stream(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
+#endif
+
 class CopyPool {
 public:
     explicit CopyPool(int n) {
@@ -64,7 +97,7 @@ public:
     void copy(void* dst, const void* src, size_t bytes) {
         const size_t grain = 2u << 20;
         const size_t nparts = bytes / grain > 0 ? std::min<size_t>(bytes / grain, (th_.size() + 1) * 4) : 1;
-        if (nparts <= 1 || th_.empty()) { memcpy(dst, src, bytes); return; }
+        if (nparts <= 1 || th_.empty()) { copy_stream(dst, src, bytes); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
             dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; nparts_ = nparts; next_ = 0; done_ = 0;
@@ -86,7 +119,7 @@ private:
                 i = next_++;
             }
             const size_t a = bytes_ * i / nparts_, b = bytes_ * (i + 1) / nparts_;
-            memcpy(dst_ + a, src_ + a, b - a);
+            copy_stream(dst_ + a, src_ + a, b - a);
             std::lock_guard<std::mutex> lk(mu_);
             if (++done_ == nparts_) cv_done_.notify_all();
         }
@@ -169,7 +202,7 @@ struct dtfill_ctx {
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
     cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
-    Buf gt_dev, partial, per_frame, sums;
+    Buf gt_dev, partial, per_frame, sums, edt_rows, edt_bits;
     // pinned mirrors of pageable caller buffers (see CopyPool) and the threads that fill / drain them
     PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar;
     CopyPool* pool_in = nullptr;
@@ -748,7 +781,7 @@ void dtfill_destroy(dtfill_t* h) {
         }
     }
     Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->lidar_out_dev,
-                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums};
+                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_bits};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* q : h->retired) cudaFree(q);
@@ -884,7 +917,13 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
             if (pin_i || pin_d || pin_t || pin_l || pin_m || pin_x) {
                 if (!h->pool_in) {
                     int n = h->stage_threads;
-                    if (n < 0) { n = (int)std::thread::hardware_concurrency() / 4; n = n < 2 ? 2 : (n > 8 ? 8 : n); }
+                    if (n < 0) {      // half of the CPUs this process may run on, 2..8
+                        cpu_set_t set;
+                        int avail = (int)std::thread::hardware_concurrency();
+                        if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+                        n = avail / 2;
+                        n = n < 2 ? 2 : (n > 8 ? 8 : n);
+                    }
                     h->pool_in = new CopyPool(n - 1);       // the calling thread works too
                     h->pool_out = new CopyPool(n - 1);
                 }
@@ -1239,6 +1278,59 @@ int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B
     CU(cudaGetLastError());
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out, o_d, npx * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int dtfill_edt(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float src_thr, int32_t* out_d2,
+               int32_t* out_idx, int out_is_device) {
+    if (!h || !in || !out_d2) return fail(DTFILL_E_ARG, "dtfill_edt: NULL handle, input or out_d2");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_edt: B, H, W must be positive");
+    if (H > 32 * EDT_MAX_CHUNKS || H > 32767 || W > 32767 || (size_t)EDT_ROWS_PER_BLOCK * W * 2 > 200 * 1024)
+        return fail(DTFILL_E_ARG, "dtfill_edt: frame size not supported (H <= 4096, W <= 25600)");
+    CU(cudaSetDevice(h->device));
+    { int frc = dtfill_flush(h); if (frc) return frc; }
+    const size_t npx = (size_t)B * H * W;
+    const int WW = (W + 31) / 32;
+    cudaStream_t s = h->stream;
+    int rc;
+    const float* i_d = in;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, in, npx * 4, cudaMemcpyHostToDevice, s));
+        i_d = (const float*)h->in_dev.p;
+    }
+    int32_t* d2 = out_d2; int32_t* ix = out_idx;
+    if (!out_is_device) {
+        if ((rc = ensure(h, h->depth_dev, npx * 4))) return rc;
+        d2 = (int32_t*)h->depth_dev.p;
+        if (out_idx) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ix = (int32_t*)h->lbl_dev.p; }
+    }
+    if ((rc = ensure(h, h->edt_bits, (size_t)B * H * WW * 4))) return rc;
+    if ((rc = ensure(h, h->edt_rows, npx * 2))) return rc;
+    const long nrows = (long)B * H;
+    {
+        const long nwords = nrows * WW;
+        const unsigned grid = (unsigned)((nwords * 32 + 255) / 256);
+        k7_edt_bits<<<grid, 256, 0, s>>>(i_d, (long)npx, W, WW, source_cut(src_thr), (uint32_t*)h->edt_bits.p);
+    }
+    k7_edt_columns<<<dim3(WW, B), 32, 0, s>>>((const uint32_t*)h->edt_bits.p, H, W, WW, (uint16_t*)h->edt_rows.p);
+    {
+        const size_t smem = (size_t)EDT_ROWS_PER_BLOCK * W * 2;
+        const unsigned grid = (unsigned)((nrows + EDT_ROWS_PER_BLOCK - 1) / EDT_ROWS_PER_BLOCK);
+        const bool tma = (W & 7) == 0;          // 16-byte aligned rows: one cp.async.bulk per block
+        if (smem > 48 * 1024) {
+            CU(cudaFuncSetAttribute(k7_edt_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(k7_edt_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (tma) k7_edt_rows<true><<<grid, 256, smem, s>>>((const uint16_t*)h->edt_rows.p, nrows, H, W, d2, ix);
+        else k7_edt_rows<false><<<grid, 256, smem, s>>>((const uint16_t*)h->edt_rows.p, nrows, H, W, d2, ix);
+    }
+    CU(cudaGetLastError());
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out_d2, d2, npx * 4, cudaMemcpyDeviceToHost, s));
+        if (out_idx) CU(cudaMemcpyAsync(out_idx, ix, npx * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
     return 0;

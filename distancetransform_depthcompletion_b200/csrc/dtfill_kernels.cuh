@@ -16,6 +16,7 @@
 //   K4  k4_metrics_*      masked RMSE/MAE/iRMSE/iMAE(/REL/delta) reductions of evaluation.py:82-123, 196-239
 //   K5  k5_dt_pool_*      one level of the CNN input stage's DT pooling (net.py:71-123)
 //   K6  k6_outlier_removal  KITTI outlier filter (data_read.py:103-128)
+//   K7  k7_edt_*          exact Euclidean feature transform (extension): column pass + parabola row pass
 // One header per kernel (dtfill_k*.cuh); dtfill_common.cuh holds the key format, the structs and the helpers.
 //
 // Key format of the fast path: dist:11 | order:4 | label:17.  "order" is the position
@@ -34,3 +35,4 @@
 #include "dtfill_k4_metrics.cuh"
 #include "dtfill_k5_pool.cuh"
 #include "dtfill_k6_outlier.cuh"
+#include "dtfill_k7_edt.cuh"

@@ -11,15 +11,40 @@ class DTFillEngine:
     """Runs DT + NN fill (+ metrics) on torch CUDA tensors, on torch's current stream, without host copies."""
 
     def __init__(self, device: int | None = None, pipeline_depth: int = 1):
-        """pipeline_depth 2: consecutive fill() calls may overlap on the GPU (the HBM-bound first stage of one batch
+        """pipeline_depth 2..4: consecutive fill() calls may overlap on the GPU (the HBM-bound first stage of one batch
         with the ALU-bound scan of the previous one); their outputs are final after flush() / status(), and a
-        call's output tensors must not be handed to the next call."""
+        call's output tensors must not be handed to the next call.  Inputs and outputs of the calls in flight are
+        kept alive by the engine until flush() / status() / eval_totals()."""
         import torch
         self.torch = torch
         self.device = _lib.default_device() if device is None else int(device)
         self.handle = _lib.Handle(self.device)
+        self.pipeline_depth = max(1, int(pipeline_depth))
         if pipeline_depth != 1:
             self.handle.set_pipeline_depth(pipeline_depth)
+        # pipelined mode: the kernels of a call run on library-internal streams that torch's caching allocator knows
+        # nothing about, so the tensors of the calls in flight are kept alive here until they have been joined
+        self._inflight = {}
+
+    def _hold(self, *tensors):
+        if self.pipeline_depth > 1:
+            key = tuple(t.data_ptr() for t in tensors if t is not None)
+            self._inflight[key] = tensors
+            if len(self._inflight) > 8 * self.pipeline_depth:
+                # a caller that allocates fresh tensors for every call: join the calls in flight (stream-level, no
+                # host synchronisation) so that the older tensors can go back to the allocator
+                self.handle.flush()
+                self._inflight = {key: tensors}
+
+    def close(self):
+        """Wait for the work in flight and release the handle."""
+        if getattr(self, "handle", None) is not None:
+            try:
+                self.handle.synchronize()
+            finally:
+                self._inflight = {}
+                self.handle.close()
+                self.handle = None
 
     def _bind_stream(self):
         # torch reports the legacy default stream as handle 0; CUDA's explicit handle for it is cudaStreamLegacy (0x1)
@@ -42,6 +67,7 @@ class DTFillEngine:
         self._bind_stream()
         self.handle.run_device_async(frames.data_ptr(), B, H, W, src_thr, val_thr, depth.data_ptr(), dt.data_ptr(),
                                      lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
+        self._hold(frames, depth, dt, mask, lbl, counts)
         return dict(depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
 
     def fill_eval(self, frames, gt, mode: int = _lib.METRICS_KITTI, src_thr: float = 0.1, val_thr: float = 0.1, out=None):
@@ -61,6 +87,7 @@ class DTFillEngine:
         self._bind_stream()
         self.handle.run_eval_async(frames.data_ptr(), gt.data_ptr(), gt.dtype == torch.float64, B, H, W, src_thr, val_thr,
                                    mode, depth.data_ptr(), dt.data_ptr(), None, mask.data_ptr(), counts.data_ptr())
+        self._hold(frames, gt, depth, dt, mask, counts)
         return dict(depth=depth, dt=dt, mask=mask, lbl=None, counts=counts)
 
     def eval_totals(self, totals=None):
@@ -72,6 +99,7 @@ class DTFillEngine:
             totals = torch.empty((_lib.METRIC_COLS + 1,), dtype=torch.float64, device=torch.device("cuda", self.device))
         self._bind_stream()
         self.handle.eval_totals(totals.data_ptr(), accumulate=acc)
+        self._inflight = {}
         return totals
 
     def fill_png(self, png, crop_top: int = 96, src_thr: float = 0.1, val_thr: float = 0.1, want_lidar: bool = True,
@@ -95,16 +123,20 @@ class DTFillEngine:
         self.handle.run_device_u16_async(png.data_ptr(), B, Hin, W, int(crop_top), src_thr, val_thr, depth.data_ptr(),
                                          lidar.data_ptr() if lidar is not None else None, dt.data_ptr(),
                                          lbl.data_ptr() if lbl is not None else None, mask.data_ptr(), counts.data_ptr())
+        self._hold(png, lidar, depth, dt, mask, lbl, counts)
         return dict(lidar=lidar, depth=depth, dt=dt, mask=mask, lbl=lbl, counts=counts)
 
     def flush(self):
         """Pipelined mode: torch's current stream waits for every fill still in flight."""
         self._bind_stream()
         self.handle.flush()
+        self._inflight = {}       # torch's current stream now follows every call: ordinary stream-ordered reuse is safe
 
     def status(self):
         """Synchronise; (first_bad_frame or -1, kernel launches of the last fill)."""
-        return self.handle.status()
+        r = self.handle.status()
+        self._inflight = {}
+        return r
 
     def metrics(self, pred, gt, mode: int = _lib.METRICS_KITTI, totals=None):
         """pred float32 [B,H,W], gt float32/float64 [B,H,W] CUDA tensors -> (per_frame [B,9], sums [10]) CUDA f64.

@@ -55,6 +55,34 @@ class _ResultBase(object):
         self.photometric = 0
         self.count = 0.0
 
+    # the bookkeeping half of the reference classes (evaluation.py:29-80 / :143-194): plain host arithmetic
+    _AVERAGED = ("irmse", "imae", "mse", "rmse", "mae", "absrel", "squared_rel", "lg10", "delta1", "delta2", "delta3",
+                 "data_time", "gpu_time", "silog", "photometric")
+    _WORST_INF = ("irmse", "imae", "mse", "rmse", "mae", "absrel", "squared_rel", "lg10", "silog")
+    _WORST_ZERO = ("delta1", "delta2", "delta3", "data_time", "gpu_time")
+
+    def set_to_worst(self):
+        """evaluation.py:29-43."""
+        for name in self._WORST_INF:
+            setattr(self, name, np.inf)
+        for name in self._WORST_ZERO:
+            setattr(self, name, 0)
+
+    def update(self, irmse, imae, mse, rmse, mae, absrel, squared_rel, lg10, delta1, delta2, delta3, gpu_time,
+               data_time, silog, photometric=0):
+        """evaluation.py:63-79: add one frame's metrics to the running sums."""
+        self.count += 1.0
+        given = dict(irmse=irmse, imae=imae, mse=mse, rmse=rmse, mae=mae, absrel=absrel, squared_rel=squared_rel,
+                     lg10=lg10, delta1=delta1, delta2=delta2, delta3=delta3, gpu_time=gpu_time, data_time=data_time,
+                     silog=silog, photometric=photometric)
+        for name, v in given.items():
+            setattr(self, name, getattr(self, name) + v)
+
+    def finalize(self):
+        """evaluation.py:46-61: running sums -> means over ``count`` frames."""
+        for name in self._AVERAGED:
+            setattr(self, name, getattr(self, name) / self.count)
+
     def evaluate(self, output, target, photometric=0):
         output, target = _prep(output, target)
         per_frame, _ = _lib.get_handle().metrics(output, target, 1, 1, int(output.size), self._mode,

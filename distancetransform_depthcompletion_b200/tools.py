@@ -48,7 +48,10 @@ def DT_complete_batch(lidar_batch, device: int | None = None):
     if min(H, W) < 2:
         raise ValueError("DT_complete_batch: frames must be 2-D after squeeze")
     frames = _as_frames_f32(lidar_batch[:, :, :, 0], "DT_complete_batch")                           # tools.py:19
-    r = _lib.get_handle(device).run_host(frames, KITTI_SRC_THR, VALID_THR)
+    # the result is a new array the caller owns (tools.py:27-33); its memory is page-locked and pooled so that the
+    # device-to-host copy lands in it directly
+    out = {"depth": _lib.output_empty((B, _H, _W), np.float32)}
+    r = _lib.get_handle(device).run_host(frames, KITTI_SRC_THR, VALID_THR, want_counts=False, out=out)
     if "index_error" in r:
         raise IndexError(r["index_error"])                                                          # tools.py:26
     return r["depth"].reshape(B, _H, _W, 1)                                                         # tools.py:27-33
@@ -66,6 +69,21 @@ def dt_fill_batch(frames, src_thr: float = KITTI_SRC_THR, val_thr: float = VALID
     if "index_error" in r:
         raise IndexError(r["index_error"])
     return r
+
+
+def euclidean_feature_transform(frames, thr: float = KITTI_SRC_THR, device: int | None = None):
+    """EXTENSION, not part of the reference (its transform is the 5x5 chamfer of nearest_point): the exact Euclidean
+    feature transform of the same source mask (tools.py:8 predicate).  frames float32 [B,H,W] or [H,W] ->
+    (d2 int32: squared distance to the nearest source, idx int32: y' * W + x' of such a source, -1 if the frame has
+    none).  ``np.sqrt(d2)`` is what scipy.ndimage.distance_transform_edt returns for the mask."""
+    x = _as_frames_f32(np.asarray(frames), "euclidean_feature_transform")
+    single = x.ndim == 2
+    if single:
+        x = x[None]
+    if x.ndim != 3:
+        raise ValueError("euclidean_feature_transform: expected [B,H,W] or [H,W]")
+    d2, idx = _lib.get_handle(device).edt(np.ascontiguousarray(x), thr)
+    return (d2[0], idx[0]) if single else (d2, idx)
 
 
 def DT_complete_batch_png(depth_png_batch, crop_top: int = 96, device: int | None = None):

@@ -189,6 +189,21 @@ int dtfill_dt_pool_ex(dtfill_t* h, const float* data, const float* mask, int in_
 int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float* out,
                            int out_is_device);
 
+/*
+ * EXTENSION (no reference function stands behind it: every call site of the reference computes the
+ * 5x5 chamfer transform above, tools.py:9): the exact Euclidean feature transform of the same source mask,
+ * source(p) = !((float)(1.0f - in[p]) > src_thr).  Separable: a column pass over the source bit rows (nearest source
+ * row per pixel), then per row the minimum over the parabolas (x - x')^2 + g(y,x')^2, rows staged in shared memory with
+ * cp.async.bulk.  in float32 [B,H,W]; out_d2 int32 [B,H,W] = squared distance to the nearest source (2^31 - 1 for a
+ * frame without sources); out_idx (nullable) int32 [B,H,W] = y' * W + x' of a source at that distance (-1 if none).
+ * Among several nearest sources the one in the column with the smallest |x - x'| wins, the left one on equal offsets,
+ * and within a column the nearer row, the upper one on equal distance.  H <= 4096, W <= 25600.
+ * Oracle: scipy.ndimage.distance_transform_edt (squared distances identical; an index is checked by the distance it
+ * attains).  Waits for completion when the outputs are host pointers.
+ */
+int dtfill_edt(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float src_thr,
+               int32_t* out_d2, int32_t* out_idx, int out_is_device);
+
 /* Pipelined mode.  depth 1 (default): strict stream order -- when a call's work completes, in stream order, its
  * outputs are final.  depth 2..4: consecutive dtfill_run_async calls may overlap: a call runs on one of `depth` internal
  * streams, behind whatever was queued on the handle's stream before it and behind the call `depth` back (which used the

@@ -275,3 +275,43 @@ def cv2_port_outlier_removal(lidar):
     lidar_aveg = lidar_sum / (lidar_count + 0.00001)                                            # :123
     potential_outliers = ((sparse_lidar - lidar_aveg) > 1.0).astype(np.float64)                 # :125
     return (sparse_lidar * (1 - potential_outliers)).astype(np.float32)                         # :128
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Exact Euclidean feature transform (an extension without a reference function): the oracle is
+# scipy.ndimage.distance_transform_edt on the source mask of tools.py:8; ``edt_bruteforce`` pins it on small frames.
+# ------------------------------------------------------------------------------------------------------------
+def source_mask(x: np.ndarray, thr: float = 0.1) -> np.ndarray:
+    """tools.py:8 in float32: True where the pixel is a source (value_mask == 0)."""
+    x = np.asarray(x, np.float32)
+    with np.errstate(invalid="ignore"):
+        return ~((np.float32(1.0) - x) > np.float32(thr))
+
+
+def edt(x: np.ndarray, thr: float = 0.1):
+    """(d2 int64 [H,W], idx int64 [H,W]) for one frame: squared Euclidean distance to the nearest source and the flat
+    index y' * W + x' of the source scipy picked (-1 / 2^31 - 1 when the frame has no source)."""
+    from scipy import ndimage
+    src = source_mask(x, thr)
+    H, W = src.shape
+    if not src.any():
+        return np.full((H, W), 2 ** 31 - 1, np.int64), np.full((H, W), -1, np.int64)
+    dist, ind = ndimage.distance_transform_edt(~src, return_distances=True, return_indices=True)
+    iy, ix = ind[0].astype(np.int64), ind[1].astype(np.int64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    d2 = (yy - iy) ** 2 + (xx - ix) ** 2
+    assert np.array_equal(np.rint(dist * dist).astype(np.int64), d2)
+    return d2, iy * W + ix
+
+
+def edt_bruteforce(x: np.ndarray, thr: float = 0.1) -> np.ndarray:
+    """Squared distance to the nearest source by exhaustive search (small frames only)."""
+    src = source_mask(x, thr)
+    H, W = src.shape
+    ys, xs = np.nonzero(src)
+    if len(ys) == 0:
+        return np.full((H, W), 2 ** 31 - 1, np.int64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    d = (yy[..., None] - ys[None, None, :]) ** 2 + (xx[..., None] - xs[None, None, :]) ** 2
+    return d.min(axis=-1).astype(np.int64)
+

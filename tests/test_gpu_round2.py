@@ -1,0 +1,258 @@
+"""GPU tests added in round 2: parity at the benchmarked batch sizes and pipeline depth, the per-call status ring, the
+fused evaluation step and its totals, the NCCL all-reduce behind the C ABI, the label-width boundary of the packed
+keys, synchronous calls while batches are in flight, pooled output buffers, threads sharing a handle.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+from distancetransform_depthcompletion_b200 import _lib, sharding, synth, tools
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle(dtfill_lib):
+    return _lib.get_handle()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    return pytest.importorskip("torch")
+
+
+def _bench_frames(workload, n):
+    import bench
+    return bench.make_frames(n, 0, workload), bench.WORKLOADS[workload][3]
+
+
+@pytest.mark.parametrize("workload,batch", [("kitti64", 256), ("kitti32", 256), ("kitti16", 256), ("kitti8", 256),
+                                            ("nyu", 1024)])
+def test_benchmarked_batches_pipelined_auto_cap(handle, torch_mod, workload, batch):
+    """The configurations DESIGN.md section 5 and bench.py quote (BASELINE.json configs[1..3]: 256 KITTI frames of
+    64/32/16/8 beams; configs[3]: 1024 NYU frames) through DTFillEngine(pipeline_depth=4) with the automatic band
+    target, which depends on the batch size and the depth: 64 frames of every run against the oracle, bit for bit."""
+    torch = torch_mod
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    frames, src_thr = _bench_frames(workload, batch)
+    x = torch.from_numpy(frames).cuda()
+    eng = DTFillEngine(0, pipeline_depth=4)
+    outs = [None] * 4
+    for i in range(6):                                   # several batches in flight, as in the timed region
+        outs[i % 4] = eng.fill(x, src_thr=src_thr, want_lbl=True, out=outs[i % 4])
+    eng.flush()
+    bad, _ = eng.status()
+    assert bad == -1
+    sel = np.unique(np.linspace(0, batch - 1, 64).astype(int))
+    want = O.dt_fill(frames[sel], src_thr=src_thr)
+    tsel = torch.from_numpy(sel).cuda()
+    for o in (outs[1], outs[0]):                         # the last call and the one three calls before it
+        for k in ("depth", "dt", "mask", "lbl"):
+            assert np.array_equal(o[k][tsel].cpu().numpy(), want[k]), (workload, k)
+    assert len(eng.handle.debug_tasks(1 << 17)) > 0
+
+
+def test_status_ring_keeps_every_calls_verdict(handle, torch_mod):
+    """3 x depth calls between two status checks, a frame without a valid pixel (numpy IndexError, tools.py:26) in the
+    FIRST call only: dtfill_status must still report it (one status slot per call)."""
+    torch = torch_mod
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    depth = 3
+    eng = DTFillEngine(0, pipeline_depth=depth)
+    good = torch.from_numpy(np.stack([synth.kitti_frame(i)[100:180, :320] for i in range(4)])).cuda()
+    badb = good.clone()
+    badb[2].zero_()
+    outs = [None] * depth
+    outs[0] = eng.fill(badb, out=outs[0])
+    for i in range(1, 3 * depth):
+        outs[i % depth] = eng.fill(good, out=outs[i % depth])
+    bad, _ = eng.status()
+    assert bad == 2
+    bad, _ = eng.status()                                # reported once
+    assert bad == -1
+    # more calls than the ring has slots: the verdict of a slot that is reused is folded, not dropped
+    outs[0] = eng.fill(badb, out=outs[0])
+    for i in range(1, 70):
+        outs[i % depth] = eng.fill(good, out=outs[i % depth])
+    bad, _ = eng.status()
+    assert bad == 2
+
+
+def test_sync_call_with_device_input_while_pipelined(handle, torch_mod):
+    """dtfill_run with a device input and HOST outputs on a handle whose pipeline depth is 3: the copies to
+    the host must follow the kernels."""
+    torch = torch_mod
+    frames = np.stack([synth.kitti_frame(i)[90:250, :640] for i in range(6)])
+    h = _lib.Handle(0)
+    h.set_pipeline_depth(3)
+    x = torch.from_numpy(frames).cuda()
+    B, H, W = frames.shape
+    depth = np.full((B, H, W), -1.0, np.float32)
+    dt = np.full((B, H, W), -1.0, np.float32)
+    bad = _lib.ctypes.c_int(-1)
+    rc = h._L.dtfill_run(h._h, _lib._ptr(x.data_ptr()), 1, B, H, W, 0.1, 0.1, _lib._ptr(depth), _lib._ptr(dt), None, None,
+                         None, 0, _lib.ctypes.byref(bad))
+    assert rc == 0
+    want = O.dt_fill(frames)
+    assert np.array_equal(depth, want["depth"]) and np.array_equal(dt, want["dt"])
+    h.close()
+
+
+def test_fused_eval_step_and_totals(handle, torch_mod):
+    """dtfill_run_eval_async + dtfill_eval_totals (one step of the sweep, eval.py:212-232) against per-frame
+    Result.evaluate of the oracle: strict and pipelined, float64 and float32 ground truth."""
+    torch = torch_mod
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    n = 10
+    frames = np.stack([synth.kitti_frame(i) for i in range(n)])
+    gt = np.stack([synth.kitti_gt(i) for i in range(n)])
+    fill = O.dt_fill(frames)["depth"]
+    per = [O.result_kitti(fill[i], gt[i]) for i in range(n)]
+    want = np.array([sum(m[k] for m in per) for k in ("mse", "rmse", "mae", "irmse", "imae")])
+    x, g = torch.from_numpy(frames).cuda(), torch.from_numpy(gt).cuda()
+    for depth in (1, 3):
+        eng = DTFillEngine(0, pipeline_depth=depth)
+        for lo in range(0, n, 2):                        # five calls of two frames
+            eng.fill_eval(x[lo:lo + 2], g[lo:lo + 2])
+        tot = eng.eval_totals().cpu().numpy()
+        assert eng.status()[0] == -1
+        np.testing.assert_allclose(tot[:5], want, rtol=1e-9)
+        assert tot[9] == n and tot[8] == sum(m["count"] for m in per)
+        assert np.all(eng.eval_totals().cpu().numpy() == 0)          # collected totals are cleared
+        run = torch.zeros(10, dtype=torch.float64, device="cuda")
+        eng.fill_eval(x[:4], g[:4]); eng.eval_totals(run)
+        eng.fill_eval(x[4:], g[4:]); eng.eval_totals(run)            # accumulate into the caller's vector
+        np.testing.assert_allclose(run.cpu().numpy()[:5], want, rtol=1e-9)
+    eng = DTFillEngine(0)
+    g32 = g.float()
+    eng.fill_eval(x, g32)
+    tot = eng.eval_totals().cpu().numpy()
+    per32 = [O.result_kitti(fill[i], gt[i].astype(np.float32)) for i in range(n)]
+    np.testing.assert_allclose(tot[1], sum(m["rmse"] for m in per32), rtol=2e-5)
+
+
+@pytest.mark.parametrize("nsrc", [(1 << 17) - 2, (1 << 17) - 1, 1 << 17, (1 << 17) + 1])
+def test_label_width_boundary(handle, nsrc):
+    """The packed key holds 17 label bits: frames with up to 2^17 - 1 sources take the fast kernels, from 2^17 on the
+    64-bit-key path.  Both sides of the boundary against the oracle."""
+    H, W = 352, 1216
+    rng = np.random.default_rng(nsrc)
+    x = np.zeros(H * W, np.float32)
+    pos = rng.choice(H * W, size=nsrc, replace=False)
+    x[pos] = rng.uniform(1.0, 60.0, nsrc).astype(np.float32)
+    x = x.reshape(1, H, W)
+    r = handle.run_host(x, 0.1, 0.1, want_dt=True, want_lbl=True, want_mask=True)
+    assert "index_error" not in r
+    o = O.dt_fill(x)
+    assert int(r["counts"][0, 0]) == nsrc
+    for k in ("depth", "dt", "lbl", "mask"):
+        assert np.array_equal(r[k], o[k]), k
+    assert int(o["lbl"].max()) == nsrc
+
+
+def test_dt_complete_batch_returns_fresh_arrays(handle):
+    """tools.py:27-33 returns a new array per call: results handed out earlier must not change when their pooled
+    page-locked buffers are reused, and dropping a result must make its buffer reusable."""
+    xa, xb = synth.kitti_batch([3]), synth.kitti_batch([4])
+    ra = tools.DT_complete_batch(xa)
+    keep = ra.copy()
+    rb = tools.DT_complete_batch(xb)
+    assert ra.ctypes.data != rb.ctypes.data
+    assert np.array_equal(ra, keep)
+    assert ra.flags.writeable and ra.dtype == np.float32 and ra.shape == (1, 352, 1216, 1)
+    addr = rb.ctypes.data
+    del rb
+    rc = tools.DT_complete_batch(xb)
+    assert rc.ctypes.data == addr                        # the buffer came back from the pool
+    assert np.array_equal(ra, keep)
+    assert np.array_equal(rc[..., 0], O.dt_fill(xb[..., 0])["depth"])
+    view = rc[0, 100:110]
+    del rc
+    rd = tools.DT_complete_batch(xa)                     # a live view keeps its buffer out of the pool
+    assert rd.ctypes.data != addr and view.base is not None
+
+
+def test_threads_share_the_device_handle(handle):
+    """Two Python threads calling the drop-ins at once go through the same cached handle: calls are
+    serialised per handle, results stay correct."""
+    xs = [synth.kitti_batch([10 + i]) for i in range(2)]
+    want = [O.dt_fill(x[..., 0])["depth"] for x in xs]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(4):
+                got = tools.DT_complete_batch(xs[i])
+                if not np.array_equal(got[..., 0], want[i]):
+                    errs.append(f"thread {i}: wrong result")
+        except Exception as e:          # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = 6
+    b, e = sharding.shard_range(n, rank, world)
+    frames = np.stack([synth.kitti_frame(i) for i in range(b, e)])
+    gt = np.stack([synth.kitti_gt(i) for i in range(b, e)])
+    eng = DTFillEngine(rank, pipeline_depth=2)
+    comm = sharding.MetricsComm(eng.handle, rank, world)
+    x, g = torch.from_numpy(frames).cuda(), torch.from_numpy(gt).cuda()
+    for lo in range(0, e - b):
+        eng.fill_eval(x[lo:lo + 1], g[lo:lo + 1])
+    tot = eng.eval_totals()
+    comm.allreduce(eng, tot)                             # dtfill_allreduce_sums on the engine's stream
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put(tot.cpu().numpy().copy())
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_allreduce_sums_two_ranks_equal_one_rank(handle, torch_mod):
+    """dtfill_allreduce_sums over 2 GPUs: the means of the sharded sweep equal the 1-rank means to 1e-12
+    (eval.py:212-232, 252-259)."""
+    torch = torch_mod
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    n = 6
+    eng = DTFillEngine(0)
+    x = torch.from_numpy(np.stack([synth.kitti_frame(i) for i in range(n)])).cuda()
+    g = torch.from_numpy(np.stack([synth.kitti_gt(i) for i in range(n)])).cuda()
+    for i in range(n):
+        eng.fill_eval(x[i:i + 1], g[i:i + 1])
+    one = eng.eval_totals().cpu().numpy()
+    np.testing.assert_allclose(got, one, rtol=1e-12)
+    m2, m1 = sharding.finalize_means(got), sharding.finalize_means(one)
+    assert m2["frames"] == n and abs(m2["rmse"] - m1["rmse"]) <= 1e-12 * m1["rmse"]
