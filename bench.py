@@ -293,7 +293,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def pin_to_gpu_numa(local_rank: int):
@@ -438,10 +438,10 @@ def run_ours(args, rank, world, local_rank):
     if sweep_only:
         sw = run_sweep(args, eng, dev, rank, world, dist, comm, barrier, args.min_seconds)
         if rank == 0:
-            print(json.dumps({"metric": "DT+NN-fill+metrics frames/s, 8192-frame sweep (BASELINE.json configs[4])",
+            emit({"metric": "DT+NN-fill+metrics frames/s, 8192-frame sweep (BASELINE.json configs[4])",
                               "value": sw["value"], "unit": UNIT, "n_gpus": world, "higher_is_better": True,
-                              "scaling": "strong", "data": "synthetic", "config": {"workload": sw["workload"]},
-                              "sweep": sw}))
+                  "scaling": "strong", "data": "synthetic", "config": {"workload": sw["workload"]},
+                  "sweep": sw})
         if comm is not None:
             comm.close()
         if dist is not None:
@@ -697,14 +697,32 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches_per_step * K * len(blocks), "gpu_launches_per_step": launches_per_step,
         "clocks": clocks, "clocks_strict": clocks_strict,
     }
-    print(json.dumps(line))
+    emit(line)
     if comm is not None:
         comm.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, alone on the real stdout (see main: everything else printed to fd 1 goes to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL prints its version banner at communicator creation) write to fd 1: keep the real stdout for the
+    # JSON line and send everything else to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

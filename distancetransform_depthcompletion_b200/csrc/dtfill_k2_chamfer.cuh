@@ -105,6 +105,23 @@ __device__ __forceinline__ void cp_async16_hint(uint32_t smem_addr, const void* 
 __device__ __forceinline__ void l2_discard_128(const void* p) {
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
+// One row of the forward state (128 * PPL contiguous bytes of scratch) -> shared memory as a single bulk-copy (TMA)
+// transaction; completion is signalled on an mbarrier that the whole warp waits on, phase by phase.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_row_to_smem(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -184,6 +201,9 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
 #ifndef DTFILL_L2POLICY
 #define DTFILL_L2POLICY 0       // 1: evict-last stores + evict-first read-back of the scratch; 2: and discard of consumed rows
 #endif
+#ifndef DTFILL_K2_TMA
+#define DTFILL_K2_TMA 1         // forward rows scratch -> shared memory: 1 = one cp.async.bulk (TMA) per row issued by an
+#endif                          // elected lane and signalled on an mbarrier; 0 = 16-byte cp.async per lane (LDGSTS)
 #ifndef DTFILL_FLUSH_LATE
 #define DTFILL_FLUSH_LATE 0     // where a step stores the depths gathered by the previous one: 0 at its start, 1 after the
 #endif                          // stencil, 2 after the scan (the gather's latency is then covered by the whole step)
@@ -270,6 +290,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     // 228 KB is the L1 that serves the depth_list gather.
     __shared__ __align__(16) uint32_t stage[32 * PPL];
     __shared__ __align__(16) uint2 fwdbuf[16 * PPL];      // forward keys of the next row to scan, [j][lane]
+#if DTFILL_K2_TMA
+    __shared__ __align__(8) uint64_t fwdbar;              // completion of the bulk copy into fwdbuf
+#endif
 
     const Task task = ws.tasks[blockIdx.x];      // slot-major: blockIdx = slot * B + frame, longest tasks first
     if (task.kind != my_kind && !(task.kind == TASK_NOSRC && my_kind == TASK_CHAMFER)) return;
@@ -416,8 +439,32 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
     const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(fwdbuf) + lane * (4 * VW);
 
+#if DTFILL_K2_TMA
+    constexpr bool TMA_ROWS = (VW == 4) && DTFILL_FAKE_SCRATCH_DIV == 1;
+#else
+    constexpr bool TMA_ROWS = false;
+#endif
+#if DTFILL_K2_TMA
+    const uint32_t fwdbar_a = (uint32_t)__cvta_generic_to_shared(&fwdbar);
+    const uint32_t fwdbuf_a = (uint32_t)__cvta_generic_to_shared(fwdbuf);
+    if (TMA_ROWS) {
+        if (lane == 0) mbar_init(fwdbar_a, 1);
+        __syncwarp();
+    }
+    uint32_t fwd_phase = 0;           // parity of the transaction being waited for
+    bool fwd_inflight = false;        // the last issue_fwd_row started a transaction (warp-uniform)
+#endif
     auto issue_fwd_row = [&](int y) {            // group A(y)
-        if (y >= task.fstart && y >= task.lo) {
+        const bool have = y >= task.fstart && y >= task.lo;
+#if DTFILL_K2_TMA
+        if (TMA_ROWS) {
+            fwd_inflight = have;
+            if (have && lane == 0)
+                bulk_row_to_smem(fwdbuf_a, reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL), 128 * PPL, fwdbar_a);
+            return;
+        }
+#endif
+        if (have) {
             const char* src = reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * (4 * VW);
 #pragma unroll
             for (int j = 0; j < PPL / VW / DTFILL_FAKE_SCRATCH_DIV; ++j) {
@@ -430,6 +477,15 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
             }
         }
         cp_async_commit();
+    };
+    auto wait_fwd_row = [&]() {
+#if DTFILL_K2_TMA
+        if (TMA_ROWS) {
+            if (fwd_inflight) { mbar_wait(fwdbar_a, fwd_phase); fwd_phase ^= 1u; }
+            return;
+        }
+#endif
+        cp_async_wait<0>();
     };
     // Depths gathered for an output row stay in registers across the loop back-edge and are stored at the start of
     // the next step: the gather's latency is covered by the row rotation, and nothing else is live meanwhile.
@@ -450,7 +506,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
 #if DTFILL_FLUSH_LATE == 0
         if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
 #endif
-        cp_async_wait<0>();                          // A(y), the only group in flight, has landed
+        wait_fwd_row();                              // A(y), the only transfer in flight, has landed
 #if DTFILL_L2POLICY >= 2
         if (VW == 4 && lane < PPL && y >= task.fstart && y >= task.lo)     // row y of the scratch is dead: one 128 B line per lane
             l2_discard_128(reinterpret_cast<const char*>(scr) + (long)(y - task.lo) * (128 * PPL) + lane * 128);
@@ -475,6 +531,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         }
 #pragma unroll
         for (int i = 0; i < PPL; ++i) c[i] = stencil_bwd<PPL>(c[i], A, Bq, i, fp.one) & ORDCLR;
+#if DTFILL_K2_TMA
+        if (TMA_ROWS) __syncwarp();                  // every lane has read fwdbuf before the next bulk copy overwrites it
+#endif
         issue_fwd_row(y - 1);                        // A(y-1): fwdbuf has been consumed above
 #if DTFILL_FLUSH_LATE == 1
         if (VEC && y + 1 >= task.r0 && y + 1 < task.r1) flush_depth_row(y + 1);     // gathered during the last step
@@ -578,7 +637,7 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         bwd_step(ra, rb, y);
         const Row<PPL> t = ra; ra = rb; rb = t;
     }
-    cp_async_wait<0>();
+    wait_fwd_row();
     if (VEC) flush_depth_row(task.r0);
 }
 
