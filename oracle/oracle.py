@@ -1,7 +1,7 @@
 """CPU oracle for the DT + nearest-neighbour fill path -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
-import this module.  The product package never imports it (tests/test_no_oracle_in_product.py checks).
+import this module.  The product package never imports it (tests/test_host_logic.py::test_product_never_imports_the_oracle checks).
 
 Three layers, each a restatement of reference lines (file:line relative to /root/reference):
 
