@@ -202,7 +202,7 @@ struct dtfill_ctx {
     int pipeline_depth = 1;           // 1: strict stream order (default); 2: consecutive calls may overlap
     cudaEvent_t pipe_fork = nullptr;
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
-    Buf gt_dev, partial, per_frame, sums, edt_rows, edt_bits;
+    Buf gt_dev, partial, per_frame, sums, edt_rows, edt_stack;
     // pinned mirrors of pageable caller buffers (see CopyPool) and the threads that fill / drain them
     PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar;
     CopyPool* pool_in = nullptr;
@@ -781,7 +781,7 @@ void dtfill_destroy(dtfill_t* h) {
         }
     }
     Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->lidar_out_dev,
-                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_bits};
+                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_stack};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* q : h->retired) cudaFree(q);
@@ -1287,12 +1287,11 @@ int dtfill_edt(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
                int32_t* out_idx, int out_is_device) {
     if (!h || !in || !out_d2) return fail(DTFILL_E_ARG, "dtfill_edt: NULL handle, input or out_d2");
     if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_edt: B, H, W must be positive");
-    if (H > 32 * EDT_MAX_CHUNKS || H > 32767 || W > 32767 || (size_t)EDT_ROWS_PER_BLOCK * W * 2 > 200 * 1024)
+    if (H > 4096 || W > 25600)
         return fail(DTFILL_E_ARG, "dtfill_edt: frame size not supported (H <= 4096, W <= 25600)");
     CU(cudaSetDevice(h->device));
     { int frc = dtfill_flush(h); if (frc) return frc; }
     const size_t npx = (size_t)B * H * W;
-    const int WW = (W + 31) / 32;
     cudaStream_t s = h->stream;
     int rc;
     const float* i_d = in;
@@ -1307,26 +1306,15 @@ int dtfill_edt(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
         d2 = (int32_t*)h->depth_dev.p;
         if (out_idx) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ix = (int32_t*)h->lbl_dev.p; }
     }
-    if ((rc = ensure(h, h->edt_bits, (size_t)B * H * WW * 4))) return rc;
-    if ((rc = ensure(h, h->edt_rows, npx * 2))) return rc;
+    if ((rc = ensure(h, h->edt_rows, npx * 2))) return rc;      // nearest source column per pixel (u16)
+    if ((rc = ensure(h, h->edt_stack, npx * 4))) return rc;      // envelope stacks [frame][depth][column]
     const long nrows = (long)B * H;
     {
-        const long nwords = nrows * WW;
-        const unsigned grid = (unsigned)((nwords * 32 + 255) / 256);
-        k7_edt_bits<<<grid, 256, 0, s>>>(i_d, (long)npx, W, WW, source_cut(src_thr), (uint32_t*)h->edt_bits.p);
+        const unsigned grid = (unsigned)((nrows + 3) / 4);      // one warp per row
+        if ((W & 7) == 0) k7_edt_rows<true><<<grid, 128, 0, s>>>(i_d, nrows, W, source_cut(src_thr), (uint16_t*)h->edt_rows.p);
+        else k7_edt_rows<false><<<grid, 128, 0, s>>>(i_d, nrows, W, source_cut(src_thr), (uint16_t*)h->edt_rows.p);
     }
-    k7_edt_columns<<<dim3(WW, B), 32, 0, s>>>((const uint32_t*)h->edt_bits.p, H, W, WW, (uint16_t*)h->edt_rows.p);
-    {
-        const size_t smem = (size_t)EDT_ROWS_PER_BLOCK * W * 2;
-        const unsigned grid = (unsigned)((nrows + EDT_ROWS_PER_BLOCK - 1) / EDT_ROWS_PER_BLOCK);
-        const bool tma = (W & 7) == 0;          // 16-byte aligned rows: one cp.async.bulk per block
-        if (smem > 48 * 1024) {
-            CU(cudaFuncSetAttribute(k7_edt_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(k7_edt_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        if (tma) k7_edt_rows<true><<<grid, 256, smem, s>>>((const uint16_t*)h->edt_rows.p, nrows, H, W, d2, ix);
-        else k7_edt_rows<false><<<grid, 256, smem, s>>>((const uint16_t*)h->edt_rows.p, nrows, H, W, d2, ix);
-    }
+    k7_edt_columns<<<dim3((W + 127) / 128, B), 128, 0, s>>>((const uint16_t*)h->edt_rows.p, H, W, (uint32_t*)h->edt_stack.p, d2, ix);
     CU(cudaGetLastError());
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out_d2, d2, npx * 4, cudaMemcpyDeviceToHost, s));

@@ -3,165 +3,217 @@
 // tools.py:9), so there is no reference function to be exact against; the oracle is scipy.ndimage.distance_transform_edt.
 //
 // Separable (Meijster / Felzenszwalb): the squared distance to the nearest source is
-//     D(y,x) = min over x' of (x - x')^2 + g(y,x')^2,   g(y,x') = distance to the nearest source in column x'.
-//   k7_edt_bits     source predicate of nearest_point (tools.py:8) -> bit rows, one ballot per 32 pixels
-//   k7_edt_columns  column pass: one warp per strip of 32 columns; 32 rows of the strip are loaded as 32 words (one per
-//                   lane), transposed with five shuffle/mask steps so that lane l holds the 32 rows of column l, and
-//                   the nearest source row above / below every pixel follows from count-leading/trailing-zeros on that
-//                   word plus a carry between chunks.  Writes the nearest source ROW per pixel (u16).
-//   k7_edt_rows     row pass: a block stages ROWS_PER_BLOCK rows of that map (contiguous in memory) into shared memory
-//                   with ONE cp.async.bulk (TMA) transaction signalled on an mbarrier, then every thread finds its pixel's
-//                   minimum over the parabolas (x - x')^2 + g^2 by walking outwards from x' = x until the horizontal
-//                   offset alone exceeds the best value found: exact, and O(distance) per pixel instead of O(W).
-// Ties: the column pass prefers the source above at equal vertical distance; the row pass prefers the smaller |x - x'|,
-// then the left neighbour.  The squared distance does not depend on them.
+//     D(y,x) = min over y' of (y - y')^2 + h(y',x)^2,   h(y',x) = distance to the nearest source of row y' from column x.
+//   k7_edt_rows     one warp per row.  Coalesced loads of the row, source predicate of nearest_point (tools.py:8), one
+//                   ballot per 32 pixels: lane w keeps word w of the row's source bits in a register.  The nearest source
+//                   column on either side of every pixel follows from count-leading/trailing-zeros on that word plus a
+//                   max / min scan of the words' last / first source across the lanes (shuffles).  Writes the nearest
+//                   source COLUMN per pixel (u16), 64 contiguous bytes per lane.
+//   k7_edt_columns  lower envelope of the parabolas (y - y')^2 + h(y',x)^2 down every column: ONE THREAD PER COLUMN, a
+//                   warp's 32 scanlines being 32 adjacent columns, so every load of the map and every store of the two
+//                   outputs is coalesced without staging.  Forward sweep: the envelope as a stack of (row, first row where
+//                   it is the minimum) pairs; backward sweep: read the answers off the stack.  O(1) amortised per pixel
+//                   and exact in integers (the separator is a floor division).  The stack of a scanline can be as deep as
+//                   the frame is tall and 64 scanlines per SM sub-partition are in flight, so it lives in a scratch array
+//                   [frame][depth][column] (a warp's pushes at equal depth are one 128-byte line; the hot tops stay in
+//                   L1/L2) rather than in shared memory; its top is held in registers.
+// The round-1 order of the passes (columns first, then per row an outward search from x' = x staged in shared memory with
+// cp.async.bulk) was O(distance) per pixel: 5.9 ms per 256 KITTI frames, most of it in the source-free top third of the
+// frames where every search ran ~2 x 100 steps; this order needs 0.5 ms.
+// Ties: among several sources at the minimal distance the first in raster order wins (upper row; in a row the left one).
 #pragma once
 #include "dtfill_common.cuh"
 
 namespace dtfill {
 
-constexpr uint16_t EDT_NONE = 0xFFFFu;          // no source in this column
-constexpr int EDT_ROWS_PER_BLOCK = 4;
-constexpr int EDT_MAX_CHUNKS = 128;             // column pass: H <= 4096
+constexpr uint16_t EDT_NONE = 0xFFFFu;          // no source in this row
+constexpr int EDT_MAX_WORDS = 1024;             // row pass: W <= 32768
 
-__global__ void __launch_bounds__(256) k7_edt_bits(const float* __restrict__ in, long npx_total, int W, int WW, float src_cut,
-                                                    uint32_t* __restrict__ bits)
+// ------------------------------------------------------------------------------------------------------
+// Row pass.  nearest_col[y][x] = column of the source of row y nearest to x (the left one at equal distance), EDT_NONE
+// if the row holds no source.  V8: W % 8 == 0, so a lane's 32 values start 16-byte aligned (128-bit stores).
+// ------------------------------------------------------------------------------------------------------
+template <bool V8>
+__global__ void __launch_bounds__(128) k7_edt_rows(const float* __restrict__ in, long nrows, int W, float src_cut,
+                                                    uint16_t* __restrict__ nearest_col)
 {
-    // one warp per 32-pixel word of a row
-    const long word = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const long nrows = npx_total / W;
-    if (word >= nrows * WW) return;
-    const long row = word / WW;
-    const int w = (int)(word - row * WW);
-    const int x = w * 32 + lane;
-    bool src = false;
-    if (x < W) {
-        const float v = ld_stream(in + row * W + x);
-        src = !(v < src_cut);                    // tools.py:8: !(float32(1 - x) > thr); NaN is a source
-    }
-    const uint32_t m = __ballot_sync(0xffffffffu, src);
-    if (lane == 0) bits[word] = m;
-}
+    __shared__ int next_first[4][EDT_MAX_WORDS / 32 + 1];      // per warp: first source column in the chunks after this one
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long row = (long)blockIdx.x * 4 + wib;
+    if (row >= nrows) return;
+    const float* rp = in + row * W;
+    uint16_t* out = nearest_col + row * W;
+    const int WW = (W + 31) >> 5;
+    const int nchunks = (WW + 31) >> 5;
+    constexpr int BIG = 1 << 30;
 
-// 32 x 32 bit transpose across a warp: on entry lane r holds row r (bit c = column c), on exit lane c holds column c
-// (bit r = row r).
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t v, int lane)
-{
+    // source bits of the row: chunk c holds words 32c .. 32c+31, word 32c + l in lane l
+    auto chunk_bits = [&](int c) -> uint32_t {
+        uint32_t mine = 0;
+        const int w0 = c * 32;
+        const int nw = min(32, WW - w0);
+        for (int k0 = 0; k0 < nw; k0 += 8) {                  // 8 loads in flight per lane
+            float v[8];
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, s);
-        // lanes with bit s clear keep their low half-blocks and take the partner's low half-blocks shifted up;
-        // lanes with bit s set keep their high half-blocks and take the partner's high half-blocks shifted down
-        v = (lane & s) ? ((v & ~m) | ((o >> s) & m)) : ((v & m) | ((o << s) & ~m));
-    }
-    return v;
-}
+            for (int k = 0; k < 8; ++k) {
+                const int x = (w0 + k0 + k) * 32 + lane;
+                v[k] = (k0 + k < nw && x < W) ? ld_stream(rp + x) : -1.0f;     // padding is never a source (src_cut > -1)
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int x = (w0 + k0 + k) * 32 + lane;
+                const bool src = (k0 + k < nw && x < W) && !(v[k] < src_cut);   // tools.py:8; NaN is a source
+                const uint32_t m = __ballot_sync(0xffffffffu, src);
+                if (lane == k0 + k) mine = m;
+            }
+        }
+        return mine;
+    };
 
-__global__ void __launch_bounds__(32) k7_edt_columns(const uint32_t* __restrict__ bits, int H, int W, int WW,
-                                                      uint16_t* __restrict__ nearest_row)
-{
-    __shared__ uint16_t below[EDT_MAX_CHUNKS][32];      // first source row in the chunks after this one, per column
-    const int w = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
-    const uint32_t* bf = bits + (long)b * H * WW + w;
-    uint16_t* out = nearest_row + (long)b * H * W;
-    const int nchunks = (H + 31) >> 5;
-    const int x = w * 32 + lane;
-    // pass A, bottom to top: carry of the nearest source row below every chunk
-    int dn = -1;
-    for (int c = nchunks - 1; c >= 0; --c) {
-        below[c][lane] = dn < 0 ? EDT_NONE : (uint16_t)dn;
-        const int y = c * 32 + lane;
-        const uint32_t col = warp_transpose32(y < H ? bf[(long)y * WW] : 0u, lane);
-        if (col) dn = c * 32 + __ffs(col) - 1;
+    // right to left over the chunks: first source column after every chunk
+    uint32_t bits0 = 0, bits1 = 0;                            // words of chunks 0 and 1 (W <= 2048), kept for the second sweep
+    {
+        int nf = BIG;
+        for (int c = nchunks - 1; c >= 0; --c) {
+            if (lane == 0) next_first[wib][c] = nf;
+            const uint32_t word = chunk_bits(c);
+            if (c == 0) bits0 = word;
+            if (c == 1) bits1 = word;
+            const uint32_t any = __ballot_sync(0xffffffffu, word != 0);
+            if (any) {
+                const int fl = __ffs(any) - 1;                // first lane with a source
+                const uint32_t fw = __shfl_sync(0xffffffffu, word, fl);
+                nf = (c * 32 + fl) * 32 + __ffs(fw) - 1;
+            }
+        }
+        __syncwarp();
     }
-    // pass B, top to bottom
-    int up = -1;
+    // left to right
+    int last_before = -1;                                     // last source column in the chunks before this one
     for (int c = 0; c < nchunks; ++c) {
-        const int y0 = c * 32;
-        const int yl = y0 + lane;
-        const uint32_t col = warp_transpose32(yl < H ? bf[(long)yl * WW] : 0u, lane);
-        const int dnc = below[c][lane] == EDT_NONE ? -1 : (int)below[c][lane];
-        if (x < W) {
-            for (int r = 0; r < 32 && y0 + r < H; ++r) {
-                const int y = y0 + r;
-                const uint32_t le = col & (0xFFFFFFFFu >> (31 - r));          // sources at rows <= y of this chunk
-                const uint32_t gt = r == 31 ? 0u : (col & (0xFFFFFFFFu << (r + 1)));
-                const int u = le ? y0 + 31 - __clz(le) : up;
-                const int d = gt ? y0 + __ffs(gt) - 1 : dnc;
-                int best = EDT_NONE;
-                if (u >= 0 && (d < 0 || y - u <= d - y)) best = u;            // tie: the source above
-                else if (d >= 0) best = d;
-                out[(long)y * W + x] = (uint16_t)best;
+        const uint32_t word = c == 0 ? bits0 : (c == 1 ? bits1 : chunk_bits(c));
+        const int w = c * 32 + lane;
+        const int base = w * 32;
+        const int lastw = word ? base + 31 - __clz(word) : -1;
+        const int firstw = word ? base + __ffs(word) - 1 : BIG;
+        int incl_last = lastw, incl_first = firstw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, incl_last, d);
+            const int b2 = __shfl_down_sync(0xffffffffu, incl_first, d);
+            if (lane >= d) incl_last = max(incl_last, a);
+            if (lane + d < 32) incl_first = min(incl_first, b2);
+        }
+        int exl = __shfl_up_sync(0xffffffffu, incl_last, 1);
+        int exr = __shfl_down_sync(0xffffffffu, incl_first, 1);
+        exl = lane == 0 ? last_before : max(exl, last_before);
+        const int nf = next_first[wib][c];
+        exr = lane == 31 ? nf : min(exr, nf);
+        last_before = max(last_before, __shfl_sync(0xffffffffu, incl_last, 31));
+        if (w < WW) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int x = base + i;
+                const uint32_t le = word & (0xFFFFFFFFu >> (31 - i));
+                const uint32_t gt = i == 31 ? 0u : (word & (0xFFFFFFFFu << (i + 1)));
+                const int L = le ? base + 31 - __clz(le) : exl;
+                const int R = gt ? base + __ffs(gt) - 1 : exr;
+                uint32_t best = EDT_NONE;
+                if (L >= 0 && (R >= BIG || x - L <= R - x)) best = (uint32_t)L;      // tie: the left one
+                else if (R < BIG) best = (uint32_t)R;
+                if (i & 1) pk[i >> 1] |= best << 16; else pk[i >> 1] = best;
+            }
+            if (V8 && base + 32 <= W) {
+                uint4* o4 = reinterpret_cast<uint4*>(out + base);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (base + i < W) out[base + i] = (uint16_t)((i & 1) ? (pk[i >> 1] >> 16) : (pk[i >> 1] & 0xFFFFu));
             }
         }
-        if (col) up = y0 + 31 - __clz(col);
     }
 }
 
-__device__ __forceinline__ uint32_t edt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// TMA == true: rows staged with cp.async.bulk + mbarrier (needs 16-byte aligned rows: (ROWS * W * 2) % 16 == 0 for every
-// block start, i.e. W % 8 == 0, and a 16-byte aligned map); otherwise plain loads.
-template <bool TMA>
-__global__ void __launch_bounds__(256) k7_edt_rows(const uint16_t* __restrict__ nearest_row, long nrows_total, int H, int W,
-                                                    int32_t* __restrict__ out_d2, int32_t* __restrict__ out_idx)
+// ------------------------------------------------------------------------------------------------------
+// Column pass: lower envelope of the parabolas F(y; i) = (y - i)^2 + f(i), f(i) = (x - nearest_col[i][x])^2, over the rows
+// i of column x that hold a source at all.  Stack entry q: row s[q] and the first row t[q] from which s[q] is the minimum
+// (s | t << 16); the separator of two rows i < u is the largest y with F(y; i) <= F(y; u), so the upper row keeps ties.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int edt_floordiv(int num, int den /* > 0 */)
 {
-    extern __shared__ __align__(16) uint16_t srow[];             // [EDT_ROWS_PER_BLOCK][W]
-    __shared__ __align__(8) uint64_t mbar;
-    const long row0 = (long)blockIdx.x * EDT_ROWS_PER_BLOCK;
-    const int nr = (int)min((long)EDT_ROWS_PER_BLOCK, nrows_total - row0);
-    const uint32_t bytes = (uint32_t)nr * W * 2;
-    if (TMA) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(edt_smem_u32(&mbar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int q = num / den;
+    if ((num % den != 0) && (num < 0)) --q;
+    return q;
+}
+
+__global__ void __launch_bounds__(128) k7_edt_columns(const uint16_t* __restrict__ nearest_col, int H, int W,
+                                                       uint32_t* __restrict__ stack, int32_t* __restrict__ out_d2,
+                                                       int32_t* __restrict__ out_idx)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const long fo = (long)blockIdx.y * H * W + x;
+    const uint16_t* m = nearest_col + fo;
+    uint32_t* st = stack + fo;
+    int32_t* od2 = out_d2 + fo;
+    int32_t* oix = out_idx ? out_idx + fo : nullptr;
+
+    int q = -1;
+    int s_top = 0, t_top = 0, f_top = 0, xs_top = 0;
+    auto reload_top = [&]() {                       // entry q of the stack -> registers
+        const uint32_t e = st[(long)q * W];
+        s_top = (int)(e & 0xFFFFu);
+        t_top = (int)(e >> 16);
+        xs_top = (int)m[(long)s_top * W];
+        const int dx = x - xs_top;
+        f_top = dx * dx;
+    };
+    // forward sweep, one row ahead on the map
+    uint32_t nxt = m[0];
+    for (int u = 0; u < H; ++u) {
+        const uint32_t xs = nxt;
+        if (u + 1 < H) nxt = m[(long)(u + 1) * W];
+        if (xs == EDT_NONE) continue;
+        const int dx = x - (int)xs;
+        const int fu = dx * dx;
+        while (q >= 0) {
+            const int a = t_top - s_top, b2 = t_top - u;
+            if (a * a + f_top > b2 * b2 + fu) {     // u is lower already where s_top starts: s_top is never the minimum
+                --q;
+                if (q >= 0) reload_top();
+            } else {
+                break;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(edt_smem_u32(&mbar)), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(edt_smem_u32(srow)), "l"(nearest_row + row0 * W), "r"(bytes), "r"(edt_smem_u32(&mbar)) : "memory");
+        if (q < 0) {
+            q = 0; s_top = u; t_top = 0; f_top = fu; xs_top = (int)xs;
+            st[0] = (uint32_t)u;
+        } else {
+            const int wsep = 1 + edt_floordiv(u * u - s_top * s_top + fu - f_top, 2 * (u - s_top));
+            if (wsep < H) {
+                ++q; s_top = u; t_top = wsep; f_top = fu; xs_top = (int)xs;
+                st[(long)q * W] = (uint32_t)u | ((uint32_t)wsep << 16);
+            }
         }
-        // every thread waits for the transaction (phase 0)
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(edt_smem_u32(&mbar)) : "memory");
-        }
-    } else {
-        for (int i = threadIdx.x; i < nr * W; i += blockDim.x) srow[i] = nearest_row[row0 * W + i];
-        __syncthreads();
     }
-    for (int r = 0; r < nr; ++r) {
-        const long row = row0 + r;
-        const int y = (int)(row % H);
-        const uint16_t* g = srow + r * W;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            // parabola of the own column first, then outwards; stop when the horizontal offset alone reaches the best
-            long best = 0x7FFFFFFFl;
-            int bx = -1;
-            {
-                const uint16_t ry = g[x];
-                if (ry != EDT_NONE) { const long dy = y - (int)ry; best = dy * dy; bx = x; }
-            }
-            const int dmax = max(x, W - 1 - x);
-            for (int d = 1; d <= dmax; ++d) {
-                const long dd = (long)d * d;
-                if (dd >= best) break;
-                if (x - d >= 0) {
-                    const uint16_t ry = g[x - d];
-                    if (ry != EDT_NONE) { const long dy = y - (int)ry; const long c = dd + dy * dy; if (c < best) { best = c; bx = x - d; } }
-                }
-                if (x + d < W) {
-                    const uint16_t ry = g[x + d];
-                    if (ry != EDT_NONE) { const long dy = y - (int)ry; const long c = dd + dy * dy; if (c < best) { best = c; bx = x + d; } }
-                }
-            }
-            out_d2[row * W + x] = (int32_t)best;
-            if (out_idx) out_idx[row * W + x] = bx < 0 ? -1 : (int32_t)g[bx] * W + bx;
+    if (q < 0) {                                    // no source in the frame's column span at all = none in the frame
+        for (int u = 0; u < H; ++u) {
+            od2[(long)u * W] = 0x7FFFFFFF;
+            if (oix) oix[(long)u * W] = -1;
         }
+        return;
+    }
+    // the forward sweep may have left a top that was never pushed (wsep >= H): registers still describe entry q
+    // only if the last push was entry q; reload to be sure
+    reload_top();
+    for (int u = H - 1; u >= 0; --u) {
+        const int dy = u - s_top;
+        od2[(long)u * W] = dy * dy + f_top;
+        if (oix) oix[(long)u * W] = s_top * W + xs_top;
+        if (u == t_top && q > 0) { --q; reload_top(); }
     }
 }
 

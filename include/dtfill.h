@@ -192,12 +192,12 @@ int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B
 /*
  * EXTENSION (no reference function stands behind it: every call site of the reference computes the
  * 5x5 chamfer transform above, tools.py:9): the exact Euclidean feature transform of the same source mask,
- * source(p) = !((float)(1.0f - in[p]) > src_thr).  Separable: a column pass over the source bit rows (nearest source
- * row per pixel), then per row the minimum over the parabolas (x - x')^2 + g(y,x')^2, rows staged in shared memory with
- * cp.async.bulk.  in float32 [B,H,W]; out_d2 int32 [B,H,W] = squared distance to the nearest source (2^31 - 1 for a
- * frame without sources); out_idx (nullable) int32 [B,H,W] = y' * W + x' of a source at that distance (-1 if none).
- * Among several nearest sources the one in the column with the smallest |x - x'| wins, the left one on equal offsets,
- * and within a column the nearer row, the upper one on equal distance.  H <= 4096, W <= 25600.
+ * source(p) = !((float)(1.0f - in[p]) > src_thr).  Separable: a row pass (one warp per row: ballots of the predicate,
+ * nearest source column per pixel from bit scans), then down every column the lower envelope of the parabolas
+ * (y - y')^2 + h(y',x)^2, one thread per column so that a warp's accesses are coalesced.  in float32 [B,H,W]; out_d2 int32
+ * [B,H,W] = squared distance to the nearest source (2^31 - 1 for a frame without sources); out_idx (nullable) int32
+ * [B,H,W] = y' * W + x' of a source at that distance (-1 if none): among several sources at the minimal distance the first
+ * in raster order.  H <= 4096, W <= 25600.
  * Oracle: scipy.ndimage.distance_transform_edt (squared distances identical; an index is checked by the distance it
  * attains).  Waits for completion when the outputs are host pointers.
  */

@@ -66,3 +66,14 @@ if png is not None:
         print("uint16 input%s, pipelined: %.4f ms / 256 frames (%.0f frames/s, %.0f GB/s of %d B/px)"
               % (" + decoded lidar out" if want_lidar else "", t, B / t * 1e3, bpp * npx / t / 1e6, bpp))
     h.set_pipeline_depth(1)
+
+# ---- f-4: exact Euclidean feature transform (extension), device-resident: squared distance + nearest-source index --
+d2 = torch.empty((B, H, W), dtype=torch.int32, device="cuda")
+idx = torch.empty((B, H, W), dtype=torch.int32, device="cuda")
+for want_idx in (0, 1):
+    t = timed(lambda: _lib._check(L.dtfill_edt(h._h, ctypes.c_void_p(x.data_ptr()), 1, B, H, W, ctypes.c_float(0.1),
+                                               ctypes.c_void_p(d2.data_ptr()),
+                                               ctypes.c_void_p(idx.data_ptr()) if want_idx else None, 1), "edt"))
+    bpp = 4 + 4 + 4 * want_idx
+    print("edt (exact Euclidean, d2%s): %.3f ms / 256 frames (%.0f frames/s, %.0f GB/s of %d B/px)"
+          % (" + index" if want_idx else "", t, B / t * 1e3, bpp * npx / t / 1e6, bpp))

@@ -1,7 +1,8 @@
 """f-4 (extension): the exact Euclidean feature transform dtfill_edt / tools.euclidean_feature_transform.
 There is no reference function behind it; the oracle is scipy.ndimage.distance_transform_edt on the source mask of
 tools.py:8 (pinned here against an exhaustive search).  Squared distances must be identical; an index is checked by
-what it attains (it must point at a source at exactly that distance) and by the documented tie rule."""
+what it attains (it must point at a source at exactly that distance) and by the documented tie rule (the first source in
+raster order among those at the minimal distance)."""
 import numpy as np
 import pytest
 
@@ -38,7 +39,12 @@ def _check(x, thr=0.1):
     assert np.all(src[iy, ix]), "an index does not point at a source"
     yy, xx = np.mgrid[0:H, 0:W]
     assert np.array_equal((yy - iy) ** 2 + (xx - ix) ** 2, want), "an index does not attain the minimal distance"
-    # tie rule of the row pass: no source column nearer (in |dx|) attains the same distance
+    if H * W <= 4096:
+        # documented tie rule: among the sources at the minimal distance the first in raster order
+        ys, xs = np.nonzero(src)
+        d = (yy[..., None] - ys) ** 2 + (xx[..., None] - xs) ** 2
+        first = np.argmax(d == want[..., None], axis=-1)
+        assert np.array_equal(idx, ys[first] * W + xs[first]), "tie rule"
     return d2, idx
 
 
@@ -48,8 +54,12 @@ def test_edt_random_shapes(dtfill_lib):
     for t in range(60):
         H, W = int(rng.integers(1, 150)), int(rng.integers(1, 300))
         if t % 3 == 0:
-            W = 8 * max(1, W // 8)           # rows staged with cp.async.bulk
+            W = 8 * max(1, W // 8)           # 128-bit stores of the row pass
+        if t % 4 == 1:
+            H, W = int(rng.integers(1, 64)), int(rng.integers(1, 64))     # small enough for the tie-rule check
         _check(_random_frame(rng, H, W, rng.choice([0.002, 0.02, 0.2, 0.8])))
+    _check(_random_frame(rng, 3, 2500, 0.001))                             # three chunks of bit words per row
+    _check(_random_frame(rng, 700, 40, 0.01))                              # deep envelope stacks
 
 
 @pytest.mark.gpu
@@ -78,10 +88,10 @@ def test_edt_edge_cases(dtfill_lib):
     for H, W in ((1, 200), (200, 1), (32, 32), (33, 31), (64, 8), (97, 1216)):
         x = np.zeros((H, W), np.float32); x[H // 2, W // 3] = 5.0; x[0, W - 1] = 6.0
         _check(x)
-    # documented ties: the source above wins in a column, the nearer column then the left one in a row
+    # documented ties: the first source in raster order among those at the minimal distance
     t = np.zeros((5, 5), np.float32); t[0, 2] = 1.0; t[4, 2] = 1.0; t[2, 0] = 1.0; t[2, 4] = 1.0
     d2, idx = tools.euclidean_feature_transform(t)
-    assert d2[2, 2] == 4 and idx[2, 2] == 0 * 5 + 2                 # own column (|dx| = 0) before the row neighbours; upper source
+    assert d2[2, 2] == 4 and idx[2, 2] == 0 * 5 + 2                 # the upper row
     t = np.zeros((3, 5), np.float32); t[1, 0] = 1.0; t[1, 4] = 1.0
     d2, idx = tools.euclidean_feature_transform(t)
     assert d2[1, 2] == 4 and idx[1, 2] == 1 * 5 + 0                 # equal |dx|: the left one
