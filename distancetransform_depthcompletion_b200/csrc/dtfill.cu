@@ -1307,14 +1307,16 @@ int dtfill_edt(dtfill_t* h, const float* in, int in_is_device, int B, int H, int
         if (out_idx) { if ((rc = ensure(h, h->lbl_dev, npx * 4))) return rc; ix = (int32_t*)h->lbl_dev.p; }
     }
     if ((rc = ensure(h, h->edt_rows, npx * 2))) return rc;      // nearest source column per pixel (u16)
-    if ((rc = ensure(h, h->edt_stack, npx * 4))) return rc;      // envelope stacks [frame][depth][column]
+    if ((rc = ensure(h, h->edt_stack, npx * 8))) return rc;      // envelope stacks [frame][depth][column], 8 bytes per entry
     const long nrows = (long)B * H;
     {
         const unsigned grid = (unsigned)((nrows + 3) / 4);      // one warp per row
         if ((W & 7) == 0) k7_edt_rows<true><<<grid, 128, 0, s>>>(i_d, nrows, W, source_cut(src_thr), (uint16_t*)h->edt_rows.p);
         else k7_edt_rows<false><<<grid, 128, 0, s>>>(i_d, nrows, W, source_cut(src_thr), (uint16_t*)h->edt_rows.p);
     }
-    k7_edt_columns<<<dim3((W + 127) / 128, B), 128, 0, s>>>((const uint16_t*)h->edt_rows.p, H, W, (uint32_t*)h->edt_stack.p, d2, ix);
+    // two scanlines per thread (the same column of frames b and b + B/2): see the kernel
+    if (B >= 2) k7_edt_columns<2><<<dim3((W + 127) / 128, (B + 1) / 2), 128, 0, s>>>((const uint16_t*)h->edt_rows.p, B, H, W, (uint2*)h->edt_stack.p, d2, ix);
+    else k7_edt_columns<1><<<dim3((W + 127) / 128, B), 128, 0, s>>>((const uint16_t*)h->edt_rows.p, B, H, W, (uint2*)h->edt_stack.p, d2, ix);
     CU(cudaGetLastError());
     if (!out_is_device) {
         CU(cudaMemcpyAsync(out_d2, d2, npx * 4, cudaMemcpyDeviceToHost, s));
