@@ -449,6 +449,12 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     const uint32_t fwdbuf_a = (uint32_t)__cvta_generic_to_shared(fwdbuf);
     if (TMA_ROWS) {
         if (lane == 0) mbar_init(fwdbar_a, 1);
+        // The forward rows were written with ordinary stores (generic proxy); the bulk copies below read them through
+        // the async proxy.  Without this fence the copy of the rows written last (hi - 1, hi - 2: the first ones the
+        // backward pass needs) can overtake their stores -- seen as wrong values in the bottom rows of a few frames per
+        // thousand when four batches were in flight.  Every lane fences its own stores, the warp barrier orders them
+        // before lane 0's copies.
+        asm volatile("fence.proxy.async;" ::: "memory");
         __syncwarp();
     }
     uint32_t fwd_phase = 0;           // parity of the transaction being waited for
