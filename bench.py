@@ -577,17 +577,20 @@ def run_ours(args, rank, world, local_rank):
             t_e2e = float(t.item())
         assert np.array_equal(r4[sel, :, :, 0], want["depth"]), "drop-in call differs from the oracle"
         nbytes = int(B * H * W * 4)
+        h2d_link, d2h_link = _lib.get_handle(local_rank).transfer_bytes()    # what the last call moved over the link
         per_rank = [nbytes * e2e_steps / t_own / 1e9]
         if dist is not None:
             g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
             dist.all_gather(g, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
             per_rank = [float(v.item()) for v in g]
-        e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+        e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_link),
+               "d2h_bytes_per_step": int(d2h_link), "host_input_bytes_per_step": nbytes, "steps": e2e_steps,
                "what": "tools.DT_complete_batch(x): pageable numpy [B,352,1216,1] in, a new numpy array out every call, "
-                       "synchronous (the reference's contract, tools.py:13-35); the input is staged through a pinned mirror "
-                       "by host threads, the output array's memory comes from a pool of page-locked buffers",
-               "per_rank_gbs_each_direction": [round(v, 2) for v in per_rank], "numa": numa,
+                       "synchronous (the reference's contract, tools.py:13-35); host threads read the input once and "
+                       "compact it to (pixel, value) pairs of the source / valid pixels (sparse upload, include/dtfill.h: "
+                       "h2d_bytes_per_step is what crossed the link, host_input_bytes_per_step the array handed in), the "
+                       "device rebuilds the dense frames; the output array's memory comes from a pool of page-locked buffers",
+               "per_rank_gbs_of_host_arrays_each_direction": [round(v, 2) for v in per_rank], "numa": numa,
                "stage_threads_per_rank": stage_threads}
         del r4
     # ---- the C ABI with pinned host buffers and all three outputs (what round 1 reported as e2e) ----

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("DTFILL_LIB") or os.path.join(_HERE, "libdtfill.so")
 E_ARG, E_CUDA, E_INDEX, E_NOMEM = -1, -2, -3, -4
 METRICS_KITTI, METRICS_NYU = 0, 1
 METRIC_COLS = 9
-ABI_VERSION = 4          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
+ABI_VERSION = 5          # DTFILL_ABI_VERSION of include/dtfill.h this module was written against
 METRIC_NAMES = ("mse", "rmse", "mae", "irmse", "imae", "delta1", "delta2", "delta3", "count")
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -72,6 +72,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_set_sky_min.argtypes = [vp, ci]
         L.dtfill_debug_set_skip.argtypes = [vp, ci]
         L.dtfill_set_stage_threads.argtypes = [vp, ci]
+        L.dtfill_set_sparse_upload.argtypes = [vp, ci]
+        L.dtfill_transfer_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
         L.dtfill_debug_get_tasks.argtypes = [vp, vp, ci]
@@ -89,7 +91,8 @@ def load() -> ctypes.CDLL:
                      "dtfill_flush", "dtfill_dt_pool", "dtfill_dt_pool_ex", "dtfill_outlier_removal",
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
                      "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip",
-                     "dtfill_run_eval_async", "dtfill_eval_totals", "dtfill_edt"):
+                     "dtfill_run_eval_async", "dtfill_eval_totals", "dtfill_edt", "dtfill_set_sparse_upload",
+                     "dtfill_transfer_bytes"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -268,6 +271,16 @@ class Handle:
     def set_stage_threads(self, threads: int):
         """Host threads per direction that stage pageable numpy buffers through pinned mirrors (-1 auto, 0 never)."""
         _check(self._L.dtfill_set_stage_threads(self._h, int(threads)), "dtfill_set_stage_threads")
+
+    def set_sparse_upload(self, enabled: bool):
+        """Pageable float32 host inputs are compacted to (index, value) pairs on the host instead of mirrored (default on)."""
+        _check(self._L.dtfill_set_sparse_upload(self._h, int(bool(enabled))), "dtfill_set_sparse_upload")
+
+    def transfer_bytes(self):
+        """(host-to-device, device-to-host) bytes the last synchronous call with host buffers moved over the link."""
+        a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        _check(self._L.dtfill_transfer_bytes(self._h, ctypes.byref(a), ctypes.byref(b)), "dtfill_transfer_bytes")
+        return int(a.value), int(b.value)
 
     def set_pipeline_depth(self, depth: int):
         """2: consecutive run_device_async calls may overlap (outputs final after flush()/status()); 1: strict."""

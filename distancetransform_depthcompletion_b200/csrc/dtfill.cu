@@ -83,6 +83,79 @@ static void copy_stream(void* dst, const void* src, size_t n) {
 static void copy_stream(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 #endif
 
+// Sparse upload.  A LiDAR frame is ~95 % pixels that are neither a source (tools.py:8) nor valid (tools.py:22); the path
+// never looks at the value of such a pixel, only at the two predicates.  When 0.0f is itself neither (src_cut > 0 and
+// val_thr >= 0, true for the reference's thresholds) a pageable input slice is therefore not copied into a pinned mirror
+// but compacted by the same host threads into (pixel index, value) pairs of the pixels that satisfy either predicate:
+// the threads read the slice once and write ~10 % of it, the link carries 0.4 instead of 4 bytes per pixel, and the
+// device rebuilds the dense slice (memset + scatter) in front of K1.  Bit-identical by construction: the predicates are
+// evaluated here exactly as K1 evaluates them (NaN is a source), and every dropped pixel is replaced by a value on the
+// same side of both.
+// A slice's pairs are kept as two arrays: indices [cap], then values [cap].
+#if defined(__x86_64__)
+struct CompressLut {
+    alignas(32) uint32_t perm[256][8];
+    CompressLut() {
+        for (int m = 0; m < 256; ++m) {
+            int k = 0;
+            for (int j = 0; j < 8; ++j) if (m & (1 << j)) perm[m][k++] = (uint32_t)j;
+            for (; k < 8; ++k) perm[m][k] = 0;
+        }
+    }
+};
+// branch-free left-packing: the kept lanes of 8 pixels move to the front with one permute, all 8 lanes are stored and the
+// cursor advances by the population count (idx / val need 8 entries of slack)
+#define DTFILL_AVX2 __attribute__((target("avx2,popcnt"), always_inline)) static inline
+DTFILL_AVX2 __m256 keep8_avx2(const float* p, __m256 vs, __m256 vv) {
+    const __m256 x = _mm256_loadu_ps(p);
+    return _mm256_or_ps(_mm256_cmp_ps(x, vs, _CMP_NLT_UQ), _mm256_cmp_ps(x, vv, _CMP_GT_OQ));
+}
+DTFILL_AVX2 size_t emit8_avx2(const CompressLut& lut, const float* p, uint32_t first, unsigned m, uint32_t* idx, uint32_t* val,
+                              size_t k) {
+    const __m256i iota = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m256i perm = _mm256_load_si256((const __m256i*)lut.perm[m]);
+    _mm256_storeu_ps((float*)(val + k), _mm256_permutevar8x32_ps(_mm256_loadu_ps(p), perm));
+    _mm256_storeu_si256((__m256i*)(idx + k),
+                        _mm256_permutevar8x32_epi32(_mm256_add_epi32(_mm256_set1_epi32((int)first), iota), perm));
+    return k + (size_t)__builtin_popcount(m);
+}
+__attribute__((target("avx2,popcnt"))) static size_t compact_block_avx2(const float* src, size_t n, uint32_t base, float scut,
+                                                                        float vthr, uint32_t* idx, uint32_t* val) {
+    static const CompressLut lut;
+    const __m256 vs = _mm256_set1_ps(scut), vv = _mm256_set1_ps(vthr);
+    size_t k = 0, i = 0;
+    for (; i + 32 <= n; i += 32) {            // most groups of 32 pixels of a LiDAR frame hold nothing: one test
+        const __m256 k0 = keep8_avx2(src + i, vs, vv), k1 = keep8_avx2(src + i + 8, vs, vv);
+        const __m256 k2 = keep8_avx2(src + i + 16, vs, vv), k3 = keep8_avx2(src + i + 24, vs, vv);
+        const __m256 any = _mm256_or_ps(_mm256_or_ps(k0, k1), _mm256_or_ps(k2, k3));
+        if (_mm256_testz_ps(any, any)) continue;
+        const unsigned m0 = (unsigned)_mm256_movemask_ps(k0), m1 = (unsigned)_mm256_movemask_ps(k1);
+        const unsigned m2 = (unsigned)_mm256_movemask_ps(k2), m3 = (unsigned)_mm256_movemask_ps(k3);
+        if (m0) k = emit8_avx2(lut, src + i, base + (uint32_t)i, m0, idx, val, k);
+        if (m1) k = emit8_avx2(lut, src + i + 8, base + (uint32_t)i + 8, m1, idx, val, k);
+        if (m2) k = emit8_avx2(lut, src + i + 16, base + (uint32_t)i + 16, m2, idx, val, k);
+        if (m3) k = emit8_avx2(lut, src + i + 24, base + (uint32_t)i + 24, m3, idx, val, k);
+    }
+    for (; i < n; ++i) {
+        const float x = src[i];
+        if (!(x < scut) || x > vthr) { memcpy(val + k, &x, 4); idx[k] = base + (uint32_t)i; ++k; }
+    }
+    return k;
+}
+#endif
+static size_t compact_block(const float* src, size_t n, uint32_t base, float scut, float vthr, uint32_t* idx, uint32_t* val) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+    if (avx2) return compact_block_avx2(src, n, base, scut, vthr, idx, val);
+#endif
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float x = src[i];
+        if (!(x < scut) || x > vthr) { memcpy(val + k, &x, 4); idx[k] = base + (uint32_t)i; ++k; }
+    }
+    return k;
+}
+
 class CopyPool {
 public:
     explicit CopyPool(int n) {
@@ -93,14 +166,12 @@ public:
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
-    // dst[0..bytes) = src[0..bytes), split over the pool's threads and the caller; returns when done
-    void copy(void* dst, const void* src, size_t bytes) {
-        const size_t grain = 2u << 20;
-        const size_t nparts = bytes / grain > 0 ? std::min<size_t>(bytes / grain, (th_.size() + 1) * 4) : 1;
-        if (nparts <= 1 || th_.empty()) { copy_stream(dst, src, bytes); return; }
+    // fn(0) .. fn(nparts - 1), split over the pool's threads and the caller; returns when all are done
+    void parallel_for(size_t nparts, const std::function<void(size_t)>& fn) {
+        if (nparts <= 1 || th_.empty()) { for (size_t i = 0; i < nparts; ++i) fn(i); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
-            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; nparts_ = nparts; next_ = 0; done_ = 0;
+            fn_ = &fn; nparts_ = nparts; next_ = 0; done_ = 0;
         }
         cv_.notify_all();
         work();
@@ -108,18 +179,50 @@ public:
         cv_done_.wait(lk, [this] { return done_ == nparts_; });
         nparts_ = 0;
     }
+    // dst[0..bytes) = src[0..bytes)
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t grain = 2u << 20;
+        const size_t nparts = bytes / grain > 0 ? std::min<size_t>(bytes / grain, (th_.size() + 1) * 4) : 1;
+        parallel_for(nparts, [=](size_t i) {
+            const size_t a = bytes * i / nparts, b = bytes * (i + 1) / nparts;
+            copy_stream((char*)dst + a, (const char*)src + a, b - a);
+        });
+    }
+    // indices and values of the pixels of src[0..n) that are a source or valid -> idx[0..count), val[0..count); returns
+    // count, or SIZE_MAX if they do not fit into cap entries (the caller then copies the slice densely)
+    size_t compact(uint32_t* idx, uint32_t* val, size_t cap, const float* src, size_t n, float scut, float vthr) {
+        const size_t block = 1u << 15;                       // pixels per work item
+        const size_t nparts = (n + block - 1) / block;
+        std::atomic<size_t> cursor{0};
+        std::atomic<bool> overflow{false};
+        parallel_for(nparts, [&](size_t i) {
+            if (overflow.load(std::memory_order_relaxed)) return;
+            thread_local std::vector<uint32_t> buf;
+            if (buf.size() < 2 * (block + 8)) buf.resize(2 * (block + 8));
+            uint32_t* bi = buf.data();
+            uint32_t* bv = buf.data() + block + 8;
+            const size_t a = i * block, len = std::min(block, n - a);
+            const size_t k = compact_block(src + a, len, (uint32_t)a, scut, vthr, bi, bv);
+            const size_t off = cursor.fetch_add(k);
+            if (off + k > cap) { overflow.store(true); return; }
+            memcpy(idx + off, bi, k * 4);
+            memcpy(val + off, bv, k * 4);
+        });
+        return overflow.load() ? SIZE_MAX : cursor.load();
+    }
 
 private:
     void work() {
         for (;;) {
             size_t i;
+            const std::function<void(size_t)>* fn;
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 if (next_ >= nparts_) return;
                 i = next_++;
+                fn = fn_;
             }
-            const size_t a = bytes_ * i / nparts_, b = bytes_ * (i + 1) / nparts_;
-            copy_stream(dst_ + a, src_ + a, b - a);
+            (*fn)(i);
             std::lock_guard<std::mutex> lk(mu_);
             if (++done_ == nparts_) cv_done_.notify_all();
         }
@@ -138,9 +241,8 @@ private:
     std::mutex mu_;
     std::condition_variable cv_, cv_done_;
     bool stop_ = false;
-    char* dst_ = nullptr;
-    const char* src_ = nullptr;
-    size_t bytes_ = 0, nparts_ = 0, next_ = 0, done_ = 0;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t nparts_ = 0, next_ = 0, done_ = 0;
 };
 
 struct PinBuf {
@@ -204,7 +306,10 @@ struct dtfill_ctx {
     Buf in_dev, depth_dev, dt_dev, lbl_dev, mask_dev, counts_out_dev, lidar_out_dev;   // staging for host-pointer calls
     Buf gt_dev, partial, per_frame, sums, edt_rows, edt_stack;
     // pinned mirrors of pageable caller buffers (see CopyPool) and the threads that fill / drain them
-    PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar;
+    PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar, pin_sparse;
+    Buf sparse_dev;                   // (index, value) pairs of a sparse upload, per slice
+    bool sparse_upload = true;        // pageable float32 inputs are compacted on the host instead of mirrored (see CopyPool)
+    size_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last synchronous host call moved over the link
     CopyPool* pool_in = nullptr;
     CopyPool* pool_out = nullptr;
     int stage_threads = -1;           // threads per direction; -1: automatic; 0: never stage (driver-staged copies)
@@ -265,6 +370,10 @@ struct HostIO {
     int32_t* lbl_pin = nullptr;
     uint8_t* mask_pin = nullptr;
     bool any_out_pin() const { return lidar_pin || depth_pin || dt_pin || lbl_pin || mask_pin; }
+    // sparse upload of a pageable float32 input (instead of in_pin): pinned pair buffer, pairs per pixel it can hold
+    uint32_t* sparse_pin = nullptr;   // per slice: indices [cap], values [cap]
+    size_t sparse_cap_div = 0;        // capacity of a slice of n pixels: cap = n / sparse_cap_div pairs
+    float sparse_scut = 0.f, sparse_vthr = 0.f;
 };
 
 bool is_pageable(const void* p) {
@@ -281,6 +390,14 @@ int ensure_pinned(PinBuf& b, size_t bytes) {
     if (e != cudaSuccess) { b.p = nullptr; return fail(DTFILL_E_NOMEM, std::string("cudaHostAlloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
     b.cap = want;
     return 0;
+}
+
+// dense slice = zeros + the pairs of a sparse upload (see CopyPool::compact)
+__global__ void __launch_bounds__(256) k0_scatter_pairs(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val,
+                                                         unsigned n, float* __restrict__ dst)
+{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) dst[idx[i]] = __uint_as_float(val[i]);
 }
 
 struct Plan {
@@ -574,16 +691,46 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     if (nsub > Lane::MAX_SUB) nsub = Lane::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
+    void* dense_pin = hio ? hio->in_pin : nullptr;      // pinned mirror of a pageable input (allocated late on the sparse path)
     auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
         const size_t frame_bytes = h->in_u16 ? (size_t)h->in_H * W * 2 : (size_t)H * W * 4;
         const char* src = (const char*)hio->in + b0 * frame_bytes;
-        if (hio->in_pin) {         // pageable input: this slice -> pinned mirror (pool threads), DMA from there
-            char* pin = (char*)hio->in_pin + b0 * frame_bytes;
+        if (hio->sparse_pin) {     // pageable float32 input: compact the slice on the host, rebuild it on the device
+            const size_t o = (size_t)b0 * H * W, n = (size_t)nb * H * W;
+            const size_t cap = n / hio->sparse_cap_div;
+            const size_t ro = 2 * (o / hio->sparse_cap_div);          // this slice's region: indices [cap], values [cap]
+            uint32_t* pi = hio->sparse_pin + ro;
+            uint32_t* pv = pi + cap;
+            const size_t cnt = n < (1ull << 32) ? h->pool_in->compact(pi, pv, cap, (const float*)src, n, hio->sparse_scut, hio->sparse_vthr)
+                                                : SIZE_MAX;
+            if (cnt != SIZE_MAX) {
+                float* dst = (float*)const_cast<void*>(in) + o;
+                CU(cudaMemsetAsync(dst, 0, n * 4, st));
+                if (cnt) {
+                    uint32_t* di = (uint32_t*)h->sparse_dev.p + ro;
+                    uint32_t* dv = di + cap;
+                    CU(cudaMemcpyAsync(di, pi, cnt * 4, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(dv, pv, cnt * 4, cudaMemcpyHostToDevice, st));
+                    k0_scatter_pairs<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(di, dv, (unsigned)cnt, dst);
+                }
+                h->last_h2d_bytes += cnt * 8;
+                return 0;
+            }
+            // a slice denser than the pair buffer allows: the mirror after all
+            if (!dense_pin) {
+                int r = ensure_pinned(h->pin_in, (size_t)B * frame_bytes);
+                if (r) return r;
+                dense_pin = h->pin_in.p;
+            }
+        }
+        if (dense_pin) {           // pageable input: this slice -> pinned mirror (pool threads), DMA from there
+            char* pin = (char*)dense_pin + b0 * frame_bytes;
             h->pool_in->copy(pin, src, nb * frame_bytes);
             src = pin;
         }
         CU(cudaMemcpyAsync((char*)const_cast<void*>(in) + b0 * frame_bytes, src, nb * frame_bytes, cudaMemcpyHostToDevice, st));
+        h->last_h2d_bytes += nb * frame_bytes;
         return 0;
     };
     auto copy_out = [&](cudaStream_t st, int b0, int nb) -> int {
@@ -597,6 +744,7 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
         if (hio->counts)
             CU(cudaMemcpyAsync(hio->counts + 2 * (size_t)b0, out_counts + 2 * (size_t)b0, (size_t)nb * 8,
                                cudaMemcpyDeviceToHost, st));
+        h->last_d2h_bytes += n * (4 + (hio->lidar ? 4 : 0) + (hio->dt ? 4 : 0) + (hio->lbl ? 4 : 0) + (hio->mask ? 1 : 0));
         return 0;
     };
     if (nsub == 1 && !(hio && hio->any_out_pin())) {
@@ -750,6 +898,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_SKY_MIN")) h->sky_min = atoi(e) < -1 ? -1 : atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     if (const char* e = getenv("DTFILL_STAGE_THREADS")) h->stage_threads = atoi(e);
+    if (const char* e = getenv("DTFILL_SPARSE_UPLOAD")) h->sparse_upload = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
         const int d = atoi(e);
         h->pipeline_depth = d < 1 ? 1 : (d > dtfill_ctx::MAX_LANES ? dtfill_ctx::MAX_LANES : d);
@@ -781,14 +930,14 @@ void dtfill_destroy(dtfill_t* h) {
         }
     }
     Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->lidar_out_dev,
-                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_stack};
+                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_stack, &h->sparse_dev};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* q : h->retired) cudaFree(q);
     if (h->counts_host) cudaFreeHost(h->counts_host);
     delete h->pool_in;
     delete h->pool_out;
-    for (PinBuf* b : {&h->pin_in, &h->pin_depth, &h->pin_dt, &h->pin_lbl, &h->pin_mask, &h->pin_lidar})
+    for (PinBuf* b : {&h->pin_in, &h->pin_depth, &h->pin_dt, &h->pin_lbl, &h->pin_mask, &h->pin_lidar, &h->pin_sparse})
         if (b->p) cudaFreeHost(b->p);
     if (h->status_ring) cudaFreeHost(h->status_ring);
     for (auto& e : h->slot_done)
@@ -905,6 +1054,7 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
         if (out_counts) { if ((rc = ensure(h, h->counts_out_dev, (size_t)B * 8))) return rc; oc = (int32_t*)h->counts_out_dev.p; }
     }
     InputScope scope(h, u16, in_H, in_crop, olid);
+    h->last_h2d_bytes = h->last_d2h_bytes = 0;
     if (pipelined) {
         HostIO hio;
         hio.in = in; hio.lidar = out_lidar; hio.depth = out_depth; hio.dt = out_dt; hio.lbl = out_lbl; hio.mask = out_mask;
@@ -927,7 +1077,18 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
                     h->pool_in = new CopyPool(n - 1);       // the calling thread works too
                     h->pool_out = new CopyPool(n - 1);
                 }
-                if (pin_i) { if ((rc = ensure_pinned(h->pin_in, in_bytes))) return rc; hio.in_pin = h->pin_in.p; }
+                // pageable float32 input whose zero pixels are neither sources nor valid: sparse upload (the dense mirror
+                // is only allocated if a slice turns out too dense)
+                const float scut = source_cut(src_thr);
+                const size_t cap_div = 4;                       // room for 25 % of the pixels
+                if (pin_i && !u16 && h->sparse_upload && scut > 0.0f && val_thr >= 0.0f) {
+                    if ((rc = ensure_pinned(h->pin_sparse, (npx / cap_div + 16) * 8))) return rc;
+                    if ((rc = ensure(h, h->sparse_dev, (npx / cap_div + 16) * 8))) return rc;
+                    hio.sparse_pin = (uint32_t*)h->pin_sparse.p;
+                    hio.sparse_cap_div = cap_div;
+                    hio.sparse_scut = scut; hio.sparse_vthr = val_thr;
+                    if (h->pin_in.cap >= in_bytes) hio.in_pin = h->pin_in.p;
+                } else if (pin_i) { if ((rc = ensure_pinned(h->pin_in, in_bytes))) return rc; hio.in_pin = h->pin_in.p; }
                 if (pin_d) { if ((rc = ensure_pinned(h->pin_depth, npx * 4))) return rc; hio.depth_pin = (float*)h->pin_depth.p; }
                 if (pin_t) { if ((rc = ensure_pinned(h->pin_dt, npx * 4))) return rc; hio.dt_pin = (float*)h->pin_dt.p; }
                 if (pin_l) { if ((rc = ensure_pinned(h->pin_lbl, npx * 4))) return rc; hio.lbl_pin = (int32_t*)h->pin_lbl.p; }
@@ -1172,6 +1333,19 @@ int dtfill_set_stage_threads(dtfill_t* h, int threads) {
         h->pool_in = h->pool_out = nullptr;
         h->stage_threads = threads;
     }
+    return 0;
+}
+
+int dtfill_set_sparse_upload(dtfill_t* h, int enabled) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_sparse_upload: NULL handle");
+    h->sparse_upload = enabled != 0;
+    return 0;
+}
+
+int dtfill_transfer_bytes(dtfill_t* h, unsigned long long* h2d, unsigned long long* d2h) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_transfer_bytes: NULL handle");
+    if (h2d) *h2d = h->last_h2d_bytes;
+    if (d2h) *d2h = h->last_d2h_bytes;
     return 0;
 }
 

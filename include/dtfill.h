@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTFILL_ABI_VERSION 4      /* 4: dtfill_run_eval_async + dtfill_eval_totals, dtfill_edt; 3: metrics_ex, allreduce, status ring */
+#define DTFILL_ABI_VERSION 5      /* 5: sparse upload (dtfill_set_sparse_upload, dtfill_transfer_bytes); 4: dtfill_run_eval_async + dtfill_eval_totals, dtfill_edt; 3: metrics_ex, allreduce, status ring */
 
 enum {
     DTFILL_OK = 0,
@@ -257,6 +257,16 @@ int dtfill_kernel_times(dtfill_t* h, float* ms);
  * driver stages the copies on the calling thread).  Buffers that are already pinned (dtfill_host_alloc,
  * cudaHostRegister) are copied directly in either case. */
 int dtfill_set_stage_threads(dtfill_t* h, int threads);
+
+/* Sparse upload (on by default; DTFILL_SPARSE_UPLOAD=0).  dtfill_run with a PAGEABLE float32 host input: the host threads
+ * that would copy a slice into a page-locked mirror compact it instead into (pixel index, value) pairs of the pixels that
+ * are a source (tools.py:8) or valid (tools.py:22) -- the only pixels whose value the path ever reads -- and the device
+ * rebuilds the dense slice from zeros + pairs in front of the first kernel.  Results are bit-identical; it applies when
+ * 0.0f is neither a source nor valid (true for the reference's thresholds 0.1 / 0.001 and 0.1) and falls back to the
+ * dense copy for a slice with more than 25 % such pixels.  dtfill_transfer_bytes reports what the last synchronous call
+ * with host buffers moved over the link in each direction. */
+int dtfill_set_sparse_upload(dtfill_t* h, int enabled);
+int dtfill_transfer_bytes(dtfill_t* h, unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
 /* Pinned host memory for fast host<->device copies (cudaHostAlloc / cudaFreeHost). */
 int  dtfill_host_alloc(void** out_ptr, size_t bytes);

@@ -281,3 +281,40 @@ def test_allreduce_sums_two_ranks_equal_one_rank(handle, torch_mod):
     np.testing.assert_allclose(got, one, rtol=1e-12)
     m2, m1 = sharding.finalize_means(got), sharding.finalize_means(one)
     assert m2["frames"] == n and abs(m2["rmse"] - m1["rmse"]) <= 1e-12 * m1["rmse"]
+
+
+@pytest.mark.gpu
+def test_sparse_upload_matches_dense_upload(handle):
+    """dtfill_run with a pageable float32 input compacts it on the host to (pixel, value) pairs (include/dtfill.h, sparse
+    upload): same outputs as the dense copy and as the oracle, for sparse frames, for frames too dense for the pair
+    buffer (fallback inside one call), for NaN / negative / denormal / signed-zero pixels and for the valid-but-not-source
+    band of tools.py:8 vs :22; thresholds that make 0.0 a source switch it off."""
+    rng = np.random.default_rng(11)
+    H, W, B = 96, 256, 20
+    x = np.zeros((B, H, W), np.float32)
+    for b in range(B):
+        dens = [0.01, 0.05, 0.2, 0.6][b % 4]                          # 0.6: more than the pair buffer holds
+        m = rng.random((H, W)) < dens
+        x[b][m] = (np.round(rng.uniform(0.05, 60.0, m.sum()) * 256) / 256).astype(np.float32)
+    x[4, 5, 7] = np.nan; x[4, 9, 9] = -4.0; x[4, 10, 10] = -0.0; x[4, 11, 11] = 1e-41       # NaN: a source, not valid
+    x[4, 20, 20] = 0.5; x[4, 21, 21] = 0.1; x[4, 22, 22] = 0.9; x[4, 23, 23] = np.float32(0.90000004)
+    want = O.dt_fill(x)
+    outs = {}
+    for sparse in (True, False):
+        handle.set_sparse_upload(sparse)
+        try:
+            r = handle.run_host(x, 0.1, 0.1, want_dt=True, want_lbl=True, want_mask=True)
+            outs[sparse] = r, handle.transfer_bytes()
+        finally:
+            handle.set_sparse_upload(True)
+        for k in ("depth", "dt", "lbl", "mask"):
+            assert np.array_equal(r[k], want[k], equal_nan=True), (sparse, k)
+    assert outs[False][1][0] == x.nbytes                                # dense: the whole array crossed the link
+    assert outs[True][1][0] < x.nbytes                                  # sparse: pairs, plus the slices that fell back
+    assert outs[True][1][1] == outs[False][1][1] == B * H * W * 13
+    # a source threshold >= 1 makes 0.0 a source: the dense copy must be taken (every pixel valid, so no IndexError)
+    xd = (np.round(rng.uniform(1.0, 50.0, (2, H, W)) * 256) / 256).astype(np.float32)
+    r = handle.run_host(xd, 1.0, 0.1, want_dt=True)
+    w2 = O.dt_fill(xd, src_thr=1.0)
+    assert np.array_equal(r["dt"], w2["dt"]) and np.array_equal(r["depth"], w2["depth"])
+    assert handle.transfer_bytes()[0] == xd.nbytes
