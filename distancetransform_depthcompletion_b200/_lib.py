@@ -73,6 +73,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_debug_set_skip.argtypes = [vp, ci]
         L.dtfill_set_stage_threads.argtypes = [vp, ci]
         L.dtfill_set_sparse_upload.argtypes = [vp, ci]
+        L.dtfill_set_metrics_exact.argtypes = [vp, ci]
         L.dtfill_transfer_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]
         L.dtfill_flush.argtypes = [vp]
@@ -92,7 +93,7 @@ def load() -> ctypes.CDLL:
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
                      "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip",
                      "dtfill_run_eval_async", "dtfill_eval_totals", "dtfill_edt", "dtfill_set_sparse_upload",
-                     "dtfill_transfer_bytes"):
+                     "dtfill_transfer_bytes", "dtfill_set_metrics_exact"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -271,6 +272,10 @@ class Handle:
     def set_stage_threads(self, threads: int):
         """Host threads per direction that stage pageable numpy buffers through pinned mirrors (-1 auto, 0 never)."""
         _check(self._L.dtfill_set_stage_threads(self._h, int(threads)), "dtfill_set_stage_threads")
+
+    def set_metrics_exact(self, enabled: bool):
+        """metrics(): numpy's pairwise summation order, bit for bit (default), or one-pass fixed-order float64 sums."""
+        _check(self._L.dtfill_set_metrics_exact(self._h, int(bool(enabled))), "dtfill_set_metrics_exact")
 
     def set_sparse_upload(self, enabled: bool):
         """Pageable float32 host inputs are compacted to (index, value) pairs on the host instead of mirrored (default on)."""

@@ -308,6 +308,8 @@ struct dtfill_ctx {
     // pinned mirrors of pageable caller buffers (see CopyPool) and the threads that fill / drain them
     PinBuf pin_in, pin_depth, pin_dt, pin_lbl, pin_mask, pin_lidar, pin_sparse;
     Buf sparse_dev;                   // (index, value) pairs of a sparse upload, per slice
+    Buf mx_terms, mx_counts, mx_leaf_start, mx_leaf_sum;     // dtfill_metrics in numpy's summation order (k4x_*)
+    bool metrics_exact = true;        // dtfill_metrics / _ex reproduce np.mean's pairwise sums bit for bit
     bool sparse_upload = true;        // pageable float32 inputs are compacted on the host instead of mirrored (see CopyPool)
     size_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last synchronous host call moved over the link
     CopyPool* pool_in = nullptr;
@@ -899,6 +901,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     if (const char* e = getenv("DTFILL_STAGE_THREADS")) h->stage_threads = atoi(e);
     if (const char* e = getenv("DTFILL_SPARSE_UPLOAD")) h->sparse_upload = atoi(e) != 0;
+    if (const char* e = getenv("DTFILL_METRICS_EXACT")) h->metrics_exact = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_PIPELINE_DEPTH")) {
         const int d = atoi(e);
         h->pipeline_depth = d < 1 ? 1 : (d > dtfill_ctx::MAX_LANES ? dtfill_ctx::MAX_LANES : d);
@@ -930,7 +933,8 @@ void dtfill_destroy(dtfill_t* h) {
         }
     }
     Buf* bufs[] = {&h->in_dev, &h->depth_dev, &h->dt_dev, &h->lbl_dev, &h->mask_dev, &h->counts_out_dev, &h->lidar_out_dev,
-                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_stack, &h->sparse_dev};
+                   &h->gt_dev, &h->partial, &h->per_frame, &h->sums, &h->edt_rows, &h->edt_stack, &h->sparse_dev,
+                   &h->mx_terms, &h->mx_counts, &h->mx_leaf_start, &h->mx_leaf_sum};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* q : h->retired) cudaFree(q);
@@ -1233,15 +1237,47 @@ int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_
         p_d = (const float*)h->in_dev.p;
         g_d = h->gt_dev.p;
     }
+    if ((rc = ensure(h, h->per_frame, (size_t)B * 9 * 8))) return rc;
+    if ((rc = ensure(h, h->sums, 10 * 8))) return rc;
+    double* pf_d = (out_is_device && per_frame) ? per_frame : (double*)h->per_frame.p;
+    double* sm_d = (out_is_device && sums) ? sums : (double*)h->sums.p;
+    if (h->metrics_exact && npx < (1l << 31)) {
+        // numpy's own summation order (k4x_*): per-pixel terms of the valid pixels compacted in raster order, then the
+        // pairwise tree of np.add.reduce; groups of frames share a scratch of at most ~1 GiB
+        const long maxl = npx / 64 + 2;
+        long G = (long)((1ull << 30) / ((size_t)4 * npx * gsz));
+        G = G < 1 ? 1 : (G > B ? B : G);
+        if ((rc = ensure(h, h->mx_terms, (size_t)G * 4 * npx * gsz))) return rc;
+        if ((rc = ensure(h, h->mx_counts, (size_t)G * 4 * 4))) return rc;
+        if ((rc = ensure(h, h->mx_leaf_start, (size_t)G * maxl * 4))) return rc;
+        if ((rc = ensure(h, h->mx_leaf_sum, (size_t)G * 4 * maxl * gsz))) return rc;
+        for (long g0 = 0; g0 < B; g0 += G) {
+            const int ng = (int)(B - g0 < G ? B - g0 : G);
+            const float* pg = p_d + g0 * npx;
+            int* cn = (int*)h->mx_counts.p;
+            int* lst = (int*)h->mx_leaf_start.p;
+            double* pfg = pf_d + g0 * 9;
+            if (gt_is_f64) {
+                const double* gg = (const double*)g_d + g0 * npx;
+                double* tm = (double*)h->mx_terms.p;
+                if (mode == 0) k4x_compact<double, 0><<<ng, K4X_THREADS, 0, s>>>(pg, gg, npx, tm, cn);
+                else k4x_compact<double, 1><<<ng, K4X_THREADS, 0, s>>>(pg, gg, npx, tm, cn);
+                k4x_reduce<double><<<ng, K4X_RTHREADS, 0, s>>>(tm, cn, npx, mode, lst, (double*)h->mx_leaf_sum.p, pfg);
+            } else {
+                const float* gg = (const float*)g_d + g0 * npx;
+                float* tm = (float*)h->mx_terms.p;
+                if (mode == 0) k4x_compact<float, 0><<<ng, K4X_THREADS, 0, s>>>(pg, gg, npx, tm, cn);
+                else k4x_compact<float, 1><<<ng, K4X_THREADS, 0, s>>>(pg, gg, npx, tm, cn);
+                k4x_reduce<float><<<ng, K4X_RTHREADS, 0, s>>>(tm, cn, npx, mode, lst, (float*)h->mx_leaf_sum.p, pfg);
+            }
+        }
+        k4x_sums<<<1, 32, 0, s>>>(pf_d, B, sm_d, accumulate);
+    } else {
     int chunks = (int)((npx + 16383) / 16384);     // chunk boundaries stay multiples of 4 pixels when npx is
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     while (chunks > 1 && (((npx + chunks - 1) / chunks) & 3)) --chunks;
     if ((rc = ensure(h, h->partial, (size_t)B * chunks * ACC * 8))) return rc;
-    if ((rc = ensure(h, h->per_frame, (size_t)B * 9 * 8))) return rc;
-    if ((rc = ensure(h, h->sums, 10 * 8))) return rc;
-    double* pf_d = (out_is_device && per_frame) ? per_frame : (double*)h->per_frame.p;
-    double* sm_d = (out_is_device && sums) ? sums : (double*)h->sums.p;
     dim3 grid(chunks, B);
     double* part = (double*)h->partial.p;
     if (gt_is_f64) {
@@ -1252,6 +1288,7 @@ int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_
         else k4_metrics_partial<float, 1><<<grid, 256, 0, s>>>(p_d, (const float*)g_d, npx, chunks, part);
     }
     k4_metrics_final<<<1, 256, 0, s>>>(part, B, chunks, mode, pf_d, sm_d, accumulate);
+    }
     CU(cudaGetLastError());
     if (!out_is_device) {
         if (per_frame) CU(cudaMemcpyAsync(per_frame, pf_d, (size_t)B * 9 * 8, cudaMemcpyDeviceToHost, s));
@@ -1333,6 +1370,12 @@ int dtfill_set_stage_threads(dtfill_t* h, int threads) {
         h->pool_in = h->pool_out = nullptr;
         h->stage_threads = threads;
     }
+    return 0;
+}
+
+int dtfill_set_metrics_exact(dtfill_t* h, int enabled) {
+    if (!h) return fail(DTFILL_E_ARG, "dtfill_set_metrics_exact: NULL handle");
+    h->metrics_exact = enabled != 0;
     return 0;
 }
 

@@ -33,7 +33,7 @@ __device__ __forceinline__ void metric_accumulate(float o, GT t, double* a)
         const GT rel = d / t;                                          // :210
         const GT r1 = og / t, r2 = t / og;                             // :217
         const GT mr = r1 > r2 ? r1 : r2;
-        const GT io = (GT)1.0 / og, it = (GT)1.0 / t;                  // :232-233
+        const GT io = (GT)(1.0f / o), it = (GT)1.0 / t;                // :232-233 (output ** (-1) stays float32)
         const GT di = io > it ? io - it : it - io;
         const GT di2 = di * di;
         a[0] += (double)d2; a[1] += (double)d; a[2] += (double)di2; a[3] += (double)di; a[4] += 1.0;

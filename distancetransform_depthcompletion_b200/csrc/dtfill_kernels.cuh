@@ -33,6 +33,7 @@
 #include "dtfill_k3_sky.cuh"
 #include "dtfill_k2_wide.cuh"
 #include "dtfill_k4_metrics.cuh"
+#include "dtfill_k4_exact.cuh"
 #include "dtfill_k5_pool.cuh"
 #include "dtfill_k6_outlier.cuh"
 #include "dtfill_k7_edt.cuh"

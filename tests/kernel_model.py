@@ -171,3 +171,35 @@ def sky_rows_closed_form(dt: np.ndarray, lbl: np.ndarray, S: int):
         ol[y] = lbl[row, col]
         odt[y] = g + (S - y)
     return odt, ol
+
+
+def numpy_pairwise_sum(a, T=None):
+    """np.add.reduce over a contiguous 1-D array, restated (numpy/_core/src/umath/loops_utils.h.src pairwise sum): the
+    order csrc/dtfill_k4_exact.cuh reproduces on the GPU.  T: accumulation dtype (default: a's)."""
+    import numpy as np
+    a = np.asarray(a)
+    T = T or a.dtype.type
+
+    def rec(lo, n):
+        if n < 8:
+            r = T(0.0)
+            for i in range(n):
+                r = T(r + a[lo + i])
+            return r
+        if n <= 128:
+            r = [a[lo + j] for j in range(8)]
+            i = 8
+            while i < n - (n % 8):
+                for j in range(8):
+                    r[j] = T(r[j] + a[lo + i + j])
+                i += 8
+            res = T(T(T(r[0] + r[1]) + T(r[2] + r[3])) + T(T(r[4] + r[5]) + T(r[6] + r[7])))
+            while i < n:
+                res = T(res + a[lo + i])
+                i += 1
+            return res
+        n2 = n // 2
+        n2 -= n2 % 8
+        return T(rec(lo, n2) + rec(lo + n2, n - n2))
+
+    return rec(0, len(a))

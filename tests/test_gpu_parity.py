@@ -12,8 +12,9 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-METRIC_RTOL_F64 = 1e-9     # float64 ground truth: both sides accumulate in float64, only the order differs
-METRIC_RTOL_F32 = 2e-5     # float32 ground truth: numpy's mean itself accumulates in float32 (pairwise)
+METRIC_RTOL_F64 = 1e-9     # one-pass sums (dtfill_run_eval_async, metrics_exact off), float64 ground truth: the order differs
+METRIC_RTOL_F32 = 2e-5     # ... float32 ground truth: numpy's mean itself accumulates in float32 (pairwise)
+# dtfill_metrics in its default mode reproduces numpy's pairwise sums: compared with == below
 
 
 def sha(a):
@@ -354,16 +355,15 @@ def test_metrics_golden_and_oracle(handle, golden_dir):
         gt = synth.kitti_gt(seed)
         R = evaluation.Result()
         assert R.evaluate(fill, gt) is None
-        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_s{seed}"], rtol=METRIC_RTOL_F64)
+        np.testing.assert_array_equal([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_s{seed}"])
         R.evaluate(np.maximum(fill, np.float32(0.9)), gt.astype(np.float32))
-        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_f32gt_s{seed}"],
-                                   rtol=METRIC_RTOL_F32)
+        np.testing.assert_array_equal([R.mse, R.rmse, R.mae, R.irmse, R.imae], z[f"kitti_f32gt_s{seed}"])
         xn, g = synth.nyu_frame(seed, return_dense=True)
         fill = eval_nyu.Distance_Transform(xn)
         R = evaluation.Result_NYU()
         R.evaluate(fill, g)
-        np.testing.assert_allclose([R.mse, R.rmse, R.mae, R.irmse, R.imae, R.delta1, R.delta2, R.delta3],
-                                   z[f"nyu_s{seed}"], rtol=METRIC_RTOL_F32)
+        np.testing.assert_array_equal([R.mse, R.rmse, R.mae, R.irmse, R.imae, R.delta1, R.delta2, R.delta3],
+                                      z[f"nyu_s{seed}"])
     # empty valid set -> nan like numpy's mean of an empty array
     R = evaluation.Result()
     R.evaluate(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float64))
@@ -377,9 +377,36 @@ def test_metrics_batch_sums(handle):
     per_frame, sums = evaluation.evaluate_batch(fills, gts, _lib.METRICS_KITTI)
     want = np.array([[m["mse"], m["rmse"], m["mae"], m["irmse"], m["imae"], 0, 0, 0, m["count"]]
                      for m in (O.result_kitti(fills[i], gts[i]) for i in range(B))])
-    np.testing.assert_allclose(per_frame, want, rtol=METRIC_RTOL_F64)
-    np.testing.assert_allclose(sums[:9], want.sum(axis=0), rtol=METRIC_RTOL_F64)
+    np.testing.assert_array_equal(per_frame, want)              # numpy's summation order, bit for bit
+    np.testing.assert_allclose(sums[:9], want.sum(axis=0), rtol=1e-14)
     assert sums[9] == B
+
+
+def test_metrics_bit_exact_over_sizes(handle):
+    """dtfill_metrics against evaluation.py restated with numpy (oracle.result_*), ==: valid counts below 8, up to 128
+    (one leaf of numpy's pairwise sum), just above, odd, and frame-sized; float32 and float64 ground truth; both modes;
+    and the one-pass mode within its stated tolerance."""
+    rng = np.random.default_rng(5)
+    for n_px, dens in ((64, 0.05), (200, 0.5), (300, 0.45), (1000, 0.9), (4099, 0.3), (12345, 1.0), (352 * 1216, 0.2),
+                       (480 * 640, 1.0)):
+        B = 3
+        out = rng.uniform(0.5, 80.0, (B, n_px)).astype(np.float32)
+        gt64 = rng.uniform(0.5, 80.0, (B, n_px)) * (rng.random((B, n_px)) < dens)
+        for gt in (gt64, gt64.astype(np.float32)):
+            for mode, ref in ((_lib.METRICS_KITTI, O.result_kitti), (_lib.METRICS_NYU, O.result_nyu)):
+                per_frame, sums = evaluation.evaluate_batch(out, gt, mode)
+                for b in range(B):
+                    m = ref(out[b], gt[b])
+                    want = [m["mse"], m["rmse"], m["mae"], m["irmse"], m["imae"], m.get("delta1", 0), m.get("delta2", 0),
+                            m.get("delta3", 0), m["count"]]
+                    np.testing.assert_array_equal(per_frame[b], want, err_msg=f"{n_px} {gt.dtype} mode {mode} frame {b}")
+    handle.set_metrics_exact(False)
+    try:
+        per_frame, _ = evaluation.evaluate_batch(out, gt64, _lib.METRICS_KITTI)
+        m = O.result_kitti(out[0], gt64[0])
+        np.testing.assert_allclose(per_frame[0, :5], [m["mse"], m["rmse"], m["mae"], m["irmse"], m["imae"]], rtol=METRIC_RTOL_F64)
+    finally:
+        handle.set_metrics_exact(True)
 
 
 def test_pipelined_mode_matches_strict(handle):

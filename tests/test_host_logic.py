@@ -77,3 +77,17 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|dtfill_oracle|libdtfill_oracle", src, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_numpy_pairwise_sum_restated():
+    """The summation order dtfill_metrics reproduces (csrc/dtfill_k4_exact.cuh) IS numpy's: the restatement in
+    tests/kernel_model.py equals np.add.reduce and np.mean bit for bit, float32 and float64, over the length classes of
+    the algorithm (below 8, one block of up to 128, splits rounded to multiples of 8)."""
+    from kernel_model import numpy_pairwise_sum
+    rng = np.random.default_rng(0)
+    for T in (np.float32, np.float64):
+        for n in list(range(1, 20)) + [127, 128, 129, 136, 255, 256, 257, 1000, 4097, 12345, 86000]:
+            a = (rng.random(n) * 1000).astype(T)
+            s = numpy_pairwise_sum(a)
+            assert s == np.add.reduce(a), (T.__name__, n)
+            assert T(s / T(n)) == np.mean(a), (T.__name__, n)
