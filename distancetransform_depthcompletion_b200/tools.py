@@ -17,11 +17,40 @@ _H, _W = 352, 1216      # tools.py:25,27 hard-coded frame size
 
 def _as_frames_f32(a: np.ndarray, what: str) -> np.ndarray:
     if a.dtype != np.float32:
-        if a.dtype == np.float64 or a.dtype == np.float16 or np.issubdtype(a.dtype, np.integer):
-            raise TypeError(f"{what}: dtype {a.dtype} is not supported by the CUDA path (float32 only; every "
-                            "in-tree producer of the reference yields float32, data_read.py:215,371)")
-        raise TypeError(f"{what}: unsupported dtype {a.dtype}")
+        raise TypeError(f"{what}: dtype {a.dtype} is not supported by the CUDA path (float32, or float64 / integers "
+                        "through the float64 route of tools.nearest_point / DT_complete_batch / Distance_Transform)")
     return np.ascontiguousarray(a)
+
+
+def _is_wide(a: np.ndarray) -> bool:
+    """float64 (or integer) input: the reference evaluates its predicates in float64 (tools.py:8, :22)."""
+    return a.dtype == np.float64 or np.issubdtype(a.dtype, np.integer)
+
+
+def _labels_f64(frames: np.ndarray, src_thr: float, device):
+    """float64 / integer frames [B,H,W]: the reference's predicates evaluated in float64 on the host (tools.py:8
+    ``1.0 - x > thr``, tools.py:22 ``x > 0.1``), handed to the kernels as a float32 surrogate frame that has exactly those
+    predicates in float32 (1.0: source and valid, 0.5: valid only, NaN: source only, 0.0: neither), so distances and
+    labels are the reference's; the depths are gathered on the host from the float64 values (tools.py:24-26), which the
+    float32 kernels cannot carry.  Returns (dt, lbl, valid masks, the run's result dict)."""
+    if not (0.0 <= float(src_thr) < 0.5):
+        raise TypeError("float64 input needs a source threshold in [0, 0.5) (the reference uses 0.1 and 0.001)")
+    x = frames.astype(np.float64, copy=False)
+    with np.errstate(invalid="ignore"):
+        src = ~((1.0 - x) > src_thr)
+        val = x > VALID_THR
+    sur = np.zeros(x.shape, np.float32)
+    sur[val] = np.float32(0.5)
+    sur[src & val] = np.float32(1.0)
+    sur[src & ~val] = np.float32(np.nan)
+    r = _lib.get_handle(device).run_host(sur, src_thr, VALID_THR, want_dt=True, want_lbl=True)
+    return r["dt"], r["lbl"], val, r
+
+
+def _gather_f64(frame: np.ndarray, val: np.ndarray, lbl: np.ndarray) -> np.ndarray:
+    """tools.py:24-26 on the host: depth_list = x[valid]; depth_list[lbl - 1] (numpy's own IndexError / index -1)."""
+    depth_list = frame[val]
+    return depth_list[lbl.reshape(-1) - 1].reshape(frame.shape)
 
 
 def nearest_point(refined_lidar, thr: float = KITTI_SRC_THR, device: int | None = None):
@@ -30,6 +59,9 @@ def nearest_point(refined_lidar, thr: float = KITTI_SRC_THR, device: int | None 
     if x.ndim != 2:
         # cv2.distanceTransformWithLabels accepts only a single-channel 2-D image
         raise ValueError(f"nearest_point: input must squeeze to 2-D, got shape {np.shape(refined_lidar)}")
+    if _is_wide(x):
+        dt, lbl, _, _ = _labels_f64(x[None], thr, device)
+        return dt[0], lbl[0]
     x = _as_frames_f32(x, "nearest_point")
     r = _lib.get_handle(device).run_host(x[None], thr, VALID_THR, want_dt=True, want_lbl=True, want_counts=False)
     return r["dt"][0], r["lbl"][0]
@@ -47,6 +79,14 @@ def DT_complete_batch(lidar_batch, device: int | None = None):
         raise ValueError(f"cannot reshape array of size {H * W} into shape ({_H},{_W})")            # tools.py:25-27
     if min(H, W) < 2:
         raise ValueError("DT_complete_batch: frames must be 2-D after squeeze")
+    if _is_wide(lidar_batch):
+        # float64 frames: labels from the kernels, depths gathered in float64, cast at the end like tools.py:30-33
+        frames = np.ascontiguousarray(lidar_batch[:, :, :, 0])
+        _, lbl, val, r = _labels_f64(frames, KITTI_SRC_THR, device)
+        if "index_error" in r:
+            raise IndexError(r["index_error"])                                                      # tools.py:26
+        out = np.stack([_gather_f64(frames[i], val[i], lbl[i]) for i in range(B)])
+        return out.reshape(B, _H, _W, 1).astype(np.float32)
     frames = _as_frames_f32(lidar_batch[:, :, :, 0], "DT_complete_batch")                           # tools.py:19
     # the result is a new array the caller owns (tools.py:27-33); its memory is page-locked and pooled so that the
     # device-to-host copy lands in it directly

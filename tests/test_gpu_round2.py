@@ -318,3 +318,36 @@ def test_sparse_upload_matches_dense_upload(handle):
     w2 = O.dt_fill(xd, src_thr=1.0)
     assert np.array_equal(r["dt"], w2["dt"]) and np.array_equal(r["depth"], w2["depth"])
     assert handle.transfer_bytes()[0] == xd.nbytes
+
+
+@pytest.mark.gpu
+def test_float64_and_integer_inputs_follow_the_reference(handle):
+    """tools.py:8 / :22 evaluate their predicates in the input's dtype and eval_NYU.Distance_Transform returns it
+    (:126-133): float64 (and integer) inputs go through the float64 route of the drop-ins -- predicates on the host in
+    float64, labels from the kernels, depths gathered from the float64 values -- and equal the line-by-line cv2 port of
+    the reference, including values that float32 would move across a threshold."""
+    cv2 = pytest.importorskip("cv2")
+    from distancetransform_depthcompletion_b200 import tools, eval_nyu
+    rng = np.random.default_rng(21)
+    x = np.zeros((2, 352, 1216, 1), np.float64)
+    m = rng.random(x.shape) < 0.05
+    x[m] = rng.uniform(1.0, 80.0, m.sum())
+    x[0, 200, 300, 0] = 0.9                          # float64: 1 - 0.9 = 0.09999999999999998 -> a source; not one in float32
+    x[0, 210, 310, 0] = 0.1 + 1e-12                  # valid in float64, equal to 0.1f after rounding
+    x[0, 220, 320, 0] = 0.5                          # valid, not a source: later labels read a shifted entry
+    want = O.cv2_port_complete_batch(x)
+    got = tools.DT_complete_batch(x)
+    assert got.dtype == np.float32 and got.shape == want.shape and np.array_equal(got, want)
+    dt_w, lbl_w = O.cv2_port_nearest_point(x[0, :, :, 0])
+    dt_g, lbl_g = tools.nearest_point(x[0, :, :, 0])
+    assert np.array_equal(dt_g, dt_w) and np.array_equal(lbl_g, lbl_w)
+    y = np.zeros((480, 640), np.float64)
+    ys, xs = rng.integers(6, 468, 500), rng.integers(8, 624, 500)
+    y[ys, xs] = rng.uniform(1.0, 10.0, 500)
+    w, _, _ = O.cv2_port_fill_frame(y, 0.001, 0.1, nyu_style=True)
+    g = eval_nyu.Distance_Transform(y)
+    assert g.dtype == np.float64 and np.array_equal(g, w)
+    yi = np.zeros((64, 96), np.int64); yi[10, 20] = 7; yi[40, 70] = 3
+    gi = eval_nyu.Distance_Transform(yi)
+    wi, _, _ = O.cv2_port_fill_frame(yi, 0.001, 0.1, nyu_style=True)
+    assert gi.dtype == yi.dtype and np.array_equal(gi, wi)

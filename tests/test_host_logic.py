@@ -16,8 +16,8 @@ def test_dt_complete_batch_shape_errors():
         tools.DT_complete_batch(np.ones((1, 100, 100, 1), np.float32))
     with pytest.raises(IndexError):                       # tools.py:19 indexes four axes
         tools.DT_complete_batch(np.ones((352, 1216), np.float32))
-    with pytest.raises(TypeError):
-        tools.DT_complete_batch(np.ones((1, 352, 1216, 1), np.float64))
+    with pytest.raises(TypeError):                        # float64 and integers take the float64 route; float16 has none
+        tools.DT_complete_batch(np.ones((1, 352, 1216, 1), np.float16))
 
 
 def test_nearest_point_and_distance_transform_shape_errors():
