@@ -1243,9 +1243,10 @@ int dtfill_metrics_ex(dtfill_t* h, const float* pred, const void* gt, int gt_is_
     double* sm_d = (out_is_device && sums) ? sums : (double*)h->sums.p;
     if (h->metrics_exact && npx < (1l << 31)) {
         // numpy's own summation order (k4x_*): per-pixel terms of the valid pixels compacted in raster order, then the
-        // pairwise tree of np.add.reduce; groups of frames share a scratch of at most ~1 GiB
+        // pairwise tree of np.add.reduce; groups of frames share a scratch of at most ~4 GiB (a batch of 256 KITTI frames
+        // with a float64 ground truth needs 3.5 GB: one group, every frame's tree in flight at once)
         const long maxl = npx / 64 + 2;
-        long G = (long)((1ull << 30) / ((size_t)4 * npx * gsz));
+        long G = (long)((1ull << 32) / ((size_t)4 * npx * gsz));
         G = G < 1 ? 1 : (G > B ? B : G);
         if ((rc = ensure(h, h->mx_terms, (size_t)G * 4 * npx * gsz))) return rc;
         if ((rc = ensure(h, h->mx_counts, (size_t)G * 4 * 4))) return rc;

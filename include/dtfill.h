@@ -131,7 +131,7 @@ int dtfill_metrics(dtfill_t* h, const float* pred, const void* gt, int gt_is_f64
 /* Summation order of dtfill_metrics / dtfill_metrics_ex.  1 (default; DTFILL_METRICS_EXACT=0 for the other): the per-pixel
  * terms of the valid pixels are compacted in raster order and summed in the order of numpy's pairwise add.reduce, in the
  * dtype numpy uses (float32 for a float32 ground truth, float64 for a float64 one), so every metric equals the
- * reference's bit for bit.  0: fixed-order float64 sums straight from the frames (one pass, ~18x faster): 1e-9 relative
+ * reference's bit for bit.  0: fixed-order float64 sums straight from the frames (one pass, ~5x faster): 1e-9 relative
  * for a float64 ground truth, ~1e-5 for a float32 one (numpy's own float32 rounding).  The fused sweep entry
  * dtfill_run_eval_async always uses the one-pass sums. */
 int dtfill_set_metrics_exact(dtfill_t* h, int enabled);
