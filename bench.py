@@ -560,7 +560,7 @@ def run_ours(args, rank, world, local_rank):
         # staging threads: the CPUs this rank may use, shared with the other ranks bound to the same NUMA node
         avail, total = len(os.sched_getaffinity(0)), os.cpu_count() or 1
         sharing = max(1, round(world * avail / total))
-        stage_threads = max(1, min(8, avail // sharing))
+        stage_threads = max(1, min(12, (3 * avail // 4) // sharing))
         _lib.get_handle(local_rank).set_stage_threads(stage_threads)
         for _ in range(3):                            # warm-up: staging mirrors, the pool of output buffers
             r4 = tools.DT_complete_batch(x4, device=local_rank)

@@ -1071,12 +1071,12 @@ int run_sync(dtfill_t* h, const void* in, int in_is_device, bool u16, int in_H, 
             if (pin_i || pin_d || pin_t || pin_l || pin_m || pin_x) {
                 if (!h->pool_in) {
                     int n = h->stage_threads;
-                    if (n < 0) {      // half of the CPUs this process may run on, 2..8
-                        cpu_set_t set;
+                    if (n < 0) {      // three quarters of the CPUs this process may run on, 2..12 (measured on a 16-CPU
+                        cpu_set_t set;    // box: 8 threads 25.5 k frames/s, 12 threads 26.4 k, 16 the same)
                         int avail = (int)std::thread::hardware_concurrency();
                         if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
-                        n = avail / 2;
-                        n = n < 2 ? 2 : (n > 8 ? 8 : n);
+                        n = 3 * avail / 4;
+                        n = n < 2 ? 2 : (n > 12 ? 12 : n);
                     }
                     h->pool_in = new CopyPool(n - 1);       // the calling thread works too
                     h->pool_out = new CopyPool(n - 1);

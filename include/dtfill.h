@@ -261,7 +261,7 @@ int dtfill_kernel_times(dtfill_t* h, float* ms);
 /* Pageable host buffers handed to dtfill_run / dtfill_run_u16 (what numpy allocates: the reference's contract,
  * tools.py:13-35) are staged through pinned mirrors owned by the handle: `threads` host threads per direction copy a
  * slice into / out of the mirror while the DMA engines move the previous slices and the kernels run, so a pageable
- * caller gets close to the PCIe limit.  -1 (default): hardware threads / 4, clamped to 2..8; 0: no staging (the
+ * caller gets close to the PCIe limit.  -1 (default): three quarters of the usable CPUs, clamped to 2..12; 0: no staging (the
  * driver stages the copies on the calling thread).  Buffers that are already pinned (dtfill_host_alloc,
  * cudaHostRegister) are copied directly in either case. */
 int dtfill_set_stage_threads(dtfill_t* h, int threads);
