@@ -83,6 +83,7 @@ def load() -> ctypes.CDLL:
         L.dtfill_dt_pool.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
         L.dtfill_dt_pool_ex.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.dtfill_outlier_removal.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci]
+        L.dtfill_dt_pool_demo.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, ci]
         L.dtfill_edt.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp, vp, ci]
         L.dtfill_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dtfill_host_free.argtypes = [vp]
@@ -93,7 +94,7 @@ def load() -> ctypes.CDLL:
                      "dtfill_kernel_times", "dtfill_metrics_ex", "dtfill_nccl_unique_id", "dtfill_comm_create",
                      "dtfill_comm_destroy", "dtfill_allreduce_sums", "dtfill_set_stage_threads", "dtfill_debug_set_skip",
                      "dtfill_run_eval_async", "dtfill_eval_totals", "dtfill_edt", "dtfill_set_sparse_upload",
-                     "dtfill_transfer_bytes", "dtfill_set_metrics_exact"):
+                     "dtfill_transfer_bytes", "dtfill_set_metrics_exact", "dtfill_dt_pool_demo"):
             getattr(L, name).restype = ci
         _lib = L
         return L
@@ -335,6 +336,13 @@ class Handle:
         _check(self._L.dtfill_dt_pool_ex(self._h, _ptr(data), _ptr(mask), 1, B, H, W, table_size, scale_num,
                                          _ptr(out_ptr), _ptr(masks_ptr), 1), "dtfill_dt_pool")
         return None
+
+    def dt_pool_demo(self, data: np.ndarray, B: int, H: int, W: int, table_size: int, scale_num: int) -> np.ndarray:
+        """demo.py:65-149 pooling levels 2..scale_num (before the division by scale_range): float32 [scale_num-1,B,H,W]."""
+        out = np.empty((max(scale_num - 1, 0), B, H, W), np.float32)
+        _check(self._L.dtfill_dt_pool_demo(self._h, _ptr(data), 0, B, H, W, int(table_size), int(scale_num), _ptr(out), 0),
+               "dtfill_dt_pool_demo")
+        return out
 
     def edt(self, frames: np.ndarray, src_thr: float, want_idx: bool = True):
         """Exact Euclidean feature transform (extension): frames float32 [B,H,W] -> (d2 int32, idx int32 or None)."""

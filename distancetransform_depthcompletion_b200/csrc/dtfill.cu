@@ -1463,6 +1463,56 @@ int dtfill_dt_pool_ex(dtfill_t* h, const float* data, const float* mask, int in_
     return 0;
 }
 
+int dtfill_dt_pool_demo(dtfill_t* h, const float* data, int in_is_device, int B, int H, int W, int table_size, int scale_num,
+                        float* out, int out_is_device) {
+    if (!h || !data) return fail(DTFILL_E_ARG, "dtfill_dt_pool_demo: NULL handle or data");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(DTFILL_E_ARG, "dtfill_dt_pool_demo: B, H, W must be positive");
+    if (table_size < 1 || (table_size & 1) == 0 || table_size > 2 * K5_MAXR + 1)
+        return fail(DTFILL_E_ARG, "dtfill_dt_pool_demo: table_size must be odd and <= 15");   // demo.py:66 assert
+    if (scale_num < 1 || scale_num > 4) return fail(DTFILL_E_ARG, "dtfill_dt_pool_demo: scale_num must be 1..4");
+    if (scale_num == 1) return 0;
+    if (!out) return fail(DTFILL_E_ARG, "dtfill_dt_pool_demo: NULL out");
+    CU(cudaSetDevice(h->device));
+    { int frc = dtfill_flush(h); if (frc) return frc; }
+    const size_t npx = (size_t)B * H * W;
+    const int nl = scale_num - 1;
+    cudaStream_t s = h->stream;
+    int rc;
+    const float* d_d = data; float* o_d = out;
+    if (!in_is_device) {
+        if ((rc = ensure(h, h->in_dev, npx * 4))) return rc;
+        CU(cudaMemcpyAsync(h->in_dev.p, data, npx * 4, cudaMemcpyHostToDevice, s));
+        d_d = (const float*)h->in_dev.p;
+    }
+    if (!out_is_device) {
+        if ((rc = ensure(h, h->depth_dev, npx * 4 * nl))) return rc;
+        o_d = (float*)h->depth_dev.p;
+    }
+    // demo.py:65-76: 10 ** (size - |i - middle| - |j - middle|) in float64, cast to float32
+    float w[(2 * K5_MAXR + 1) * (2 * K5_MAXR + 1)];
+    const int mid = (table_size - 1) / 2;
+    for (int i = 0; i < table_size; ++i)
+        for (int j = 0; j < table_size; ++j) {
+            double p = 1.0;
+            for (int k = 0; k < table_size - abs(i - mid) - abs(j - mid); ++k) p *= 10.0;      // exact in float64 (<= 1e15)
+            w[i * table_size + j] = (float)p;
+        }
+    if ((rc = ensure(h, h->sums, 1024))) return rc;
+    CU(cudaMemcpyAsync(h->sums.p, w, sizeof(float) * table_size * table_size, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));                     // w lives on this stack frame
+    dim3 grid((W + K5_TW - 1) / K5_TW, (H + K5_TH - 1) / K5_TH, B);
+    for (int l = 0; l < nl; ++l) {
+        const float* src = l == 0 ? d_d : o_d + (size_t)(l - 1) * npx;
+        k5_dt_pool_demo<<<grid, 256, 0, s>>>(src, (const float*)h->sums.p, H, W, table_size, o_d + (size_t)l * npx);
+    }
+    CU(cudaGetLastError());
+    if (!out_is_device) {
+        CU(cudaMemcpyAsync(out, o_d, npx * 4 * nl, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
 int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
                    int table_size, int scale_num, float* out, int out_is_device) {
     return dtfill_dt_pool_ex(h, data, mask, in_is_device, B, H, W, table_size, scale_num, out, nullptr, out_is_device);

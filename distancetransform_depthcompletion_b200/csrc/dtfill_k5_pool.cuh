@@ -324,4 +324,44 @@ __global__ void __launch_bounds__(256) k5_dt_pool_win(const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The older variant of the pooling that demo.py carries (demo.py:65-149): no mask; the weight of a window position is
+// 10 ** (T - |dy| - |dx|) (demo.py:65-76, float32) and the pixels selected are those whose VALUE TIMES WEIGHT equals
+// the window's maximum (demo.py:120-121), so a far pixel ten times deeper than a near one wins; the denominator counts
+// the selected pixels that are not zero (tf.math.count_nonzero, demo.py:122).  Zero padding takes part in the maximum
+// like tf.image.extract_patches(padding='SAME').  One thread per pixel, 32 x 8 tile + halo in shared memory, two sweeps
+// of the T x T window (maximum, then sum and count in row-major order).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k5_dt_pool_demo(const float* __restrict__ data, const float* __restrict__ weights /*[T*T]*/,
+                                                        int H, int W, int T, float* __restrict__ out)
+{
+    __shared__ float sd[K5_TH + 2 * K5_MAXR][K5_TW + 2 * K5_MAXR + 1];
+    __shared__ float sw[(2 * K5_MAXR + 1) * (2 * K5_MAXR + 1)];
+    const int R = T / 2;
+    const long fpx = (long)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * K5_TW, y0 = blockIdx.y * K5_TH;
+    const int tw = K5_TW + 2 * R, th = K5_TH + 2 * R;
+    for (int i = threadIdx.x; i < T * T; i += 256) sw[i] = weights[i];
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int ly = i / tw, lx = i - ly * tw;
+        const int gy = y0 + ly - R, gx = x0 + lx - R;
+        sd[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? data[fpx + (long)gy * W + gx] : 0.0f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+    float mx = -3.402823466e38f;
+    for (int dy = 0; dy < T; ++dy)
+        for (int dx = 0; dx < T; ++dx) mx = fmaxf(mx, __fmul_rn(sd[ty + dy][tx + dx], sw[dy * T + dx]));
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int dy = 0; dy < T; ++dy)
+        for (int dx = 0; dx < T; ++dx) {
+            const float v = sd[ty + dy][tx + dx];
+            if (__fmul_rn(v, sw[dy * T + dx]) == mx) { sum = __fadd_rn(sum, v); cnt += v != 0.0f; }
+        }
+    out[fpx + (long)gy * W + gx] = __fdiv_rn(sum, __fadd_rn(0.000001f, (float)cnt));
+}
+
 }  // namespace dtfill

@@ -72,3 +72,34 @@ def dt_pooling_masks(lidar_data, lidar_mask, table_size: int = 7, scale_num: int
     outs += [None] * (4 - len(outs))
     mks += [None] * (4 - len(mks))
     return tuple(outs), tuple(mks)
+
+
+def create_weight_matrix_demo(size: int = 11) -> np.ndarray:
+    """demo.py:65-76: weight 10 ** (size - |i - mid| - |j - mid|) per window position, flattened, float32."""
+    assert (size + 1) % 2 == 0                                               # demo.py:66
+    mid = (size - 1) // 2
+    i = np.abs(np.arange(size) - mid)
+    return (10.0 ** (size - i[:, None] - i[None, :])).reshape(-1).astype(np.float32)
+
+
+def generate_multi_channel_demo(lidar_data, table_size: int = 11, scale_range: float = 90.0, scale_num: int = 4,
+                                device: int | None = None):
+    """demo.py:107-149, the older pooling without a mask (value-weighted maximum, count_nonzero denominator).
+    lidar_data float32 [B,H,W,1] (or [B,H,W]); returns (lidar_1, .., lidar_4) / scale_range, [B,H,W], None beyond
+    scale_num, like the reference."""
+    d = np.asarray(lidar_data)
+    if d.dtype != np.float32:
+        raise TypeError("generate_multi_channel_demo: float32 array expected")
+    d3 = d[..., 0] if d.ndim == 4 else d
+    if d3.ndim != 3:
+        raise ValueError("generate_multi_channel_demo: expected [B,H,W,1] or [B,H,W]")
+    assert (table_size + 1) % 2 == 0                                         # demo.py:66
+    if not 1 <= scale_num <= 4:
+        raise ValueError("scale_num must be 1..4")
+    B, H, W = d3.shape
+    d3 = np.ascontiguousarray(d3)
+    levels = _lib.get_handle(device).dt_pool_demo(d3, B, H, W, table_size, scale_num)
+    sr = np.float32(scale_range)
+    outs = [d3 / sr] + [levels[k] / sr for k in range(scale_num - 1)]        # demo.py:141-148
+    outs += [None] * (4 - len(outs))
+    return tuple(outs)

@@ -192,6 +192,13 @@ int dtfill_dt_pool(dtfill_t* h, const float* data, const float* mask, int in_is_
 int dtfill_dt_pool_ex(dtfill_t* h, const float* data, const float* mask, int in_is_device, int B, int H, int W,
                       int table_size, int scale_num, float* out, uint8_t* out_masks, int out_is_device);
 
+/* The older variant of the pooling in demo.py:65-149 (no mask; weights 10 ** (T - |dy| - |dx|), demo.py:65-76; the selected
+ * pixels are those whose value times weight equals the window's maximum, demo.py:120-121; denominator
+ * 1e-6 + count_nonzero of the selected values, :122).  data float32 [B,H,W]; out float32 [scale_num - 1][B,H,W] = levels
+ * 2..scale_num before the division by scale_range (the Python mirror divides).  table_size odd, <= 15 (demo.py uses 11). */
+int dtfill_dt_pool_demo(dtfill_t* h, const float* data, int in_is_device, int B, int H, int W, int table_size,
+                        int scale_num, float* out, int out_is_device);
+
 /* KITTI outlier filter outlier_removal (data_read.py:103-128), the step just before the path: in, out float32
  * [B,H,W]; a depth more than 1.0 m farther than the average of the valid depths in its 7 x 7 diamond is zeroed. */
 int dtfill_outlier_removal(dtfill_t* h, const float* in, int in_is_device, int B, int H, int W, float* out,

@@ -259,6 +259,35 @@ def generate_multi_channel(lidar_data: np.ndarray, lidar_mask: np.ndarray, table
     return tuple(outs[:4])
 
 
+def demo_create_weight_matrix(size: int = 11) -> np.ndarray:
+    """demo.py:65-76."""
+    assert (size + 1) % 2 == 0
+    middle = (size - 1) / 2
+    w = np.zeros((size, size))
+    for i in range(size):
+        for j in range(size):
+            w[i, j] = 10 ** (size - abs(i - middle) - abs(j - middle))
+    return np.reshape(w, (size * size,)).astype(np.float32)
+
+
+def demo_generate_multi_channel(lidar_data: np.ndarray, table_size: int = 11, scale_range: float = 90.0, scale_num: int = 4):
+    """demo.py:107-149 for arrays [B,H,W] (numpy restatement of the TF lines; TensorFlow is absent: parity unpinned)."""
+    w = demo_create_weight_matrix(table_size)
+    d = lidar_data.astype(np.float32)
+    outs = [d / np.float32(scale_range)]
+    for _ in range(scale_num - 1):
+        ex = _extract_patches_same(d, table_size)                            # :119
+        prod = ex * w
+        mi = (prod == prod.max(axis=-1, keepdims=True)).astype(np.float32)   # :120
+        sel = ex * mi
+        d = (sel.sum(axis=-1) / (np.float32(0.000001) + np.count_nonzero(sel, axis=-1).astype(np.float32))).astype(np.float32)
+        outs.append(d / np.float32(scale_range))
+    while len(outs) < 4:
+        outs.append(None)
+    return tuple(outs[:4])
+
+
+
 # ---------------------------------------------------------------------------------------------------------
 # KITTI outlier filter (SURVEY.md section 8 f-2): data_read.py:103-128 with the real cv2.filter2D.
 # ---------------------------------------------------------------------------------------------------------

@@ -102,3 +102,31 @@ def test_gpu_full_size_and_errors():
         net_pool.generate_multi_channel(data.astype(np.float64), mask)
     with pytest.raises(ValueError):
         net_pool.generate_multi_channel(data, mask[:, :10])
+
+
+@pytest.mark.gpu
+def test_demo_variant_of_the_pooling(dtfill_lib):
+    """demo.py:65-149, the older pooling (weights 10 ** ..., value-weighted maximum, count_nonzero denominator), against
+    its numpy restatement in oracle/oracle.py (TensorFlow is absent here: this row is parity unpinned, like f-1).  A
+    single selected pixel (the rule, ties need equal value times weight) is reproduced exactly; sums of several agree to
+    float32 rounding."""
+    from distancetransform_depthcompletion_b200 import net_pool, synth
+    from oracle import oracle as O
+    assert np.array_equal(net_pool.create_weight_matrix_demo(11), O.demo_create_weight_matrix(11))
+    rng = np.random.default_rng(3)
+    frames = [synth.kitti_frame(0)[96:224, 300:620], synth.kitti_frame(1, beam_step=4)[200:328, 100:420]]
+    x = np.stack(frames).astype(np.float32)
+    x[1, 10:14, 10:14] = 7.5                                            # equal values: ties inside a window
+    for T, sn in ((11, 4), (7, 3), (3, 2)):
+        got = net_pool.generate_multi_channel_demo(x[..., None], table_size=T, scale_num=sn)
+        want = O.demo_generate_multi_channel(x, T, 90.0, sn)
+        for g, w in zip(got, want):
+            assert (g is None) == (w is None)
+            if g is not None:
+                assert g.shape == w.shape and g.dtype == np.float32
+                np.testing.assert_allclose(g, w, rtol=2e-6, atol=0)
+    r = rng.random((1, 33, 47)).astype(np.float32) * (rng.random((1, 33, 47)) < 0.3)     # odd sizes, borders
+    got = net_pool.generate_multi_channel_demo(r, table_size=5, scale_num=4)
+    want = O.demo_generate_multi_channel(r, 5, 90.0, 4)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=2e-6, atol=0)
