@@ -73,6 +73,8 @@ def load() -> ctypes.CDLL:
         L.dtfill_debug_set_skip.argtypes = [vp, ci]
         L.dtfill_set_stage_threads.argtypes = [vp, ci]
         L.dtfill_set_sparse_upload.argtypes = [vp, ci]
+        L.dtfill_debug_compact.argtypes = [vp, ctypes.c_long, cf, cf, vp, vp, ctypes.c_long]
+        L.dtfill_debug_compact.restype = ctypes.c_long
         L.dtfill_set_metrics_exact.argtypes = [vp, ci]
         L.dtfill_transfer_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.dtfill_set_pipeline_depth.argtypes = [vp, ci]

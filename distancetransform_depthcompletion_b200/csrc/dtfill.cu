@@ -1374,6 +1374,12 @@ int dtfill_set_stage_threads(dtfill_t* h, int threads) {
     return 0;
 }
 
+// Host-only hook for the CPU test-suite (no handle, no device): the compaction of the sparse upload on one block of pixels.
+long dtfill_debug_compact(const float* src, long n, float src_thr, float val_thr, uint32_t* idx, uint32_t* val, long cap) {
+    if (!src || !idx || !val || n < 0 || cap < n + 8) return -1;      // the packed stores need 8 entries of slack
+    return (long)compact_block(src, (size_t)n, 0u, source_cut(src_thr), val_thr, idx, val);
+}
+
 int dtfill_set_metrics_exact(dtfill_t* h, int enabled) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_set_metrics_exact: NULL handle");
     h->metrics_exact = enabled != 0;

@@ -91,3 +91,26 @@ def test_numpy_pairwise_sum_restated():
             s = numpy_pairwise_sum(a)
             assert s == np.add.reduce(a), (T.__name__, n)
             assert T(s / T(n)) == np.mean(a), (T.__name__, n)
+
+
+def test_sparse_upload_compaction_on_the_host():
+    """The host half of the sparse upload (csrc/dtfill.cu compact_block, AVX2 left-packing) needs no GPU: it must keep
+    exactly the pixels that are a source (tools.py:8, float32) or valid (tools.py:22), in order, with their bits."""
+    import ctypes
+    from distancetransform_depthcompletion_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(4)
+    for n, dens, thr in ((0, 0.0, 0.1), (5, 0.5, 0.1), (31, 0.3, 0.1), (32, 1.0, 0.1), (1000, 0.05, 0.1), (70001, 0.05, 0.001),
+                         (4096, 0.0, 0.1), (4099, 0.9, 0.1)):
+        x = np.zeros(n, np.float32)
+        m = rng.random(n) < dens
+        x[m] = rng.choice([0.05, 0.1, 0.5, 0.9, np.float32(0.90000004), 0.999, 1.0, 37.25, -3.0, np.nan, np.inf, 1e-41, -0.0], m.sum())
+        idx = np.zeros(n + 8, np.uint32); val = np.zeros(n + 8, np.uint32)
+        k = L.dtfill_debug_compact(x.ctypes.data, n, thr, 0.1, idx.ctypes.data, val.ctypes.data, n + 8)
+        with np.errstate(invalid="ignore"):
+            keep = ~((np.float32(1.0) - x) > np.float32(thr)) | (x > np.float32(0.1))
+        want = np.nonzero(keep)[0]
+        assert k == len(want), (n, dens, thr)
+        assert np.array_equal(idx[:k], want)
+        assert np.array_equal(val[:k], x.view(np.uint32)[want])
+    assert L.dtfill_debug_compact(x.ctypes.data, n, 0.1, 0.1, idx.ctypes.data, val.ctypes.data, n) == -1     # no slack
