@@ -114,3 +114,21 @@ def test_sparse_upload_compaction_on_the_host():
         assert np.array_equal(idx[:k], want)
         assert np.array_equal(val[:k], x.view(np.uint32)[want])
     assert L.dtfill_debug_compact(x.ctypes.data, n, 0.1, 0.1, idx.ctypes.data, val.ctypes.data, n) == -1     # no slack
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host alone and prints ONE JSON line with the keys the driver reads
+    (impl, metric, value, unit, cpu_baseline.kind/cores/sample, e2e with zero copy bytes); here it finds the reference
+    checkout when there is one and the cv2 port otherwise."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--batch", "4"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
