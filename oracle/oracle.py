@@ -206,8 +206,10 @@ def result_nyu(output: np.ndarray, target: np.ndarray) -> dict:
 
 # ---------------------------------------------------------------------------------------------------------
 # DT pooling of the CNN input stage: numpy RESTATEMENT of net.py:71-123.
-# TensorFlow is not installed in the build container, so this cannot be pinned against the reference run
-# live ("parity unpinned" for this row); it follows the reference lines one by one.
+# TensorFlow is not installed in the build container.  The pin is the reference's own lines, AST-extracted and run on a
+# numpy stand-in for the nine TensorFlow operations they call (tests/golden/tf_numpy_shim.py, make_golden.py): this
+# restatement reproduces their outputs bit for bit (tests/test_oracle_golden.py, tests/test_oracle_vs_reference.py).
+# TensorFlow's own kernels (the order of the <= T*T additions inside reduce_sum) stay unverified.
 # ---------------------------------------------------------------------------------------------------------
 def create_weight_matrix(table_size: int = 7) -> np.ndarray:
     """net.py:71-81: weight T - |i-mid| - |j-mid| of every window position, flattened, float32."""
@@ -271,7 +273,8 @@ def demo_create_weight_matrix(size: int = 11) -> np.ndarray:
 
 
 def demo_generate_multi_channel(lidar_data: np.ndarray, table_size: int = 11, scale_range: float = 90.0, scale_num: int = 4):
-    """demo.py:107-149 for arrays [B,H,W] (numpy restatement of the TF lines; TensorFlow is absent: parity unpinned)."""
+    """demo.py:107-149 for arrays [B,H,W] (numpy restatement of the TF lines; pinned like
+    generate_multi_channel to the reference lines run on tests/golden/tf_numpy_shim.py)."""
     w = demo_create_weight_matrix(table_size)
     d = lidar_data.astype(np.float32)
     outs = [d / np.float32(scale_range)]

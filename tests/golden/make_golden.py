@@ -3,10 +3,11 @@
 The reference (/root/reference, read-only) ships no tests or golden vectors, so the pin is its own output on
 seeded synthetic inputs:  solution_DeepNet/tools.py (imported with a stub `tensorflow` module and the `cv2` it
 forgot to import injected), the two functions of solution_DeepNet/eval_NYU.py:114-133 (AST-extracted, that
-script builds a TF model at import), evaluation.py's Result / Result_NYU, and live cv2 4.13.0.
+script builds a TF model at import), evaluation.py's Result / Result_NYU, live cv2 4.13.0, and the DT-pooling lines of net.py:71-123 / demo.py:65-149
+(AST-extracted, run on tests/golden/tf_numpy_shim.py: TensorFlow itself is absent).
 /root/reference does not exist on the GPU box, which is why the vectors are committed.
 
-    python tests/golden/make_golden.py        (from the repo root; needs /root/reference and cv2)
+    python tests/golden/make_golden.py [pool]   (from the repo root; needs /root/reference and cv2)
 """
 import ast
 import hashlib
@@ -38,8 +39,83 @@ def load_reference():
     return tools, evaluation, ns["nearest_point"], ns["Distance_Transform"], cv2
 
 
+def load_pooling_reference():
+    """The reference's own DT-pooling lines, AST-extracted and run on tf_numpy_shim (TensorFlow is absent here):
+    net.py:71-123 (methods create_weight_matrix / generate_multi_channel of the first model class) and
+    demo.py:65-76, :107-149.  Returns (net_pool(data, mask, table_size, scale_num), demo_pool(data, table_size,
+    scale_range, scale_num)); inputs and outputs carry the reference's shapes ([B,H,W,1] in, [B,H,W] levels out)."""
+    sys.path.insert(0, OUT)
+    import tf_numpy_shim as tf
+    ns = {"np": np, "tf": tf}
+    tree = ast.parse(open(os.path.join(REF, "solution_DeepNet", "net.py")).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef)
+               and any(isinstance(m, ast.FunctionDef) and m.name == "generate_multi_channel" for m in n.body))
+    for m in cls.body:
+        if isinstance(m, ast.FunctionDef) and m.name in ("create_weight_matrix", "generate_multi_channel"):
+            m.name = "net_" + m.name
+            exec(compile(ast.Module([m], []), "net.py", "exec"), ns)
+    dns = {"np": np, "tf": tf}
+    tree = ast.parse(open(os.path.join(REF, "solution_DeepNet", "demo.py")).read())
+    for n in tree.body:
+        if isinstance(n, ast.FunctionDef) and n.name in ("create_weight_matrix", "generate_multi_channel"):
+            exec(compile(ast.Module([n], []), "demo.py", "exec"), dns)
+
+    def net_pool(data, mask, table_size=7, scale_num=4):
+        me = types.SimpleNamespace(table_size=table_size, scale_num=scale_num)
+        me.create_weight_matrix = lambda: ns["net_create_weight_matrix"](me)
+        me.weights_matrix = me.create_weight_matrix()                     # net.py:34
+        return ns["net_generate_multi_channel"](me, data, mask)
+
+    def demo_pool(data, table_size=11, scale_range=90.0, scale_num=4):
+        return dns["generate_multi_channel"](data, table_size, scale_range=scale_range, scale_num=scale_num)
+
+    net_pool.create_weight_matrix = lambda t: ns["net_create_weight_matrix"](types.SimpleNamespace(table_size=t))
+    demo_pool.create_weight_matrix = dns["create_weight_matrix"]
+    return net_pool, demo_pool
+
+
+def pool_cases():
+    """Inputs of the DT-pooling fixtures: name -> (raw depth [B,H,W] float32, table_size, scale_num)."""
+    from distancetransform_depthcompletion_b200 import synth
+    rng = np.random.default_rng(77)
+    a = np.stack([synth.kitti_frame(5)[120:184, 200:360], synth.kitti_frame(6, beam_step=4)[120:184, 200:360]])
+    b = np.stack([((rng.random((48, 96)) < 0.03) * rng.uniform(1, 80, (48, 96))).astype(np.float32),
+                  np.zeros((48, 96), np.float32)])
+    c = synth.nyu_frame(2)[None, 100:150, 200:283]                      # odd width
+    return {"kitti_t7_s4": (a, 7, 4), "kitti_t5_s3": (a, 5, 3), "kitti_t3_s4": (a, 3, 4), "kitti_t9_s3": (a, 9, 3),
+            "random_t7_s4": (b, 7, 4), "random_t11_s3": (b, 11, 3), "nyu_t7_s2": (c, 7, 2)}
+
+
+def pool_inputs(x):
+    """net.py:464-467, :486: validity mask x > 0.1, data x / 90 * mask, both float32 [B,H,W,1]."""
+    x4 = x[..., None].astype(np.float32)
+    mask = (x4 > 0.1).astype(np.float32)
+    return (x4 / np.float32(90.0) * mask).astype(np.float32), mask
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def write_pool_golden():
+    # DT pooling (net.py:83-123, demo.py:107-149): the reference lines on the numpy stand-in for TensorFlow
+    net_pool, demo_pool = load_pooling_reference()
+    pool = {}
+    for name, (x, t, s) in pool_cases().items():
+        data, mask = pool_inputs(x)
+        lv = net_pool(data, mask, t, s)
+        assert lv[0] is data and all(v is None for v in lv[s:])
+        for k in range(1, s):
+            pool[f"net/{name}/l{k + 1}"] = np.asarray(lv[k], np.float32)
+        if t in (7, 11):
+            # demo.py:108 unpacks np.shape(np.squeeze(lidar_data)) into two names: one frame per call
+            dl = [demo_pool(x[i:i + 1, :, :, None].astype(np.float32), t, 90.0, s) for i in range(len(x))]
+            for k in range(s):
+                pool[f"demo/{name}/l{k + 1}"] = np.concatenate([np.asarray(d[k], np.float32) for d in dl])
+    for t in (3, 7, 11):
+        pool[f"weights/net_t{t}"] = net_pool.create_weight_matrix(t)
+        pool[f"weights/demo_t{t}"] = demo_pool.create_weight_matrix(t)
+    np.savez_compressed(os.path.join(OUT, "dt_pool.npz"), **pool)
 
 
 def main():
@@ -123,10 +199,14 @@ def main():
         R.evaluate(fill, g)
         met[f"nyu_s{seed}"] = np.array([R.mse, R.rmse, R.mae, R.irmse, R.imae, R.delta1, R.delta2, R.delta3])
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **met)
+    write_pool_golden()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["pool"]:          # only dt_pool.npz (the other fixtures stay byte-identical in git)
+        write_pool_golden()
+    else:
+        main()

@@ -1,5 +1,11 @@
-"""DT pooling of the CNN input stage (net.py:71-123).  TensorFlow is absent, so the oracle is
-a numpy RESTATEMENT of the reference lines (oracle.generate_multi_channel) -- parity unpinned for this row."""
+"""DT pooling of the CNN input stage (net.py:71-123).  TensorFlow is absent, so the pin is
+the reference's own lines (AST-extracted) run on a numpy stand-in for the nine TensorFlow operations they call
+(tests/golden/tf_numpy_shim.py): their outputs are committed as tests/golden/dt_pool.npz, the numpy restatement
+oracle.generate_multi_channel reproduces them bit for bit (tests/test_oracle_golden.py), and the kernels are compared
+with both.  What stays unverifiable here is TensorFlow's own summation order inside reduce_sum (2e-6 relative)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -130,3 +136,30 @@ def test_demo_variant_of_the_pooling(dtfill_lib):
     want = O.demo_generate_multi_channel(r, 5, 90.0, 4)
     for g, w in zip(got, want):
         np.testing.assert_allclose(g, w, rtol=2e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_reference_lines_fixture(golden_dir):
+    """The kernels against tests/golden/dt_pool.npz = outputs of net.py:83-123 / demo.py:107-149 themselves (run on the
+    numpy stand-in for TensorFlow, see the module docstring)."""
+    sys.path.insert(0, golden_dir)
+    import make_golden
+    z = np.load(os.path.join(golden_dir, "dt_pool.npz"))
+    for t in (3, 7, 11):
+        assert np.array_equal(net_pool.create_weight_matrix(t), z[f"weights/net_t{t}"])
+        assert np.array_equal(net_pool.create_weight_matrix_demo(t), z[f"weights/demo_t{t}"])
+    n = 0
+    for name, (x, t, s) in make_golden.pool_cases().items():
+        data, mask = make_golden.pool_inputs(x)
+        got = net_pool.generate_multi_channel(data, mask, table_size=t, scale_num=s)
+        for k in range(1, s):
+            want = z[f"net/{name}/l{k + 1}"]
+            np.testing.assert_allclose(got[k], want, rtol=2e-6, atol=1e-9, err_msg=f"{name} level {k + 1}")
+            assert np.array_equal(got[k] > 0.001, want > 0.001)
+            n += 1
+        if f"demo/{name}/l1" in z.files:
+            dg = net_pool.generate_multi_channel_demo(x[..., None].astype(np.float32), table_size=t, scale_num=s)
+            for k in range(s):
+                np.testing.assert_allclose(dg[k], z[f"demo/{name}/l{k + 1}"], rtol=2e-6, atol=0, err_msg=f"demo {name} {k + 1}")
+                n += 1
+    assert n >= 25

@@ -84,3 +84,34 @@ def test_index_errors():
     x[4, 4] = 0.5               # valid, not a source: one source, one valid -> fine
     r = O.dt_fill(x)
     assert np.all(r["depth"] == np.float32(0.5))
+
+
+def _pool_cases():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    return make_golden.pool_cases(), make_golden.pool_inputs
+
+
+def test_dt_pooling_restatement_equals_the_reference_lines(golden_dir):
+    """f-1: tests/golden/dt_pool.npz holds the outputs of net.py:83-123 / demo.py:107-149 THEMSELVES (AST-extracted,
+    run on tests/golden/tf_numpy_shim.py because TensorFlow is absent); the numpy restatement in oracle/oracle.py must
+    reproduce them bit for bit (both sum a window's float32 terms in numpy's order)."""
+    z = np.load(os.path.join(golden_dir, "dt_pool.npz"))
+    cases, pool_inputs = _pool_cases()
+    for t in (3, 7, 11):
+        assert np.array_equal(O.create_weight_matrix(t), z[f"weights/net_t{t}"])
+        assert np.array_equal(O.demo_create_weight_matrix(t), z[f"weights/demo_t{t}"])
+    n = 0
+    for name, (x, t, s) in cases.items():
+        data, mask = pool_inputs(x)
+        lv = O.generate_multi_channel(data[..., 0], mask[..., 0], t, s)
+        for k in range(1, s):
+            assert np.array_equal(lv[k], z[f"net/{name}/l{k + 1}"]), (name, k)
+            n += 1
+        if f"demo/{name}/l1" in z.files:
+            dl = O.demo_generate_multi_channel(x.astype(np.float32), t, 90.0, s)
+            for k in range(s):
+                assert np.array_equal(dl[k], z[f"demo/{name}/l{k + 1}"]), (name, k)
+                n += 1
+    assert n >= 25
