@@ -268,8 +268,7 @@ class Handle:
         _check(self._L.dtfill_debug_set_skip(self._h, int(mask)), "dtfill_debug_set_skip")
 
     def set_sky_min(self, rows: int):
-        """Least number of source-free top rows handed to the closed-form kernel k3_sky; 0: never; -1 (default):
-        8 in pipelined mode, never in strict order."""
+        """Least number of source-free top rows handed to the closed-form kernel k3_sky; 0: never; -1 (default): 8."""
         _check(self._L.dtfill_set_sky_min(self._h, int(rows)), "dtfill_set_sky_min")
 
     def set_stage_threads(self, threads: int):
