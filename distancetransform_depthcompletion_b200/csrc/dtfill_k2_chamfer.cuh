@@ -207,9 +207,35 @@ __device__ __forceinline__ void decode_row_bits(const RowBits& r, int x0, typena
 #ifndef DTFILL_FLUSH_LATE
 #define DTFILL_FLUSH_LATE 0     // where a step stores the depths gathered by the previous one: 0 at its start, 1 after the
 #endif                          // stencil, 2 after the scan (the gather's latency is then covered by the whole step)
+#ifndef DTFILL_K2_SMEMROW
+#define DTFILL_K2_SMEMROW 0     // 1 (PPL = 20 only): the row two steps back (y-2 / y+2) lives in shared memory in column
+#endif                          // order (a ring of two rows that doubles as the output transposition buffer) instead of
+                                // 24 registers; the neighbours' columns are then plain loads
 #ifndef DTFILL_K2_WARPS
-#define DTFILL_K2_WARPS 20      // resident warps per SM the PPL = 20 instance is compiled for (register budget)
+#define DTFILL_K2_WARPS (DTFILL_K2_SMEMROW ? 28 : 20)      // resident warps per SM the PPL = 20 instance is compiled for (register budget)
 #endif
+
+// row of a tile in shared memory, column order: lane l owns columns [l*PPL, (l+1)*PPL); v[] by 128-bit accesses
+// (80-byte lane stride: conflict-free per quarter warp), the two neighbouring columns by 32-bit loads
+template <int PPL>
+__device__ __forceinline__ void load_row_smem(Row<PPL>& r, const uint32_t* row, int lane, uint32_t init_key) {
+    const uint4* p = reinterpret_cast<const uint4*>(row + lane * PPL);
+#pragma unroll
+    for (int j = 0; j < PPL / 4; ++j) {
+        const uint4 q = p[j];
+        r.v[4 * j] = q.x; r.v[4 * j + 1] = q.y; r.v[4 * j + 2] = q.z; r.v[4 * j + 3] = q.w;
+    }
+    const uint32_t a = row[lane == 0 ? 0 : lane * PPL - 1], c = row[lane == 31 ? 0 : lane * PPL + PPL];
+    r.l1 = lane == 0 ? init_key : a;
+    r.r0 = lane == 31 ? init_key : c;
+    r.l2 = r.r1 = init_key;       // never read for the row two steps back
+}
+template <int PPL>
+__device__ __forceinline__ void store_row_smem(uint32_t* row, const Row<PPL>& r, int lane) {
+    uint4* p = reinterpret_cast<uint4*>(row + lane * PPL);
+#pragma unroll
+    for (int j = 0; j < PPL / 4; ++j) p[j] = make_uint4(r.v[4 * j], r.v[4 * j + 1], r.v[4 * j + 2], r.v[4 * j + 3]);
+}
 
 template <int PPL>
 __device__ __forceinline__ uint32_t stencil_fwd(const Row<PPL>& A /*row y-1*/, const Row<PPL>& Bq /*row y-2*/, int i, uint32_t one)
@@ -288,7 +314,9 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
 {
     // Transposition buffer for the keys of an output row.  Keeping shared memory small matters: what is left of the
     // 228 KB is the L1 that serves the depth_list gather.
-    __shared__ __align__(16) uint32_t stage[32 * PPL];
+    constexpr bool SB = DTFILL_K2_SMEMROW && PPL == 20;
+    __shared__ __align__(16) uint32_t stage_ring[(SB ? 2 : 1) * 32 * PPL];   // SB: rows y and y -/+ 1 of the tile, slot = y & 1
+    uint32_t* stage = stage_ring;
     __shared__ __align__(16) uint2 fwdbuf[16 * PPL];      // forward keys of the next row to scan, [j][lane]
 #if DTFILL_K2_TMA
     __shared__ __align__(8) uint64_t fwdbar;              // completion of the bulk copy into fwdbuf
@@ -410,10 +438,26 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
 
     // one copy of the step in the instruction stream (the unrolled step is ~13 KB of code); the two live rows
     // are rotated with register moves, which go to the otherwise idle FMA pipe
+    if (SB) {
+        store_row_smem<PPL>(stage_ring, ra, lane);
+        store_row_smem<PPL>(stage_ring + 32 * PPL, ra, lane);
+        __syncwarp();
+#pragma unroll 1
+        for (int y = task.fstart; y < task.hi; ++y) {
+            uint32_t* slot = stage_ring + (y & 1) * (32 * PPL);      // holds row y-2, receives row y
+            load_row_smem<PPL>(rb, slot, lane, init_key);
+            fwd_step(ra, rb, y);
+            __syncwarp();                                            // every lane has read its neighbours' columns of row y-2
+            store_row_smem<PPL>(slot, rb, lane);
+            ra = rb;
+        }
+        __syncwarp();
+    } else {
 #pragma unroll 1
     for (int y = task.fstart; y < task.hi; ++y) {
         fwd_step(ra, rb, y);
         const Row<PPL> t = ra; ra = rb; rb = t;
+    }
     }
 
     // ---------------- backward pass: rows hi-1 .. r0 ----------------
@@ -422,6 +466,11 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
     // LDGSTS cost 8 LSU cycles each and 20-38 of them per row step saturate the LSU -- measured.)
     fill_row(ra, init_key);
     fill_row(rb, init_key);
+    if (SB) {
+        store_row_smem<PPL>(stage_ring, ra, lane);
+        store_row_smem<PPL>(stage_ring + 32 * PPL, ra, lane);
+        __syncwarp();
+    }
     const float* dl = ws.dlist + fpx;
     const uint64_t pol_dlist = l2_policy_keep();
     const char* dlm1_bytes = reinterpret_cast<const char*>(dl - 1);       // depth_list[lbl - 1]
@@ -435,8 +484,8 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         if (lc < 32 * PPL && col >= task.c0 && col < task.c1) okmask |= 1u << j;
     }
     const long colbase = fpx + task.clo + lane * 4;
-    const uint4* sread = reinterpret_cast<const uint4*>(&stage[lane * 4]);
-    uint2* swrite = reinterpret_cast<uint2*>(&stage[xl]);
+    const uint4* sread0 = reinterpret_cast<const uint4*>(&stage[lane * 4]);
+    uint2* swrite0 = reinterpret_cast<uint2*>(&stage[xl]);
     const uint32_t fwdbuf_lane = (uint32_t)__cvta_generic_to_shared(fwdbuf) + lane * (4 * VW);
 
 #if DTFILL_K2_TMA
@@ -585,10 +634,20 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
         // ---- output of row y: keys -> shared memory (transpose), then per lane 4 consecutive pixels per group:
         // dt / lbl stores and the gather depth_list[lbl-1] (tools.py:26).  In this layout neighbouring lanes ask
         // for neighbouring labels (consecutive ranks along a beam), so a gather instruction touches few lines.
-        if (y >= task.r0 && y < task.r1) {
-#pragma unroll
-            for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+        const int slot_off = SB ? (y & 1) * (32 * PPL) : 0;     // SB: the row goes to its slot of the ring in any case
+        const uint4* sread = sread0 + slot_off / 4;
+        uint2* swrite = swrite0 + slot_off / 2;
+        stage = stage_ring + slot_off;
+        if (SB) {
+            store_row_smem<PPL>(stage, Bq, lane);
             __syncwarp();
+        }
+        if (y >= task.r0 && y < task.r1) {
+            if (!SB) {
+#pragma unroll
+                for (int j = 0; j < PPL / 2; ++j) swrite[j] = make_uint2(Bq.v[2 * j], Bq.v[2 * j + 1]);
+                __syncwarp();
+            }
             const long ro = (long)y * W;
             if (VEC) {
                 float* pdt = out_dt + colbase + ro;
@@ -634,14 +693,23 @@ __global__ void __launch_bounds__(32, (PPL >= 38 ? 12 : (PPL >= 20 ? DTFILL_K2_W
                     }
                 }
             }
-            __syncwarp();                            // stage is free for the next row
+            if (!SB) __syncwarp();                   // stage is free for the next row
         }
     };
 
+    if (SB) {
+#pragma unroll 1
+        for (int y = task.hi - 1; y >= task.r0; --y) {
+            load_row_smem<PPL>(rb, stage_ring + (y & 1) * (32 * PPL), lane, init_key);      // row y+2
+            bwd_step(ra, rb, y);
+            ra = rb;
+        }
+    } else {
 #pragma unroll 1
     for (int y = task.hi - 1; y >= task.r0; --y) {
         bwd_step(ra, rb, y);
         const Row<PPL> t = ra; ra = rb; rb = t;
+    }
     }
     wait_fwd_row();
     if (VEC) flush_depth_row(task.r0);
