@@ -142,11 +142,59 @@ __attribute__((target("avx2,popcnt"))) static size_t compact_block_avx2(const fl
     }
     return k;
 }
+// AVX-512: the two predicates of 16 pixels are mask registers, 64 pixels without a hit cost four loads, eight compares and
+// one test; the kept lanes are packed by VCOMPRESSPS / VPCOMPRESSD in registers (the register form is fast on every
+// AVX-512 core, the memory form is microcoded on some) and all 16 lanes are stored (idx / val need 16 entries of slack)
+#define DTFILL_AVX512 __attribute__((target("avx512f,popcnt"), always_inline)) static inline
+DTFILL_AVX512 __mmask16 keep16_avx512(const __m512 x, const __m512 vs, const __m512 vv) {
+    return (__mmask16)(_mm512_cmp_ps_mask(x, vs, _CMP_NLT_UQ) | _mm512_cmp_ps_mask(x, vv, _CMP_GT_OQ));
+}
+DTFILL_AVX512 size_t emit16_avx512(const __m512 x, const __mmask16 m, const uint32_t first, uint32_t* idx, uint32_t* val, size_t k) {
+    const __m512i iota = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    _mm512_storeu_ps((float*)(val + k), _mm512_maskz_compress_ps(m, x));
+    _mm512_storeu_si512((void*)(idx + k), _mm512_maskz_compress_epi32(m, _mm512_add_epi32(_mm512_set1_epi32((int)first), iota)));
+    return k + (size_t)__builtin_popcount((unsigned)m);
+}
+__attribute__((target("avx512f,popcnt"))) static size_t compact_block_avx512(const float* src, size_t n, uint32_t base, float scut,
+                                                                             float vthr, uint32_t* idx, uint32_t* val) {
+    const __m512 vs = _mm512_set1_ps(scut), vv = _mm512_set1_ps(vthr);
+    size_t k = 0, i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m512 x0 = _mm512_loadu_ps(src + i), x1 = _mm512_loadu_ps(src + i + 16);
+        const __m512 x2 = _mm512_loadu_ps(src + i + 32), x3 = _mm512_loadu_ps(src + i + 48);
+        const __mmask16 m0 = keep16_avx512(x0, vs, vv), m1 = keep16_avx512(x1, vs, vv);
+        const __mmask16 m2 = keep16_avx512(x2, vs, vv), m3 = keep16_avx512(x3, vs, vv);
+        if (!((unsigned)m0 | (unsigned)m1 | (unsigned)m2 | (unsigned)m3)) continue;
+        if (m0) k = emit16_avx512(x0, m0, base + (uint32_t)i, idx, val, k);
+        if (m1) k = emit16_avx512(x1, m1, base + (uint32_t)i + 16, idx, val, k);
+        if (m2) k = emit16_avx512(x2, m2, base + (uint32_t)i + 32, idx, val, k);
+        if (m3) k = emit16_avx512(x3, m3, base + (uint32_t)i + 48, idx, val, k);
+    }
+    for (; i + 16 <= n; i += 16) {
+        const __m512 x = _mm512_loadu_ps(src + i);
+        const __mmask16 m = keep16_avx512(x, vs, vv);
+        if (m) k = emit16_avx512(x, m, base + (uint32_t)i, idx, val, k);
+    }
+    for (; i < n; ++i) {
+        const float x = src[i];
+        if (!(x < scut) || x > vthr) { memcpy(val + k, &x, 4); idx[k] = base + (uint32_t)i; ++k; }
+    }
+    return k;
+}
 #endif
+constexpr size_t COMPACT_SLACK = 16;      // entries the packed stores may write beyond the pairs they keep
 static size_t compact_block(const float* src, size_t n, uint32_t base, float scut, float vthr, uint32_t* idx, uint32_t* val) {
 #if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
-    if (avx2) return compact_block_avx2(src, n, base, scut, vthr, idx, val);
+    // DTFILL_COMPACT_ISA=avx2|scalar (tuning / tests) keeps the wider paths off
+    static const int isa = [] {
+        const char* e = getenv("DTFILL_COMPACT_ISA");
+        const int limit = !e ? 3 : (!strcmp(e, "scalar") ? 0 : (!strcmp(e, "avx2") ? 2 : 3));
+        if (limit >= 3 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("popcnt")) return 3;
+        if (limit >= 2 && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt")) return 2;
+        return 0;
+    }();
+    if (isa == 3) return compact_block_avx512(src, n, base, scut, vthr, idx, val);
+    if (isa == 2) return compact_block_avx2(src, n, base, scut, vthr, idx, val);
 #endif
     size_t k = 0;
     for (size_t i = 0; i < n; ++i) {
@@ -198,9 +246,9 @@ public:
         parallel_for(nparts, [&](size_t i) {
             if (overflow.load(std::memory_order_relaxed)) return;
             thread_local std::vector<uint32_t> buf;
-            if (buf.size() < 2 * (block + 8)) buf.resize(2 * (block + 8));
+            if (buf.size() < 2 * (block + COMPACT_SLACK)) buf.resize(2 * (block + COMPACT_SLACK));
             uint32_t* bi = buf.data();
-            uint32_t* bv = buf.data() + block + 8;
+            uint32_t* bv = buf.data() + block + COMPACT_SLACK;
             const size_t a = i * block, len = std::min(block, n - a);
             const size_t k = compact_block(src + a, len, (uint32_t)a, scut, vthr, bi, bv);
             const size_t off = cursor.fetch_add(k);
@@ -1377,7 +1425,7 @@ int dtfill_set_stage_threads(dtfill_t* h, int threads) {
 
 // Host-only hook for the CPU test-suite (no handle, no device): the compaction of the sparse upload on one block of pixels.
 long dtfill_debug_compact(const float* src, long n, float src_thr, float val_thr, uint32_t* idx, uint32_t* val, long cap) {
-    if (!src || !idx || !val || n < 0 || cap < n + 8) return -1;      // the packed stores need 8 entries of slack
+    if (!src || !idx || !val || n < 0 || cap < n + (long)COMPACT_SLACK) return -1;      // the packed stores need slack
     return (long)compact_block(src, (size_t)n, 0u, source_cut(src_thr), val_thr, idx, val);
 }
 

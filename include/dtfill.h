@@ -284,7 +284,7 @@ int dtfill_set_sparse_upload(dtfill_t* h, int enabled);
 int dtfill_transfer_bytes(dtfill_t* h, unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 /* Host-only test hook (needs neither a handle nor a GPU): the compaction of the sparse upload on src[0..n): indices and
  * value bits of the pixels that are a source or valid for the given thresholds, in order; returns their number, or -1 on
- * bad arguments (cap >= n + 8 entries are needed in idx and val). */
+ * bad arguments (cap >= n + 16 entries are needed in idx and val: the packed stores write whole vectors). */
 long dtfill_debug_compact(const float* src, long n, float src_thr, float val_thr, uint32_t* idx, uint32_t* val, long cap);
 
 /* Pinned host memory for fast host<->device copies (cudaHostAlloc / cudaFreeHost). */

@@ -93,20 +93,18 @@ def test_numpy_pairwise_sum_restated():
             assert T(s / T(n)) == np.mean(a), (T.__name__, n)
 
 
-def test_sparse_upload_compaction_on_the_host():
-    """The host half of the sparse upload (csrc/dtfill.cu compact_block, AVX2 left-packing) needs no GPU: it must keep
-    exactly the pixels that are a source (tools.py:8, float32) or valid (tools.py:22), in order, with their bits."""
-    import ctypes
+def _check_compaction():
+    import ctypes  # noqa: F401
     from distancetransform_depthcompletion_b200 import _lib
     L = _lib.load()
     rng = np.random.default_rng(4)
-    for n, dens, thr in ((0, 0.0, 0.1), (5, 0.5, 0.1), (31, 0.3, 0.1), (32, 1.0, 0.1), (1000, 0.05, 0.1), (70001, 0.05, 0.001),
-                         (4096, 0.0, 0.1), (4099, 0.9, 0.1)):
+    for n, dens, thr in ((0, 0.0, 0.1), (5, 0.5, 0.1), (31, 0.3, 0.1), (32, 1.0, 0.1), (63, 0.2, 0.1), (64, 0.02, 0.1), (81, 1.0, 0.1),
+                         (1000, 0.05, 0.1), (70001, 0.05, 0.001), (4096, 0.0, 0.1), (4099, 0.9, 0.1)):
         x = np.zeros(n, np.float32)
         m = rng.random(n) < dens
         x[m] = rng.choice([0.05, 0.1, 0.5, 0.9, np.float32(0.90000004), 0.999, 1.0, 37.25, -3.0, np.nan, np.inf, 1e-41, -0.0], m.sum())
-        idx = np.zeros(n + 8, np.uint32); val = np.zeros(n + 8, np.uint32)
-        k = L.dtfill_debug_compact(x.ctypes.data, n, thr, 0.1, idx.ctypes.data, val.ctypes.data, n + 8)
+        idx = np.zeros(n + 16, np.uint32); val = np.zeros(n + 16, np.uint32)
+        k = L.dtfill_debug_compact(x.ctypes.data, n, thr, 0.1, idx.ctypes.data, val.ctypes.data, n + 16)
         with np.errstate(invalid="ignore"):
             keep = ~((np.float32(1.0) - x) > np.float32(thr)) | (x > np.float32(0.1))
         want = np.nonzero(keep)[0]
@@ -114,6 +112,20 @@ def test_sparse_upload_compaction_on_the_host():
         assert np.array_equal(idx[:k], want)
         assert np.array_equal(val[:k], x.view(np.uint32)[want])
     assert L.dtfill_debug_compact(x.ctypes.data, n, 0.1, 0.1, idx.ctypes.data, val.ctypes.data, n) == -1     # no slack
+
+
+@pytest.mark.parametrize("isa", ["", "avx2", "scalar"])
+def test_sparse_upload_compaction_on_the_host(isa):
+    """The host half of the sparse upload (csrc/dtfill.cu compact_block: AVX-512 compress, AVX2 left-packing or scalar,
+    whichever the CPU has; DTFILL_COMPACT_ISA caps it, read once per process, hence the subprocess) needs no GPU: it
+    must keep exactly the pixels that are a source (tools.py:8, float32) or valid (tools.py:22), in order, with their bits."""
+    import subprocess
+    import sys
+    env = dict(os.environ, DTFILL_COMPACT_ISA=isa) if isa else {k: v for k, v in os.environ.items() if k != "DTFILL_COMPACT_ISA"}
+    code = "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_host_logic as t; t._check_compaction()" % (
+        ROOT, os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
 
 
 def test_bench_reference_arm_contract():
