@@ -113,7 +113,7 @@ def test_gpu_full_size_and_errors():
 @pytest.mark.gpu
 def test_demo_variant_of_the_pooling(dtfill_lib):
     """demo.py:65-149, the older pooling (weights 10 ** ..., value-weighted maximum, count_nonzero denominator), against
-    its numpy restatement in oracle/oracle.py (TensorFlow is absent here: this row is parity unpinned, like f-1).  A
+    its numpy restatement in oracle/oracle.py (pinned like f-1 to the reference's own lines run on tests/golden/tf_numpy_shim.py).  A
     single selected pixel (the rule, ties need equal value times weight) is reproduced exactly; sums of several agree to
     float32 rounding."""
     from distancetransform_depthcompletion_b200 import net_pool, synth
