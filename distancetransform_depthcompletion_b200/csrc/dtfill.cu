@@ -379,6 +379,8 @@ struct dtfill_ctx {
                                   // 0.137 ms, 16 frames 0.222 -> 0.165, 256 frames 0.551 -> 0.536; the launch costs
                                   // 2 % on frames without such rows, 256 NYU frames 0.603 -> 0.616)
     int nsub = -1;                // -1: automatic
+    bool narrow_main = true;      // the half-width scan instance on the call's own stream, the full-width one on the side
+                                  // stream (DTFILL_NARROW_MAIN=0: the other way round; strict step of 256 KITTI frames 0.536 -> 0.519)
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
     cudaEvent_t ev[DTFILL_NUM_KERNELS + 1] = {};
 };
@@ -613,33 +615,42 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
     const bool want_lbl = ol != nullptr;
-    // half-width tiles run on a side stream next to the full-width tasks (different kernel instances)
-    cudaStream_t s2 = s;
+    // half-width and full-width tiles are different kernel instances and run next to each other on two streams.  The
+    // instance that a frame of this shape normally uses stays on the call's own stream, so that the chain
+    // K1 -> K1b -> scan -> k3_sky does not cross streams twice (narrow_main; the other instance finds no task as a rule)
     const bool run_k2 = !(h->debug_skip & 4);
-    if (fp.narrow_ppl && run_k2) {
-        s2 = L->side[sub_index];
+    const bool two = fp.narrow_ppl && run_k2;
+    const bool narrow_main = two && h->narrow_main && !h->profiling;
+    cudaStream_t s_side = s;
+    if (two) {
+        s_side = L->side[sub_index];
         CU(cudaEventRecord(L->side_fork[sub_index], s));
-        CU(cudaStreamWaitEvent(s2, L->side_fork[sub_index], 0));
-        if (fp.narrow_ppl == 20) launch_k2<20>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
-        else launch_k2<10>(false, want_lbl, nb * MAXT, s2, fp, ws, od, odt, ol, TASK_NARROW);
+        CU(cudaStreamWaitEvent(s_side, L->side_fork[sub_index], 0));
+    }
+    cudaStream_t s_narrow = narrow_main ? s : s_side, s_full = narrow_main ? s_side : s;
+    if (two) {
+        if (fp.narrow_ppl == 20) launch_k2<20>(false, want_lbl, nb * MAXT, s_narrow, fp, ws, od, odt, ol, TASK_NARROW);
+        else launch_k2<10>(false, want_lbl, nb * MAXT, s_narrow, fp, ws, od, odt, ol, TASK_NARROW);
         ++*launches;
-        CU(cudaEventRecord(L->side_join[sub_index], s2));
     }
     if (run_k2) switch (plan.ppl) {
-        case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
-        case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
-        case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;
-        default: launch_k2<10>(true, want_lbl, nb * MAXT, s, fp, ws, od, odt, ol, TASK_CHAMFER); break;  // NOSRC only
+        case 10: launch_k2<10>(plan.pad, want_lbl, nb * MAXT, s_full, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        case 20: launch_k2<20>(plan.pad, want_lbl, nb * MAXT, s_full, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        case 38: launch_k2<38>(plan.pad, want_lbl, nb * MAXT, s_full, fp, ws, od, odt, ol, TASK_CHAMFER); break;
+        default: launch_k2<10>(true, want_lbl, nb * MAXT, s_full, fp, ws, od, odt, ol, TASK_CHAMFER); break;  // NOSRC only
     }
     if (run_k2) ++*launches;
     // 64-bit-key fallback: returns immediately for every task the fast kernels handle.  It touches other frames
     // than they do, so it runs next to the narrow tiles; only per-kernel profiling serialises it behind the join.
     const size_t wide_smem = (size_t)3 * (W + 4) * sizeof(uint64_t);
     if (!h->profiling && run_k2) {
-        k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
+        k2_chamfer_wide<<<nb, 32, wide_smem, s_full>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
-    if (fp.narrow_ppl && run_k2) CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
+    if (two) {
+        CU(cudaEventRecord(L->side_join[sub_index], s_side));
+        CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
+    }
     if (h->profiling) {
         CU(cudaEventRecord(h->ev[3], s));
         k2_chamfer_wide<<<nb, 32, wide_smem, s>>>(fp, ws, od, odt, ol);
@@ -948,6 +959,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_MAX_COL_TILES")) h->max_col_tiles = atoi(e);
     if (const char* e = getenv("DTFILL_SKY_MIN")) h->sky_min = atoi(e) < -1 ? -1 : atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
+    if (const char* e = getenv("DTFILL_NARROW_MAIN")) h->narrow_main = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_STAGE_THREADS")) h->stage_threads = atoi(e);
     if (const char* e = getenv("DTFILL_SPARSE_UPLOAD")) h->sparse_upload = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_METRICS_EXACT")) h->metrics_exact = atoi(e) != 0;
