@@ -303,7 +303,7 @@ struct PinBuf {
 // scan of the previous call.
 struct Lane {
     static const int MAX_SUB = 16;
-    Buf srcbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, status, sky, skykeys;
+    Buf srcbits, wprefix, rowcell, rowsrc, rowval, counts, dlist, scratch, tasks, sky, skykeys;
     Buf ev_partial, ev_per_frame, ev_totals;   // dtfill_run_eval_async: metric partial sums / per-frame metrics / running totals
     bool ev_dirty = false;                     // ev_totals holds sums not yet collected by dtfill_eval_totals
     cudaStream_t sub[MAX_SUB] = {};      // sub-batch streams (host buffers: slices pipeline the PCIe copies)
@@ -338,6 +338,21 @@ struct dtfill_ctx {
     bool slot_dirty[STATUS_RING] = {};
     cudaEvent_t slot_done[STATUS_RING] = {};
     int sticky_bad = INT_MAX;
+    // The device side of a slot: STATUS_STRIDE ints per slot in one allocation, {INT_MAX, 0, ...} from dtfill_create on.
+    // A call's kernels only ever change them for a bad frame or a 64-bit-key frame, so a slot whose host copy came back
+    // unchanged needs no re-arming before its next use, and the copy to the host is issued right behind
+    // k1b_scan_compact (the only writer) on a stream of its own: neither transfer sits between two calls' kernels
+    // (they cost ~8 us per call: one KITTI frame 0.135 -> see profiles/r02_experiments.txt).
+    static const int STATUS_STRIDE = 64;
+    int* status_dev = nullptr;        // device [STATUS_RING][STATUS_STRIDE]
+    bool slot_rearm[STATUS_RING] = {}; // the slot's device words left their initial state: re-arm before the next use
+    cudaStream_t status_stream = nullptr;
+    cudaEvent_t status_fork = nullptr;
+    int* cur_status = nullptr;        // device status words of the call being enqueued
+    int cur_slot = 0;
+    bool cur_status_early = false;    // this call copies its status words to the host right behind k1b_scan_compact
+    bool cur_status_copied = false;
+    int last_slot = 0;
     std::vector<void*> retired;       // device buffers replaced by larger ones; freed at the next synchronisation point
     size_t wide_smem_configured = 0;  // dynamic shared memory limit of k2_chamfer_wide raised so far on this device
     bool cur_pipelined = false;       // the call being enqueued runs on a lane's own stream
@@ -572,7 +587,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
     ws.dlist = (float*)L->dlist.p + npx0;
     ws.scratch = (uint32_t*)L->scratch.p + (size_t)b0 * scratch_units_per_frame * 32;
     ws.tasks = (Task*)L->tasks.p + (size_t)b0 * MAXT;
-    ws.status = (int*)L->status.p;
+    ws.status = h->cur_status;
     ws.sky = (int*)L->sky.p + b0;
     ws.skykeys = (uint32_t*)L->skykeys.p + (size_t)b0 * 2 * W;
     float* olid = h->lidar_dev ? h->lidar_dev + npx0 : nullptr;
@@ -611,6 +626,13 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
     if (!(h->debug_skip & 2)) {
         k1b_scan_compact<<<nb, K1B_THREADS, 0, s>>>(fp, ws, oc);
         ++*launches;
+        if (h->cur_status_early) {       // the status words are final: to the host on the status stream
+            CU(cudaEventRecord(h->status_fork, s));
+            CU(cudaStreamWaitEvent(h->status_stream, h->status_fork, 0));
+            CU(cudaMemcpyAsync(h->status_ring + 2 * h->cur_slot, h->cur_status, 8, cudaMemcpyDeviceToHost, h->status_stream));
+            CU(cudaEventRecord(h->slot_done[h->cur_slot], h->status_stream));
+            h->cur_status_copied = true;
+        }
     }
     if (h->profiling) CU(cudaEventRecord(h->ev[2], s));
 
@@ -700,7 +722,6 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     const int scratch_units_per_frame = plan.ppl ? 3 * H * plan.ppl : (int)(((size_t)H * W + 31) / 32);
     if ((rc = ensure(h, L->scratch, (size_t)B * scratch_units_per_frame * 128))) return rc;
     if ((rc = ensure(h, L->tasks, (size_t)B * MAXT * sizeof(Task)))) return rc;
-    if ((rc = ensure(h, L->status, 256))) return rc;
     if ((rc = ensure(h, L->sky, (size_t)B * 4))) return rc;
     if ((rc = ensure(h, L->skykeys, (size_t)B * 2 * W * 4))) return rc;
     {
@@ -741,9 +762,16 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     if (h->slot_dirty[slot]) {
         CU(cudaEventSynchronize(h->slot_done[slot]));
         if (h->status_ring[2 * slot] < h->sticky_bad) h->sticky_bad = h->status_ring[2 * slot];
+        if (h->status_ring[2 * slot] != INT_MAX || h->status_ring[2 * slot + 1] != 0) h->slot_rearm[slot] = true;
         h->slot_dirty[slot] = false;
     }
-    CU(cudaMemcpyAsync(L->status.p, h->status_init, 8, cudaMemcpyHostToDevice, s_front));
+    h->cur_slot = slot;
+    h->cur_status = h->status_dev + (size_t)slot * dtfill_ctx::STATUS_STRIDE;
+    if (h->slot_rearm[slot] || (h->debug_skip & 2)) {      // (a run without k1b_scan_compact reports nothing)
+        CU(cudaMemcpyAsync(h->cur_status, h->status_init, 8, cudaMemcpyHostToDevice, s_front));
+        h->slot_rearm[slot] = false;
+    }
+    h->cur_status_copied = false;
 
     // sub-batches on forked streams (skipped while per-kernel profiling is on: the event pairs need one stream)
     int nsub = h->nsub;
@@ -753,6 +781,7 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
     if (nsub > Lane::MAX_SUB) nsub = Lane::MAX_SUB;
     if (nsub > B) nsub = B;
     if (h->profiling || nsub < 1) nsub = 1;
+    h->cur_status_early = nsub == 1 && !(h->debug_skip & 2);     // slices share the words: their copy follows the last slice
     void* dense_pin = hio ? hio->in_pin : nullptr;      // pinned mirror of a pageable input (allocated late on the sparse path)
     auto copy_in = [&](cudaStream_t st, int b0, int nb) -> int {
         if (!hio) return 0;
@@ -888,9 +917,13 @@ int enqueue(dtfill_t* h, const void* in, int B, int H, int W, float src_thr, flo
         launches += 2;
         L->ev_dirty = true;
     }
-    CU(cudaMemcpyAsync(h->status_ring + 2 * slot, L->status.p, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(h->slot_done[slot], s));
+    if (!h->cur_status_copied) {
+        CU(cudaMemcpyAsync(h->status_ring + 2 * slot, h->cur_status, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(h->slot_done[slot], s));
+    }
+    h->cur_status_early = false;
     h->slot_dirty[slot] = true;
+    h->last_slot = slot;
     CU(cudaGetLastError());
     if (pipelined) {
         CU(cudaEventRecord(L->done, s));
@@ -937,6 +970,15 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     h->status_init[0] = INT_MAX;
     h->status_init[1] = 0;
     for (auto& e : h->slot_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        const size_t n = (size_t)dtfill_ctx::STATUS_RING * dtfill_ctx::STATUS_STRIDE;
+        std::vector<int> init(n, 0);
+        for (int i = 0; i < dtfill_ctx::STATUS_RING; ++i) init[(size_t)i * dtfill_ctx::STATUS_STRIDE] = INT_MAX;
+        CU(cudaMalloc((void**)&h->status_dev, n * sizeof(int)));
+        CU(cudaMemcpy(h->status_dev, init.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaStreamCreateWithFlags(&h->status_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->status_fork, cudaEventDisableTiming));
+    }
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // numerically lower = higher priority
     for (Lane& L : h->lanes) {
@@ -977,7 +1019,7 @@ void dtfill_destroy(dtfill_t* h) {
     cudaDeviceSynchronize();
     for (Lane& L : h->lanes) {
         Buf* lb[] = {&L.srcbits, &L.wprefix, &L.rowcell, &L.rowsrc, &L.rowval, &L.counts, &L.dlist,
-                     &L.scratch, &L.tasks, &L.status, &L.sky, &L.skykeys, &L.ev_partial, &L.ev_per_frame, &L.ev_totals};
+                     &L.scratch, &L.tasks, &L.sky, &L.skykeys, &L.ev_partial, &L.ev_per_frame, &L.ev_totals};
         for (Buf* b : lb)
             if (b->p) cudaFree(b->p);
         if (L.fork_ev) cudaEventDestroy(L.fork_ev);
@@ -1005,6 +1047,9 @@ void dtfill_destroy(dtfill_t* h) {
     for (PinBuf* b : {&h->pin_in, &h->pin_depth, &h->pin_dt, &h->pin_lbl, &h->pin_mask, &h->pin_lidar, &h->pin_sparse})
         if (b->p) cudaFreeHost(b->p);
     if (h->status_ring) cudaFreeHost(h->status_ring);
+    if (h->status_dev) cudaFree(h->status_dev);
+    if (h->status_stream) cudaStreamDestroy(h->status_stream);
+    if (h->status_fork) cudaEventDestroy(h->status_fork);
     for (auto& e : h->slot_done)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->ev)
@@ -1065,6 +1110,7 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
     if (!h) return fail(DTFILL_E_ARG, "dtfill_status: NULL handle");
     int rc = dtfill_synchronize(h);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(h->status_stream));
     if (kernel_launches) *kernel_launches = h->lanes[h->last_lane].last_launches;
     // calls examined: every one since the previous dtfill_status (each has its own slot of the status ring)
     int bad = h->sticky_bad;
@@ -1072,6 +1118,7 @@ int dtfill_status(dtfill_t* h, int* first_bad_frame, int* kernel_launches) {
     for (int i = 0; i < dtfill_ctx::STATUS_RING; ++i)
         if (h->slot_dirty[i]) {
             if (h->status_ring[2 * i] < bad) bad = h->status_ring[2 * i];
+            if (h->status_ring[2 * i] != INT_MAX || h->status_ring[2 * i + 1] != 0) h->slot_rearm[i] = true;
             h->slot_dirty[i] = false;
         }
     if (first_bad_frame) *first_bad_frame = (bad == INT_MAX) ? -1 : bad;
@@ -1388,7 +1435,7 @@ int dtfill_debug_read_status(dtfill_t* h, int32_t* out, int n) {
     if (!h || !out || n < 0 || n > 64) return fail(DTFILL_E_ARG, "dtfill_debug_read_status: bad argument");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(out, h->lanes[h->last_lane].status.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, h->status_dev + (size_t)h->last_slot * dtfill_ctx::STATUS_STRIDE, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
