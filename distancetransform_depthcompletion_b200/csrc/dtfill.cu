@@ -394,6 +394,7 @@ struct dtfill_ctx {
                                   // 0.137 ms, 16 frames 0.222 -> 0.165, 256 frames 0.551 -> 0.536; the launch costs
                                   // 2 % on frames without such rows, 256 NYU frames 0.603 -> 0.616)
     int nsub = -1;                // -1: automatic
+    bool sky_split = true;        // strict order: k3_sky beside the narrow tiles (DTFILL_SKY_SPLIT=0: behind them)
     bool narrow_main = true;      // the half-width scan instance on the call's own stream, the full-width one on the side
                                   // stream (DTFILL_NARROW_MAIN=0: the other way round; strict step of 256 KITTI frames 0.536 -> 0.519)
     int band_cap = -1;            // -1: automatic (see enqueue); 0: never split frames; >0: task cost target in row steps
@@ -553,6 +554,11 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
     fp.narrow_ppl = (h->tiles2d && plan.ppl) ? plan.narrow : 0;
     fp.frame0 = b0;
     fp.sky_min = h->sky_min >= 0 ? h->sky_min : 8;
+    // strict order with two scan instances: k3_sky follows the full-width instance on the side stream (see the planner)
+    // -- while the scan leaves SMs idle: measured on KITTI frames, 4 / 16 / 32 / 64 frames per call -4 / -10 / -9 / -2 %,
+    // 128 / 256 frames +4 / +2 % (the wide instance then takes registers from the narrow tiles)
+    fp.sky_split = (h->sky_split && !h->cur_pipelined && !h->profiling && h->tiles2d && plan.ppl && plan.narrow &&
+                    h->narrow_main && fp.sky_min > 0 && W <= SKY_MAX_W && (long)Btot * H * W <= 28000000L) ? 1 : 0;
     fp.max_col_tiles = h->max_col_tiles;
     fp.mul_dist = 1u << (32 - DSH);
     fp.four = 4u;
@@ -669,6 +675,14 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
         k2_chamfer_wide<<<nb, 32, wide_smem, s_full>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
+    const bool run_sky = fp.band_cap > 0 && fp.sky_min > 0 && W <= SKY_MAX_W && !(h->debug_skip & 8);
+    bool sky_done = false;
+    if (two && narrow_main && fp.sky_split && run_sky) {
+        // the base rows of every frame come from the full-width instance just launched on the side stream
+        k3_sky<<<dim3(nb, (H + SKY_ROWS - 1) / SKY_ROWS), 256, 0, s_side>>>(fp, ws, od, odt, ol);
+        ++*launches;
+        sky_done = true;
+    }
     if (two) {
         CU(cudaEventRecord(L->side_join[sub_index], s_side));
         CU(cudaStreamWaitEvent(s, L->side_join[sub_index], 0));
@@ -681,7 +695,7 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
     }
     // rows above the first source row, from the two base rows the scan left in ws.skykeys (blocks of frames without
     // such rows return at once)
-    if (fp.band_cap > 0 && fp.sky_min > 0 && W <= SKY_MAX_W && !(h->debug_skip & 8)) {
+    if (run_sky && !sky_done) {
         k3_sky<<<dim3(nb, (H + SKY_ROWS - 1) / SKY_ROWS), 256, 0, s>>>(fp, ws, od, odt, ol);
         ++*launches;
     }
@@ -1002,6 +1016,7 @@ int dtfill_create(int device, dtfill_t** out_handle) {
     if (const char* e = getenv("DTFILL_SKY_MIN")) h->sky_min = atoi(e) < -1 ? -1 : atoi(e);
     if (const char* e = getenv("DTFILL_BAND_CAP")) h->band_cap = atoi(e);
     if (const char* e = getenv("DTFILL_NARROW_MAIN")) h->narrow_main = atoi(e) != 0;
+    if (const char* e = getenv("DTFILL_SKY_SPLIT")) h->sky_split = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_STAGE_THREADS")) h->stage_threads = atoi(e);
     if (const char* e = getenv("DTFILL_SPARSE_UPLOAD")) h->sparse_upload = atoi(e) != 0;
     if (const char* e = getenv("DTFILL_METRICS_EXACT")) h->metrics_exact = atoi(e) != 0;

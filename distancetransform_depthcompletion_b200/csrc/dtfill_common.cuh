@@ -57,6 +57,8 @@ struct FrameParams {
     int narrow_ppl;            // pixels per lane of the half-width instance, 0 if frames are never split in columns
     int max_col_tiles;         // planner: at most this many narrow tiles side by side (2..4)
     int sky_min;               // planner: least number of source-free top rows worth handing to k3_sky; 0 disables
+    int sky_split;             // planner: the band that feeds k3_sky (rows S..S+3) is a full-width task of its own, so that
+                               // k3_sky can follow the full-width launch on the side stream while the narrow tiles still run
     int frame0;                // index of this sub-batch's first frame in the caller's batch (error reporting)
     // Multipliers handed over at run time so that ptxas keeps the multiply-adds below on the FMA pipe instead of
     // strength-reducing them to shifts/LEAs on the ALU pipe, which is the pipe the scan kernel saturates.

@@ -281,6 +281,10 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
             while (cy < nh && ok) {
                 const int r0 = cy * CELL_H;
                 int lo = 1 << 30, hi = 0, prev = 0, end = cy, best_lo = 0, best_hi = 0, umax = 0, best_u = 0;
+                // strict order: the cell row that holds the base rows S, S+1 of k3_sky is a band (and a full-width task)
+                // of its own -- a short scan that the side stream finishes early, so that k3_sky's writes run beside
+                // the narrow tiles instead of behind them
+                const bool base_band = fp.sky_split && S > 0 && r0 == S;
                 for (int c = cy; c < nh; ++c) {
                     lo = min(lo, c * CELL_H - cellU[c]);
                     hi = max(hi, min(H, (c + 1) * CELL_H) + cellU[c]);
@@ -289,8 +293,8 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                     const int cst = (Hh - L) + (Hh - r0);
                     // extend while the tile stays under the target cost, while extending is (nearly) free, or while
                     // the band is still short compared with its halo (sparse frames: tall bands, less redundancy)
-                    const bool take = c == cy || nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H ||
-                                      (c - cy) * CELL_H < 2 * cellU[c];
+                    const bool take = c == cy || (!base_band && (nt >= MAXT - 4 || cst <= fp.band_cap || cst - prev <= CELL_H ||
+                                                                 (c - cy) * CELL_H < 2 * cellU[c]));
                     if (!take) break;
                     prev = cst; end = c + 1; best_lo = L; best_hi = Hh; best_u = umax;
                 }
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                 // n overlapping narrow tiles when the bound leaves every written pixel's ball inside its tile and the
                 // extra columns stay below ~60 % (n * nwid <= 1.6 W)
                 int ntile = 0;
-                if (nwid > 0 && W > nwid && (W & 3) == 0) {
+                if (nwid > 0 && W > nwid && (W & 3) == 0 && !base_band) {
                     for (int n = 2; n <= fp.max_col_tiles && !ntile; ++n) {
                         if (5 * n * nwid > 8 * W || nt + n > MAXT) break;
                         bool fits = true;                      // every interior tile edge at least best_u away
