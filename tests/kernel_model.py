@@ -121,15 +121,16 @@ def chamfer_band(src: np.ndarray, rank: np.ndarray, lo: int, hi: int, ppl: int):
 
 
 # ---- coarse planning bound (guaranteed upper bound on the row maximum of dt) --------------------------------
-def coarse_row_bound(src: np.ndarray, ch: int, cw: int, halves: bool = True) -> np.ndarray:
+def coarse_row_bound(src: np.ndarray, ch: int, cw: int, halves: bool = False) -> np.ndarray:
     """Upper bound U[y] >= max_x dt(y,x) from a CH x CW cell-occupancy grid: an exact anisotropic city-block
     distance on the cell grid (vertical step ch, horizontal step cw) plus the in-cell slack.
 
-    ``halves`` (what k1b_scan_compact does): K1 reports occupancy per HALF cell (cw/2 columns).  A cell whose two halves
+    ``halves`` (evaluated, NOT what k1b_scan_compact does -- see profiles/r02_experiments.txt): occupancy per HALF cell
+    (cw/2 columns).  A cell whose two halves
     both hold a source has a source column within cw/2 - 1 of every column of its own span, so a pixel k cells away
     horizontally is at most cw*k + cw/2 - 1 columns from one of its sources (instead of cw*k + cw - 1): such a cell
     starts the distance propagation at 0, a cell with one occupied half at cw/2, and the in-cell slack that is added at
-    the end is (ch - 1) + (cw/2 - 1).  In a densely sampled band this gives 10 where the plain bound gives 14."""
+    the end is (ch - 1) + (cw/2 - 1).  Valid, but a cell row's bound is the maximum over its cells and stays where it was."""
     H, W = src.shape
     nh, nw = -(-H // ch), -(-W // cw)
     BIG = 1 << 20
