@@ -351,3 +351,52 @@ def test_float64_and_integer_inputs_follow_the_reference(handle):
     gi = eval_nyu.Distance_Transform(yi)
     wi, _, _ = O.cv2_port_fill_frame(yi, 0.001, 0.1, nyu_style=True)
     assert gi.dtype == yi.dtype and np.array_equal(gi, wi)
+
+
+@pytest.mark.parametrize("batch", [1, 7, 64, 66])
+def test_strict_calls_on_both_sides_of_the_sky_split(handle, torch_mod, batch):
+    """Strict order, full-size KITTI frames: up to 64 frames per call the cell row with k3_sky's base rows is a full-width
+    task of its own and k3_sky runs beside the narrow tiles on the side stream; larger calls keep k3_sky behind the scan
+    (csrc/dtfill.cu, fp.sky_split).  Every frame of both kinds of call against the oracle, labels on and off, and the
+    task list shows which plan ran."""
+    torch = torch_mod
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    frames = np.stack([synth.kitti_frame(100 + i, beam_step=(1, 2, 1, 4)[i % 4]) for i in range(batch)])
+    want = O.dt_fill(frames)
+    eng = DTFillEngine(0)
+    x = torch.from_numpy(frames).cuda()
+    for want_lbl in (False, True):
+        out = eng.fill(x, want_lbl=want_lbl)
+        bad, _ = eng.status()
+        assert bad == -1
+        for k in ("depth", "dt", "mask") + (("lbl",) if want_lbl else ()):
+            assert np.array_equal(out[k].cpu().numpy(), want[k]), (batch, k)
+    t = eng.handle.debug_tasks(1 << 16)
+    kinds = t[:, 5]
+    full_width = int((kinds == 0).sum())
+    assert int((kinds == 4).sum()) > 0
+    assert (full_width >= batch) if batch <= 64 else (full_width == 0), (batch, full_width)
+
+
+def test_status_slots_are_rearmed_after_a_verdict(handle, torch_mod):
+    """The device side of a status slot is armed once and re-armed only after it reported something: more calls than the
+    ring has slots with a bad frame every 64th + 5th call, checked in groups -- a stale verdict would show up in a later
+    group, a missing re-arm as a verdict that never goes away."""
+    torch = torch_mod
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    eng = DTFillEngine(0)
+    good = torch.from_numpy(np.stack([synth.kitti_frame(i)[100:180, :320] for i in range(3)])).cuda()
+    badb = good.clone()
+    badb[1].zero_()
+    out = None
+    for group in range(5):
+        for i in range(40):
+            out = eng.fill(badb if (group % 2 == 0 and i == 5) else good, out=out)
+        bad, _ = eng.status()
+        assert bad == (1 if group % 2 == 0 else -1), group
+    for i in range(200):                                   # no status call in between: slots are reused three times
+        out = eng.fill(badb if i == 3 else good, out=out)
+    assert eng.status()[0] == 1
+    for i in range(70):
+        out = eng.fill(good, out=out)
+    assert eng.status()[0] == -1
