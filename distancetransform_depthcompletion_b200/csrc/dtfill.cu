@@ -578,7 +578,10 @@ int enqueue_range(dtfill_t* h, Lane* L, cudaStream_t s, cudaStream_t s_front, co
             else {
                 const long band_rows = (5L * H / 2) / per_frame;                       // ~2.5 tiles per band of rows
                 cap = (int)(2 * band_rows + 42);
-                if (cap < 96) cap = 96;
+                // (the floor: bands shorter than twice their halo are not cut anyway; measured on KITTI frames, 1 / 4 frames
+                // per call 0.129 -> 0.119 / 0.133 -> 0.126 ms with 80 instead of 96, 16 frames 0.144 -> 0.150)
+                const int floor_cap = Btot <= 8 ? 80 : 96;
+                if (cap < floor_cap) cap = floor_cap;
             }
         }
         fp.band_cap = plan.ppl ? cap : 0;
