@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
     __shared__ uint32_t sm[K1B_THREADS / 32 + 1];
     __shared__ uint16_t cellD[MAX_CELLS];        // planner: distance (pixels) to the nearest occupied cell
     __shared__ int cellU[1024];                  // planner: per cell-row upper bound of dt
-    __shared__ uint8_t occw[MAX_CELLS / 4 + 1024];   // planner: per cell-row and word, occupancy nibble
     __shared__ uint32_t srcrows[128];            // planner: bit y = row y holds a source (H <= 4096)
     __shared__ Task st[MAXT];                    // planner: tasks of this frame before ordering
     __shared__ int scost[MAXT];
@@ -141,32 +140,31 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         // coarse occupancy -> exact anisotropic city-block distance on the cell grid (two sweeps per axis)
         // rowcell nibbles of CELL_H consecutive rows OR-ed per word, then one distance cell per bit
         const uint8_t* rc = ws.rowcell + (long)b * H * WW;
-        for (int i0 = c0row * WW; i0 < nh * WW; i0 += 256 * 8) {  // 32 independent byte loads in flight per thread
-            uint32_t o[8];
+        // one warp per cell row, two cell rows per turn, a lane per word: the CELL_H rows' nibbles OR-ed and expanded
+        // into the word's four distance cells at once (no index division, 8 byte loads in flight per lane)
+        for (int cy0 = c0row + pw; cy0 < nh; cy0 += 16) {
+            for (int w0 = 0; w0 < WW; w0 += 32) {
+                const int w = w0 + lane;
+                uint32_t o[2] = {0u, 0u};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * 256 + ptid;
-                o[k] = 0;
-                if (i < nh * WW) {
-                    const int cy = i / WW, w = i - cy * WW;
+                for (int t = 0; t < 2; ++t) {
+                    const int cy = cy0 + 8 * t;
 #pragma unroll
                     for (int r = 0; r < CELL_H; ++r) {
                         const int y = cy * CELL_H + r;
-                        if (y < H) o[k] |= rc[(long)y * WW + w];
+                        if (cy < nh && y < H && w < WW) o[t] |= rc[(long)y * WW + w];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int cy = cy0 + 8 * t;
+                    if (cy < nh && w < WW) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (4 * w + j < nw) cellD[cy * nw + 4 * w + j] = ((o[t] >> j) & 1u) ? 0 : 60000;
                     }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * 256 + ptid;
-                if (i < nh * WW) occw[i] = (uint8_t)o[k];
-            }
-        }
-        planner_sync();
-        dbg_mark(1);
-        for (int i = c0row * nw + ptid; i < nh * nw; i += 256) {
-            const int cy = i / nw, cx = i - cy * nw;
-            cellD[i] = ((occw[cy * WW + (cx >> 2)] >> (cx & 3)) & 1u) ? 0 : 60000;
         }
         planner_sync();
         dbg_mark(2);
@@ -200,45 +198,72 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
         // (min,+) scans across lanes via shuffles; only the row maximum leaves the warp
         const int chunk = (nw + 31) / 32;
         if (chunk <= 8) {
-            for (int cy = c0row + pw; cy < nh; cy += 8) {
-                const uint16_t* rowp = cellD + cy * nw;
+            // two cell rows per warp and turn, their (independent) chains interleaved
+            for (int cy0 = c0row + pw; cy0 < nh; cy0 += 16) {
                 const int xa = lane * chunk;
-                uint32_t v[8];
+                uint32_t v[2][8], d[2], e[2], mx[2];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = (k < chunk && xa + k < nw) ? (uint32_t)rowp[xa + k] : 120000u;
+                for (int t = 0; t < 2; ++t) {
+                    const int cy = cy0 + 8 * t;
+                    const uint16_t* rowp = cellD + (cy < nh ? cy : cy0) * nw;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[t][k] = (k < chunk && xa + k < nw) ? (uint32_t)rowp[xa + k] : 120000u;
+                }
                 // left -> right
-                uint32_t d = 120000u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) if (k < chunk) d = min(d + CELL_W, v[k]);
-                uint32_t e = d;
+                for (int t = 0; t < 2; ++t) {
+                    d[t] = 120000u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (k < chunk) d[t] = min(d[t] + CELL_W, v[t][k]);
+                    e[t] = d[t];
+                }
 #pragma unroll
                 for (int s_ = 1; s_ < 32; s_ <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, e, s_);
-                    if (lane >= s_) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, e[t], s_);
+                        if (lane >= s_) e[t] = min(e[t], o + (uint32_t)(s_ * chunk * CELL_W));
+                    }
                 }
-                uint32_t cin = __shfl_up_sync(0xffffffffu, e, 1);
-                d = lane == 0 ? 120000u : cin;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) if (k < chunk) { d = min(d + CELL_W, v[k]); v[k] = d; }
-                // right -> left
-                d = 120000u;
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t cin = __shfl_up_sync(0xffffffffu, e[t], 1);
+                    d[t] = lane == 0 ? 120000u : cin;
 #pragma unroll
-                for (int k = 7; k >= 0; --k) if (k < chunk) d = min(d + CELL_W, v[k]);
-                e = d;
+                    for (int k = 0; k < 8; ++k) if (k < chunk) { d[t] = min(d[t] + CELL_W, v[t][k]); v[t][k] = d[t]; }
+                    // right -> left
+                    d[t] = 120000u;
+#pragma unroll
+                    for (int k = 7; k >= 0; --k) if (k < chunk) d[t] = min(d[t] + CELL_W, v[t][k]);
+                    e[t] = d[t];
+                }
 #pragma unroll
                 for (int s_ = 1; s_ < 32; s_ <<= 1) {
-                    const uint32_t o = __shfl_down_sync(0xffffffffu, e, s_);
-                    if (lane + s_ < 32) e = min(e, o + (uint32_t)(s_ * chunk * CELL_W));
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t o = __shfl_down_sync(0xffffffffu, e[t], s_);
+                        if (lane + s_ < 32) e[t] = min(e[t], o + (uint32_t)(s_ * chunk * CELL_W));
+                    }
                 }
-                cin = __shfl_down_sync(0xffffffffu, e, 1);
-                d = lane == 31 ? 120000u : cin;
-                uint32_t mx = 0;
 #pragma unroll
-                for (int k = 7; k >= 0; --k)
-                    if (k < chunk) { d = min(d + CELL_W, v[k]); if (xa + k < nw) mx = max(mx, d); }
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t cin = __shfl_down_sync(0xffffffffu, e[t], 1);
+                    d[t] = lane == 31 ? 120000u : cin;
+                    mx[t] = 0;
 #pragma unroll
-                for (int s_ = 16; s_ > 0; s_ >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s_));
-                if (lane == 0) cellU[cy] = (int)min(mx, 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
+                    for (int k = 7; k >= 0; --k)
+                        if (k < chunk) { d[t] = min(d[t] + CELL_W, v[t][k]); if (xa + k < nw) mx[t] = max(mx[t], d[t]); }
+                }
+#pragma unroll
+                for (int s_ = 16; s_ > 0; s_ >>= 1) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) mx[t] = max(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], s_));
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int cy = cy0 + 8 * t;
+                    if (lane == 0 && cy < nh) cellU[cy] = (int)min(mx[t], 60000u) + (CELL_H - 1) + (CELL_W - 1);   // >= max dt of the cell row
+                }
             }
         } else {
             for (int cy = c0row + pw * 32 + lane; cy < nh; cy += 256) {      // very wide frames: one thread per cell row
