@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                         bool fits = true;                      // every interior tile edge at least best_u away
                         int prev_split = 0;
                         for (int k = 0; k < n && fits; ++k) {
-                            const int s0 = (int)(((long)(W - nwid) * k / (n - 1)) & ~3L);
-                            const int s1 = (int)(((long)(W - nwid) * (k + 1) / (n - 1)) & ~3L);
+                            const int s0 = (((W - nwid) * k / (n - 1)) & ~3);
+                            const int s1 = (((W - nwid) * (k + 1) / (n - 1)) & ~3);
                             const int split = k == n - 1 ? W : ((s1 + s0 + nwid) / 2) & ~3;
                             if ((k > 0 && prev_split - s0 < best_u) || (k < n - 1 && s0 + nwid - split < best_u) ||
                                 split <= prev_split) fits = false;
@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(K1B_THREADS) k1b_scan_compact(FrameParams fp, 
                     q.kind = TASK_NARROW;
                     int prev_split = 0;
                     for (int k = 0; k < ntile; ++k) {
-                        const int s0 = (int)(((long)(W - nwid) * k / (ntile - 1)) & ~3L);           // sub-image start
-                        const int s1 = (int)(((long)(W - nwid) * (k + 1) / (ntile - 1)) & ~3L);     // next tile's start
+                        const int s0 = (((W - nwid) * k / (ntile - 1)) & ~3);           // sub-image start
+                        const int s1 = (((W - nwid) * (k + 1) / (ntile - 1)) & ~3);     // next tile's start
                         const int split = k == ntile - 1 ? W : ((s1 + s0 + nwid) / 2) & ~3;        // middle of the overlap
                         q.clo = s0; q.c0 = prev_split; q.c1 = split; q.scratch_off = scr;
                         // halo check (the sizes above guarantee it; keep the planner honest)
