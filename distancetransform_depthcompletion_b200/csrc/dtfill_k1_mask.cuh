@@ -20,6 +20,15 @@ __device__ __forceinline__ uint32_t sign_nibble(float t0, float t1, float t2, fl
     const uint32_t w = __byte_perm(p01, p23, 0x5410) & 0x80808080u;
     return (w * 0x00204081u) >> 28;
 }
+// the same, and the four sign bits as bytes 0/1 (the validity mask's bytes: one shift instead of nibble -> multiply -> and)
+__device__ __forceinline__ uint32_t sign_nibble_bytes(float t0, float t1, float t2, float t3, uint32_t& bytes01)
+{
+    const uint32_t p01 = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0073);
+    const uint32_t p23 = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0073);
+    const uint32_t w = __byte_perm(p01, p23, 0x5410) & 0x80808080u;
+    bytes01 = w >> 7;
+    return (w * 0x00204081u) >> 28;
+}
 
 // W16: W % 16 == 0 (KITTI 1216, NYU 640): a lane's 16 pixels are inside the row or outside it as a whole.
 template <typename T, bool W16>
@@ -65,6 +74,7 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
                                      __float_as_uint(q[g].z), __float_as_uint(q[g].w));
             }
             uint32_t sb = 0, vb = 0;
+            uint32_t m[4];                                   // validity mask bytes of the lane's 16 pixels
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 // tools.py:8: source <=> !(float32(1 - x) > src_thr) <=> !(x < src_cut), src_cut being the smallest
@@ -72,8 +82,8 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
                 // tools.py:22: valid <=> x > val_thr
                 const uint32_t ns = sign_nibble(__fsub_rn(q[g].x, scut), __fsub_rn(q[g].y, scut), __fsub_rn(q[g].z, scut),
                                                 __fsub_rn(q[g].w, scut));                   // bit = x < src_cut
-                const uint32_t nv = sign_nibble(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
-                                                __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w));
+                const uint32_t nv = sign_nibble_bytes(__fsub_rn(vthr, q[g].x), __fsub_rn(vthr, q[g].y),
+                                                      __fsub_rn(vthr, q[g].z), __fsub_rn(vthr, q[g].w), m[g]);
                 sb |= ns << (4 * g);
                 vb |= nv << (4 * g);
             }
@@ -82,9 +92,10 @@ __global__ void __launch_bounds__(256) k1_mask_rows_v16(const T* __restrict__ in
             sb = ~sb & inb;
             vb &= inb;
             if (out_mask && col < W) {
-                uint32_t m[4];
+                if (!W16) {                                  // pixels beyond the row's end are not valid
 #pragma unroll
-                for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                    for (int g = 0; g < 4; ++g) m[g] = (((vb >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                }
                 uint8_t* mp = out_mask + row * W + col;
                 if (W16) {
                     st_stream_v4(mp, m[0], m[1], m[2], m[3]);
