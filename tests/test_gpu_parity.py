@@ -552,3 +552,41 @@ def test_pipelined_random_shapes_against_oracle(handle):
                 assert np.array_equal(o["depth"].cpu().numpy().view(np.uint32), want["depth"].view(np.uint32)), x_.shape
                 assert np.array_equal(o["mask"].cpu().numpy(), want["mask"]), x_.shape
             pending = []
+
+
+@pytest.mark.gpu
+def test_strict_random_shapes_with_two_scan_instances(handle):
+    """Strict order on frames wide enough for both scan instances (half-width tiles on the call's stream, full-width tasks
+    and -- for small calls -- k3_sky on the side stream): random sizes, widths that are and are not multiples of 4 or 16,
+    densities from a few sources to dense, source-free tops of any height, 1..12 frames per call, the automatic band
+    target and small explicit ones, labels on and off.  Every output against the oracle."""
+    import torch
+    from distancetransform_depthcompletion_b200.engine import DTFillEngine
+    rng = np.random.default_rng(77)
+    eng = DTFillEngine(0)
+    split_seen = False
+    try:
+        for t in range(30):
+            H, W = int(rng.integers(24, 353)), int(rng.integers(660, 1217))
+            if t % 3:
+                W = (W // 16) * 16 if t % 3 == 1 else (W // 4) * 4
+            B = int(rng.integers(1, 13))
+            dens = float(rng.choice([0.002, 0.02, 0.05, 0.3]))
+            top = int(rng.integers(0, H - 10))
+            x = ((rng.random((B, H, W)) < dens) * rng.uniform(1, 60, (B, H, W))).astype(np.float32)
+            x[:, :top] = 0
+            x[:, top, rng.integers(0, W)] = 4.0
+            if t % 5 == 0:
+                x[0, top + 1:] = 0                      # a frame with one source in all
+            eng.handle.set_band_cap(int(rng.choice([-1, -1, 40, 64, 120])))
+            want_lbl = bool(t % 2)
+            o = eng.fill(torch.from_numpy(x).cuda(), want_lbl=want_lbl)
+            assert eng.status()[0] == -1
+            want = O.dt_fill(x, 0.1, 0.1)
+            for k in ("depth", "dt", "mask") + (("lbl",) if want_lbl else ()):
+                assert np.array_equal(o[k].cpu().numpy(), want[k]), (t, x.shape, k)
+            tk = eng.handle.debug_tasks(1 << 16)
+            split_seen |= bool(((tk[:, 5] == 0) & (tk[:, 11] >= 8)).any() and (tk[:, 5] == 4).any())
+    finally:
+        eng.handle.set_band_cap(-1)
+    assert split_seen, "some call must have run k3_sky's base rows as a full-width task next to half-width tiles"
